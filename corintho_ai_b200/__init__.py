@@ -1,0 +1,316 @@
+"""corintho_ai_b200 -- host-side mirror of the reference's self-play interface over the
+B200 engine (libcorintho_b200.so, C ABI in include/corintho_b200.h).
+
+The class :class:`Trainer` has the member names, argument meaning and call protocol of the
+reference's C++ ``Trainer`` (corintho_ai/cpp/include/trainer.h:17-53) as bound by its Cython
+layer (corintho_ai/python/main.pyx:17-38): ``doIteration / num_requests / writeRequests /
+writeSamples / num_samples / score / avg_mate_length / writeScores``. There is no CPU
+fallback: importing works anywhere, but every compute call raises ``Corintho200Error`` unless
+the CUDA library is built and a B200-class GPU is usable.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["Trainer", "Corintho200Error", "game_step", "lib", "build", "NUM_MOVES", "STATE_SIZE",
+           "WEIGHT_FLOATS", "planes_from_reference_order", "reference_order_from_planes",
+           "random_weights", "fold_batchnorm"]
+
+NUM_MOVES = 96      # util.h:43
+STATE_SIZE = 70     # util.h:41
+NUM_SYMMETRIES = 8  # util.h:47
+WEIGHT_FLOATS = 127997
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcorintho_b200.so")
+
+
+class Corintho200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libcorintho_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise Corintho200Error("building libcorintho_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load the CUDA library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Corintho200Error(
+            f"{LIB_PATH} is missing: the CUDA extension is not built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
+    sig = {
+        "cb200_last_error": (C.c_char_p, []),
+        "cb200_device_count": (i32, []),
+        "cb200_set_device": (i32, [i32]),
+        "cb200_set_stream": (i32, [vp]),
+        "cb200_launch_count": (i64, []),
+        "cb200_game_step": (i32, [i64, vp, u64, vp, vp, vp]),
+        "cb200_game_step_device": (i32, [i64, vp, u64, vp, vp, vp]),
+        "cb200_trainer_create": (vp, [i32, C.c_char_p, i32, i32, i32, f32, f32, i32, i32, i32]),
+        "cb200_trainer_create_shard": (vp, [i32, i32, i32, C.c_char_p, i32, i32, i32, f32, f32,
+                                            i32, i32]),
+        "cb200_trainer_destroy": (None, [vp]),
+        "cb200_trainer_do_iteration": (i32, [vp, vp, vp, i32]),
+        "cb200_trainer_num_requests": (i32, [vp, i32]),
+        "cb200_trainer_write_requests": (i32, [vp, vp, i32]),
+        "cb200_trainer_num_samples": (i32, [vp]),
+        "cb200_trainer_write_samples": (i32, [vp, vp, vp, vp]),
+        "cb200_trainer_score": (f32, [vp]),
+        "cb200_trainer_avg_mate_length": (f32, [vp]),
+        "cb200_trainer_write_scores": (i32, [vp, C.c_char_p]),
+        "cb200_trainer_counters": (i32, [vp, vp]),
+        "cb200_trainer_write_raw_samples": (i32, [vp, vp, vp, vp, vp]),
+        "cb200_trainer_game_results": (i32, [vp, vp]),
+        "cb200_trainer_set_weights": (i32, [vp, i32, vp, C.c_size_t, i32]),
+        "cb200_trainer_evaluate": (i32, [vp, i32, i32, vp, vp, vp]),
+        "cb200_trainer_run_selfplay": (i32, [vp, i32, i32]),
+        "cb200_trainer_dump_tree": (i32, [vp, i32, i32, vp, vp, i32]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise Corintho200Error(f"corintho_b200 error {rc}: {lib().cb200_last_error().decode()}")
+    return rc
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+# ---- packed state helpers -----------------------------------------------------------------
+def planes_from_reference_order(states):
+    """[n,2] u64 with board bit row*16+col*4+t (reference Game::board_ order) -> cstate planes."""
+    st = np.ascontiguousarray(states, np.uint64).reshape(-1, 2)
+    w0 = st[:, 0]
+    out = np.zeros_like(w0)
+    for s in range(16):
+        for t in range(4):
+            out |= ((w0 >> np.uint64(4 * s + t)) & np.uint64(1)) << np.uint64(16 * t + s)
+    return np.ascontiguousarray(np.stack([out, st[:, 1]], 1))
+
+
+def reference_order_from_planes(states):
+    st = np.ascontiguousarray(states, np.uint64).reshape(-1, 2)
+    w0 = st[:, 0]
+    out = np.zeros_like(w0)
+    for s in range(16):
+        for t in range(4):
+            out |= ((w0 >> np.uint64(16 * t + s)) & np.uint64(1)) << np.uint64(4 * s + t)
+    return np.ascontiguousarray(np.stack([out, st[:, 1]], 1))
+
+
+def game_step(states, seed=0, want_encoding=False):
+    """Game-logic step on host arrays of cstates -> (mask_flags[n,4] u32, next[n,2] u64, enc)."""
+    st = np.ascontiguousarray(states, np.uint64).reshape(-1, 2)
+    n = st.shape[0]
+    mf = np.zeros((n, 4), np.uint32)
+    nx = np.zeros((n, 2), np.uint64)
+    enc = np.zeros((n, STATE_SIZE), np.float32) if want_encoding else None
+    _check(lib().cb200_game_step(n, _ptr(st), seed, _ptr(mf), _ptr(nx), _ptr(enc)))
+    return mf, nx, enc
+
+
+# ---- network weights ----------------------------------------------------------------------
+def random_weights(seed=0):
+    """Random-init network of the reference architecture (wrapper.py:256-271): Glorot-uniform
+    Dense kernels, zero biases, BatchNorm at its initial state (gamma 1, beta 0, mean 0, var 1,
+    eps 1e-3). Returns the *unfolded* parameter dict; see fold_batchnorm()."""
+    rng = np.random.default_rng(seed)
+    dims = [STATE_SIZE] + [100] * 12
+    layers = []
+    for i in range(12):
+        fan_in, fan_out = dims[i], dims[i + 1]
+        lim = np.sqrt(6.0 / (fan_in + fan_out))
+        layers.append({
+            "W": rng.uniform(-lim, lim, size=(fan_in, fan_out)).astype(np.float32),
+            "b": np.zeros(fan_out, np.float32),
+            "gamma": np.ones(fan_out, np.float32), "beta": np.zeros(fan_out, np.float32),
+            "mean": np.zeros(fan_out, np.float32), "var": np.ones(fan_out, np.float32),
+        })
+    lim_v, lim_p = np.sqrt(6.0 / (100 + 1)), np.sqrt(6.0 / (100 + NUM_MOVES))
+    head = {
+        "Wv": rng.uniform(-lim_v, lim_v, size=(100, 1)).astype(np.float32),
+        "bv": np.zeros(1, np.float32),
+        "Wp": rng.uniform(-lim_p, lim_p, size=(100, NUM_MOVES)).astype(np.float32),
+        "bp": np.zeros(NUM_MOVES, np.float32),
+    }
+    return {"layers": layers, "head": head}
+
+
+def fold_batchnorm(params, eps=1e-3):
+    """Fold each inference-time BatchNormalization (which FOLLOWS the ReLU, wrapper.py:259-266)
+    into the next Dense and flatten to the C-ABI weight vector (127997 floats, fp32):
+    y = relu(xW+b); z = s*y + t with s = gamma/sqrt(var+eps), t = beta - mean*s;
+    next Dense: zW' + b' = y (diag(s) W') + (t W' + b')."""
+    out = []
+    s = np.ones(STATE_SIZE, np.float64)
+    t = np.zeros(STATE_SIZE, np.float64)
+    for L in params["layers"]:
+        W = L["W"].astype(np.float64)
+        b = L["b"].astype(np.float64)
+        out.append((s[:, None] * W).astype(np.float32).ravel())
+        out.append((t @ W + b).astype(np.float32))
+        s = L["gamma"].astype(np.float64) / np.sqrt(L["var"].astype(np.float64) + eps)
+        t = L["beta"].astype(np.float64) - L["mean"].astype(np.float64) * s
+    H = params["head"]
+    Wh = np.concatenate([H["Wv"], H["Wp"]], 1).astype(np.float64)
+    bh = np.concatenate([H["bv"], H["bp"]]).astype(np.float64)
+    out.append((s[:, None] * Wh).astype(np.float32).ravel())
+    out.append((t @ Wh + bh).astype(np.float32))
+    flat = np.concatenate(out).astype(np.float32)
+    assert flat.size == WEIGHT_FLOATS, flat.size
+    return flat
+
+
+class Trainer:
+    """Drop-in for the reference ``Trainer`` (trainer.h:17-53) on one GPU.
+
+    Reference-named methods (camelCase, as in the Cython binding) and snake_case aliases are
+    both provided. numpy float32 buffers are passed as raw pointers exactly like
+    main.pyx:132-165 does.
+    """
+
+    def __init__(self, num_games, log_folder="", seed=0, max_searches=1600, searches_per_eval=16,
+                 c_puct=1.0, epsilon=0.25, num_logged=0, num_threads=1, testing=False,
+                 total_games=None, first_game=0):
+        L = lib()
+        self.num_games = int(num_games)
+        self.spe = int(searches_per_eval)
+        self.max_searches = int(max_searches)
+        self.testing = bool(testing)
+        if total_games is None:
+            h = L.cb200_trainer_create(num_games, log_folder.encode(), seed, max_searches,
+                                       searches_per_eval, c_puct, epsilon, num_logged,
+                                       num_threads, int(testing))
+        else:
+            h = L.cb200_trainer_create_shard(total_games, first_game, num_games,
+                                             log_folder.encode(), seed, max_searches,
+                                             searches_per_eval, c_puct, epsilon, num_logged,
+                                             int(testing))
+        if not h:
+            raise Corintho200Error("Trainer: " + L.cb200_last_error().decode())
+        self._h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cb200_trainer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference API ------------------------------------------------------------------
+    def doIteration(self, evaluations=None, probabilities=None, to_play=-1):
+        return bool(_check(lib().cb200_trainer_do_iteration(
+            self._h, _ptr(evaluations), _ptr(probabilities), to_play)))
+
+    def num_requests(self, to_play=-1):
+        return _check(lib().cb200_trainer_num_requests(self._h, to_play))
+
+    def writeRequests(self, game_states, to_play=-1):
+        _check(lib().cb200_trainer_write_requests(self._h, _ptr(game_states), to_play))
+
+    def num_samples(self):
+        return _check(lib().cb200_trainer_num_samples(self._h))
+
+    def writeSamples(self, game_states, eval_samples, prob_samples):
+        _check(lib().cb200_trainer_write_samples(self._h, _ptr(game_states), _ptr(eval_samples),
+                                                 _ptr(prob_samples)))
+
+    def score(self):
+        return np.float32(lib().cb200_trainer_score(self._h))
+
+    def avg_mate_length(self):
+        return np.float32(lib().cb200_trainer_avg_mate_length(self._h))
+
+    def writeScores(self, file):
+        _check(lib().cb200_trainer_write_scores(self._h, str(file).encode()))
+
+    # ---- snake_case conveniences returning fresh arrays (what the test drivers call) ------
+    def do_iteration(self, evals=None, probs=None, to_play=-1):
+        return self.doIteration(evals, probs, to_play)
+
+    def write_requests(self, to_play=-1):
+        n = self.num_requests(to_play)
+        out = np.zeros((max(n, 1), STATE_SIZE), np.float32)
+        if n:
+            self.writeRequests(out, to_play)
+        return out[:n]
+
+    def write_samples(self):
+        n = self.num_samples()
+        gs = np.zeros((max(n, 1) * 8, STATE_SIZE), np.float32)
+        ev = np.zeros(max(n, 1) * 8, np.float32)
+        pr = np.zeros((max(n, 1) * 8, NUM_MOVES), np.float32)
+        if n:
+            self.writeSamples(gs, ev, pr)
+        return gs[:n * 8], ev[:n * 8], pr[:n * 8]
+
+    # ---- engine-only ------------------------------------------------------------------------
+    def counters(self):
+        out = np.zeros(4, np.int64)
+        _check(lib().cb200_trainer_counters(self._h, _ptr(out)))
+        return {"simulations": int(out[0]), "moves": int(out[1]), "leaf_evals": int(out[2]),
+                "iterations": int(out[3])}
+
+    def set_weights(self, flat_weights, model=0, precision="fp32"):
+        w = np.ascontiguousarray(flat_weights, np.float32)
+        prec = {"fp32": 0, "bf16": 1}[precision]
+        _check(lib().cb200_trainer_set_weights(self._h, model, _ptr(w), w.size, prec))
+
+    def evaluate(self, game_states, model=0):
+        gs = np.ascontiguousarray(game_states, np.float32).reshape(-1, STATE_SIZE)
+        n = gs.shape[0]
+        ev = np.zeros(n, np.float32)
+        pr = np.zeros((n, NUM_MOVES), np.float32)
+        _check(lib().cb200_trainer_evaluate(self._h, model, n, _ptr(gs), _ptr(ev), _ptr(pr)))
+        return ev, pr
+
+    def run_selfplay(self, max_iterations=0, stagger=False):
+        return bool(_check(lib().cb200_trainer_run_selfplay(self._h, max_iterations, int(stagger))))
+
+    def raw_samples(self):
+        n = self.num_samples()
+        st = np.zeros((max(n, 1), 2), np.uint64)
+        pr = np.zeros((max(n, 1), NUM_MOVES), np.float32)
+        lb = np.zeros(max(n, 1), np.float32)
+        go = np.zeros(max(n, 1), np.int32)
+        _check(lib().cb200_trainer_write_raw_samples(self._h, _ptr(st), _ptr(pr), _ptr(lb), _ptr(go)))
+        return st[:n], pr[:n], lb[:n], go[:n]
+
+    def game_results(self):
+        out = np.zeros(self.num_games, np.int32)
+        _check(lib().cb200_trainer_game_results(self._h, _ptr(out)))
+        return out
+
+    def dump_tree(self, game, player, cap=1 << 22):
+        out = np.zeros(8, np.int64)
+        words = np.zeros(cap, np.uint32)
+        used = _check(lib().cb200_trainer_dump_tree(self._h, game, player, _ptr(out), _ptr(words), cap))
+        return out, words[:min(used, cap)]

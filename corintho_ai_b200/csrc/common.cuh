@@ -1,0 +1,76 @@
+// Shared host/device plumbing of libcorintho_b200.so (single translation unit: engine.cu).
+#ifndef CORINTHO_B200_COMMON_CUH
+#define CORINTHO_B200_COMMON_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/corintho_b200.h"
+#include "corintho_tables.h"
+#include "rules.cuh"
+
+namespace cb200 {
+
+// ---- error plumbing (never throw across the C ABI) ------------------------------------------
+inline std::string &last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline int set_error(int code, const std::string &msg) {
+  last_error_ref() = msg;
+  return code;
+}
+#define CB_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      return cb200::set_error(CB200_ERR_CUDA, std::string(#expr) + ": " +                   \
+                                                  cudaGetErrorString(_e));                  \
+    }                                                                                       \
+  } while (0)
+
+struct Globals {
+  cudaStream_t stream = nullptr;
+  std::atomic<int64_t> launches{0};
+  bool tables_ready[16] = {false};
+};
+inline Globals &G() {
+  static Globals g;
+  return g;
+}
+#define CB_LAUNCHED() (cb200::G().launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---- device-resident rule data (uploaded once per device by ensure_tables) ------------------
+// line-breaker masks padded to 4 words so one 128-bit load fetches a mask
+__device__ uint32_t d_line_breakers[102 * 4];
+__device__ float d_gamma[1024];
+
+struct DeviceLB {
+  __device__ __forceinline__ const uint32_t *operator()(int idx) const {
+    return d_line_breakers + 4 * idx;
+  }
+};
+
+inline int ensure_tables() {
+  int dev = 0;
+  CB_CUDA(cudaGetDevice(&dev));
+  if (dev < 16 && G().tables_ready[dev]) return CB200_OK;
+  static uint32_t lb[102 * 4];
+  for (int i = 0; i < 102; ++i) {
+    lb[4 * i] = kCLineBreakers[i][0], lb[4 * i + 1] = kCLineBreakers[i][1];
+    lb[4 * i + 2] = kCLineBreakers[i][2], lb[4 * i + 3] = 0;
+  }
+  CB_CUDA(cudaMemcpyToSymbol(d_line_breakers, lb, sizeof(lb)));
+  CB_CUDA(cudaMemcpyToSymbol(d_gamma, kCGammaBits, sizeof(kCGammaBits)));
+  if (dev < 16) G().tables_ready[dev] = true;
+  return CB200_OK;
+}
+
+constexpr unsigned kFull = 0xffffffffu;
+
+}  // namespace cb200
+#endif

@@ -1,0 +1,673 @@
+// libcorintho_b200.so -- host side of the B200 self-play engine and its C ABI
+// (include/corintho_b200.h). Mirrors the reference Trainer (corintho_ai/cpp/src/trainer.cpp)
+// call for call; all game state lives in HBM and every step of the path is a CUDA kernel.
+// There is deliberately no CPU implementation of the path in this library.
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "game_step.cuh"
+#include "mlp.cuh"
+#include "mlp_tc.cuh"
+#include "tree.cuh"
+
+using namespace cb200;
+
+namespace cb200 {
+
+__device__ uint8_t d_space_sym[8 * 16];
+__device__ uint8_t d_move_sym[8 * 96];
+
+// SelfPlayer::writeSamples (selfplayer.cpp:79-113): 8 symmetries per stored sample.
+// One warp per (game, sample); soff[g] = index of game g's first sample row.
+__global__ void __launch_bounds__(256)
+    k_write_samples(TreeParams P, const int32_t *__restrict__ soff, float *__restrict__ gs_out,
+                    float *__restrict__ ev_out, float *__restrict__ pr_out) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int g = w / kMaxSamples, i = w - g * kMaxSamples;
+  if (g >= P.num_games) return;
+  const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+  const int ns = ctl[CW_N_SAMPLES];
+  if (i >= ns) return;
+  const ulonglong2 sv = P.sample_state[(size_t)g * kMaxSamples + i];
+  const CState st{sv.x, sv.y};
+  const float *pr = P.sample_probs + ((size_t)g * kMaxSamples + i) * CB200_NUM_MOVES;
+  float ev = ctl[CW_RESULT] == kResultDraw ? 0.0f : 1.0f;
+  if ((ns - 1 - i) & 1) ev = -ev;  // evaluation *= -1.0 per step back from the last move
+  const size_t row = ((size_t)soff[g] + i) * 8;
+  for (int k = 0; k < 8; ++k) {
+    float *go = gs_out + (row + k) * CB200_STATE_SIZE;
+    for (int j = lane; j < CB200_STATE_SIZE; j += 32) {
+      const int src = j < 64 ? d_space_sym[k * 16 + (j >> 2)] * 4 + (j & 3) : j;
+      go[j] = encode_elem(st, src);
+    }
+    if (lane == 0) ev_out[row + k] = ev;
+    float *po = pr_out + (row + k) * CB200_NUM_MOVES;
+    for (int j = lane; j < CB200_NUM_MOVES; j += 32) po[j] = pr[d_move_sym[k * 96 + j]];
+  }
+}
+
+}  // namespace cb200
+
+// ==============================================================================================
+struct cb200_trainer {
+  int device = 0;
+  TreeParams P{};
+  int iterations_done = 0;
+  int stagger_div = 1;
+  std::string log_folder;
+  size_t cap = 0;  // num_games * spe request rows
+  float *d_eval = nullptr, *d_probs = nullptr, *d_rows = nullptr;
+  ulonglong2 *d_packed = nullptr;
+  int32_t *d_offs = nullptr, *d_summary = nullptr, *d_soff = nullptr;
+  int32_t *h_summary = nullptr;  // pinned
+  NetF32 net32[2];
+  NetTC nettc[2];
+  int precision[2] = {-1, -1};
+  int last_to_play_scanned = -2;
+  std::vector<int32_t> h_ctl;
+};
+
+namespace {
+
+uint32_t mt_seed_word(uint32_t prev, int i) { return 1812433253u * (prev ^ (prev >> 30)) + i; }
+
+struct HostMT {
+  uint32_t mt[624];
+  int idx = 624;
+  void seed(uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = mt_seed_word(mt[i - 1], i);
+    idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+
+int upload_tables_once() {
+  int rc = ensure_tables();
+  if (rc != CB200_OK) return rc;
+  static bool sym_ready[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 16 && sym_ready[dev]) return CB200_OK;
+  CB_CUDA(cudaMemcpyToSymbol(d_space_sym, kCSpaceSym, sizeof(kCSpaceSym)));
+  CB_CUDA(cudaMemcpyToSymbol(d_move_sym, kCMoveSym, sizeof(kCMoveSym)));
+  if (dev < 16) sym_ready[dev] = true;
+  return CB200_OK;
+}
+
+template <class T>
+int dmalloc(T **p, size_t count) {
+  CB_CUDA(cudaMalloc((void **)p, count * sizeof(T)));
+  return CB200_OK;
+}
+
+int scan(cb200_trainer *t, int to_play) {
+  k_scan_requests<<<1, 1024, 0, G().stream>>>(t->P, to_play, t->d_offs, t->d_summary);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  return CB200_OK;
+}
+
+int fetch_summary(cb200_trainer *t) {
+  CB_CUDA(cudaMemcpyAsync(t->h_summary, t->d_summary, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                          G().stream));
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  if (t->h_summary[2] != 0)
+    return set_error(t->h_summary[2],
+                     "a game overflowed its node arena / path / sample buffer (raise "
+                     "CB200_ARENA_NODES) or reached an impossible state");
+  return CB200_OK;
+}
+
+int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_play) {
+  const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
+  k_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, t->d_offs, to_play,
+                                                       t->iterations_done, t->stagger_div);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  if (to_play != 0 && to_play != 1) ++t->iterations_done;
+  return CB200_OK;
+}
+
+int pack(cb200_trainer *t, int to_play, float *d_rows, ulonglong2 *d_packed) {
+  const int grid = (t->P.num_games + 7) / 8;
+  k_pack_requests<<<grid, 256, 0, G().stream>>>(t->P, to_play, t->d_offs, d_rows, d_packed);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  return CB200_OK;
+}
+
+int run_net(cb200_trainer *t, int model, const ulonglong2 *d_states, const int32_t *d_n,
+            int n_static, int n_max) {
+  if (t->precision[model] == 0)
+    return launch_mlp_f32(t->net32[model], d_states, d_n, n_static, n_max, t->d_eval, t->d_probs);
+  if (t->precision[model] == 1)
+    return launch_mlp_tc(t->nettc[model], d_states, d_n, n_static, n_max, t->d_eval, t->d_probs);
+  return set_error(CB200_ERR_STATE, "no weights set for this model (cb200_trainer_set_weights)");
+}
+
+int guard(cb200_trainer *t) {
+  if (!t) return set_error(CB200_ERR_ARG, "null trainer");
+  CB_CUDA(cudaSetDevice(t->device));
+  return CB200_OK;
+}
+
+}  // namespace
+
+// ==============================================================================================
+extern "C" {
+
+const char *cb200_last_error(void) { return last_error_ref().c_str(); }
+
+int cb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int cb200_set_device(int device) {
+  CB_CUDA(cudaSetDevice(device));
+  return CB200_OK;
+}
+
+int cb200_set_stream(void *cuda_stream) {
+  G().stream = (cudaStream_t)cuda_stream;
+  return CB200_OK;
+}
+
+int64_t cb200_launch_count(void) { return G().launches.load(); }
+
+int cb200_game_step_device(int64_t n, const void *states_device, uint64_t seed,
+                           void *mask_flags_device, void *next_device, void *enc_device) {
+  if (n < 0 || (n > 0 && (!states_device || !mask_flags_device || !next_device)))
+    return set_error(CB200_ERR_ARG, "cb200_game_step_device: bad arguments");
+  return launch_game_step(n, states_device, seed, mask_flags_device, next_device, enc_device);
+}
+
+int cb200_game_step(int64_t n, const uint64_t *states, uint64_t seed, uint32_t *mask_flags,
+                    uint64_t *next, float *enc) {
+  if (n < 0 || (n > 0 && (!states || !mask_flags || !next)))
+    return set_error(CB200_ERR_ARG, "cb200_game_step: bad arguments");
+  if (n == 0) return CB200_OK;
+  void *d_s = nullptr, *d_m = nullptr, *d_n = nullptr, *d_e = nullptr;
+  int rc = CB200_OK;
+  cudaError_t e;
+  if ((e = cudaMalloc(&d_s, n * 16)) != cudaSuccess || (e = cudaMalloc(&d_m, n * 16)) != cudaSuccess ||
+      (e = cudaMalloc(&d_n, n * 16)) != cudaSuccess ||
+      (enc && (e = cudaMalloc(&d_e, n * CB200_STATE_SIZE * sizeof(float))) != cudaSuccess)) {
+    rc = set_error(CB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  cudaStream_t s = G().stream;
+  if (rc == CB200_OK && (e = cudaMemcpyAsync(d_s, states, n * 16, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+    rc = set_error(CB200_ERR_CUDA, cudaGetErrorString(e));
+  if (rc == CB200_OK) rc = launch_game_step(n, d_s, seed, d_m, d_n, d_e);
+  if (rc == CB200_OK) {
+    e = cudaMemcpyAsync(mask_flags, d_m, n * 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(next, d_n, n * 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && enc)
+      e = cudaMemcpyAsync(enc, d_e, n * CB200_STATE_SIZE * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = set_error(CB200_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(d_s), cudaFree(d_m), cudaFree(d_n), cudaFree(d_e);
+  return rc;
+}
+
+// ---- Trainer --------------------------------------------------------------------------------
+cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int num_games,
+                                          const char *log_folder, int seed, int max_searches,
+                                          int searches_per_eval, float c_puct, float epsilon,
+                                          int num_logged, int testing) {
+  (void)num_logged;
+  // the reference only assert()s these (trainer.cpp:25-34); here they are hard errors
+  if (num_games <= 0 || total_games < num_games || first_game < 0 ||
+      first_game + num_games > total_games || max_searches <= 0 || searches_per_eval <= 0 ||
+      max_searches < searches_per_eval || !(c_puct > 0.0f) || !(epsilon >= 0.0f) ||
+      !(epsilon <= 1.0f)) {
+    set_error(CB200_ERR_ARG, "cb200_trainer_create: invalid argument");
+    return nullptr;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || upload_tables_once() != CB200_OK) {
+    if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "no usable CUDA device");
+    return nullptr;
+  }
+  cb200_trainer *t = new cb200_trainer();
+  t->device = dev;
+  t->log_folder = log_folder ? log_folder : "";
+  TreeParams &P = t->P;
+  P.num_games = num_games, P.first_game = first_game, P.total_games = total_games;
+  P.max_searches = max_searches, P.spe = searches_per_eval;
+  P.c_puct = c_puct, P.epsilon = epsilon, P.testing = testing ? 1 : 0;
+  // arena budget: kept subtree + max_searches new nodes per move with head-room; a game that
+  // still overflows fails loudly (CB200_ERR_OVERFLOW). ~28 slots/node on average.
+  long long nodes = (long long)max_searches * 5 / 2 + 96;
+  if (const char *env = getenv("CB200_ARENA_NODES")) nodes = atoll(env);
+  long long words = nodes * (8 + 4 * 28);
+  words = (words + 3) & ~3ll;
+  if (words < 1024) words = 1024;
+  P.arena_words = (uint32_t)words;
+  t->stagger_div = total_games / max_searches;
+  if (t->stagger_div < 1) t->stagger_div = 1;
+  const size_t Gn = (size_t)num_games;
+  t->cap = Gn * searches_per_eval;
+  bool ok = dmalloc(&P.arenas, Gn * 3 * P.arena_words) == CB200_OK &&
+            dmalloc(&P.ctl, Gn * kCtlWords) == CB200_OK &&
+            dmalloc(&P.tree, Gn * 2 * kTreeCtlWords) == CB200_OK &&
+            dmalloc(&P.mt, Gn * 624) == CB200_OK &&
+            dmalloc(&P.pending, t->cap * kPendWords) == CB200_OK &&
+            dmalloc(&P.leaf_state, t->cap) == CB200_OK &&
+            dmalloc(&P.sample_state, Gn * kMaxSamples) == CB200_OK &&
+            dmalloc(&P.sample_probs, Gn * kMaxSamples * CB200_NUM_MOVES) == CB200_OK &&
+            dmalloc(&P.counters, Gn * 4) == CB200_OK && dmalloc(&t->d_eval, t->cap) == CB200_OK &&
+            dmalloc(&t->d_probs, t->cap * CB200_NUM_MOVES) == CB200_OK &&
+            dmalloc(&t->d_rows, t->cap * CB200_STATE_SIZE) == CB200_OK &&
+            dmalloc(&t->d_packed, t->cap) == CB200_OK && dmalloc(&t->d_offs, Gn) == CB200_OK &&
+            dmalloc(&t->d_soff, Gn) == CB200_OK && dmalloc(&t->d_summary, 4) == CB200_OK &&
+            cudaMallocHost((void **)&t->h_summary, 4 * sizeof(int32_t)) == cudaSuccess;
+  if (!ok) {
+    if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
+    cb200_trainer_destroy(t);
+    return nullptr;
+  }
+  // host-side initialisation: seeds (trainer.cpp:238-256), control blocks
+  std::vector<int32_t> ctl(Gn * kCtlWords, 0), tree(Gn * 2 * kTreeCtlWords, 0);
+  std::vector<uint32_t> mt(Gn * 624);
+  HostMT gen;
+  gen.seed((uint32_t)seed);
+  for (int i = 0; i < first_game; ++i) gen.next();
+  for (size_t g = 0; g < Gn; ++g) {
+    uint32_t *m = mt.data() + g * 624;
+    m[0] = gen.next();
+    for (int i = 1; i < 624; ++i) m[i] = mt_seed_word(m[i - 1], i);
+    int32_t *c = ctl.data() + g * kCtlWords;
+    c[CW_PARITY] = (int)((first_game + g) & 1);
+    c[CW_SPARE] = 2;
+    c[CW_MT_IDX] = 624;
+    for (int p = 0; p < 2; ++p) {
+      int32_t *tw = tree.data() + (g * 2 + p) * kTreeCtlWords;
+      tw[TW_ARENA] = p;
+      tw[TW_ROOT_VISITS] = 1;
+      tw[TW_ROOT_ALLV] = 1;
+    }
+  }
+  cudaError_t e = cudaMemcpy(P.ctl, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(P.tree, tree.data(), tree.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(P.mt, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(P.counters, 0, Gn * 4 * sizeof(long long));
+  if (e == cudaSuccess) e = cudaMemset(t->d_offs, 0, Gn * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMemset(t->d_summary, 0, 4 * sizeof(int32_t));
+  if (e != cudaSuccess) {
+    set_error(CB200_ERR_CUDA, std::string("init upload: ") + cudaGetErrorString(e));
+    cb200_trainer_destroy(t);
+    return nullptr;
+  }
+  return t;
+}
+
+cb200_trainer *cb200_trainer_create(int num_games, const char *log_folder, int seed,
+                                    int max_searches, int searches_per_eval, float c_puct,
+                                    float epsilon, int num_logged, int num_threads, int testing) {
+  (void)num_threads;
+  return cb200_trainer_create_shard(num_games, 0, num_games, log_folder, seed, max_searches,
+                                    searches_per_eval, c_puct, epsilon, num_logged, testing);
+}
+
+void cb200_trainer_destroy(cb200_trainer *t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  TreeParams &P = t->P;
+  cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
+  cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);
+  cudaFree(t->d_eval), cudaFree(t->d_probs), cudaFree(t->d_rows), cudaFree(t->d_packed);
+  cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary);
+  if (t->h_summary) cudaFreeHost(t->h_summary);
+  for (int m = 0; m < 2; ++m) {
+    cudaFree(t->net32[m].w);
+    net_tc_free(t->nettc[m]);
+  }
+  delete t;
+}
+
+int cb200_trainer_num_requests(cb200_trainer *t, int to_play) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if ((rc = scan(t, to_play)) != CB200_OK) return rc;
+  if ((rc = fetch_summary(t)) != CB200_OK) return rc;
+  return t->h_summary[0];
+}
+
+int cb200_trainer_write_requests(cb200_trainer *t, float *game_states, int to_play) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (!game_states) return set_error(CB200_ERR_ARG, "null game_states");
+  if ((rc = scan(t, to_play)) != CB200_OK) return rc;
+  if ((rc = pack(t, to_play, t->d_rows, nullptr)) != CB200_OK) return rc;
+  if ((rc = fetch_summary(t)) != CB200_OK) return rc;
+  const int n = t->h_summary[0];
+  if (n > 0) {
+    CB_CUDA(cudaMemcpyAsync(game_states, t->d_rows, (size_t)n * CB200_STATE_SIZE * sizeof(float),
+                            cudaMemcpyDeviceToHost, G().stream));
+    CB_CUDA(cudaStreamSynchronize(G().stream));
+  }
+  return CB200_OK;
+}
+
+int cb200_trainer_do_iteration(cb200_trainer *t, const float *eval, const float *probs,
+                               int to_play) {
+  int rc = guard(t);
+  if (rc) return rc;
+  // offsets of the answers = prefix sums of the request counts they were written for
+  if ((rc = scan(t, to_play)) != CB200_OK) return rc;
+  if ((rc = fetch_summary(t)) != CB200_OK) return rc;
+  const int n = t->h_summary[0];
+  if (n > 0) {
+    if (!eval || !probs) return set_error(CB200_ERR_ARG, "requests pending but eval/probs null");
+    CB_CUDA(cudaMemcpyAsync(t->d_eval, eval, (size_t)n * sizeof(float), cudaMemcpyHostToDevice,
+                            G().stream));
+    CB_CUDA(cudaMemcpyAsync(t->d_probs, probs, (size_t)n * CB200_NUM_MOVES * sizeof(float),
+                            cudaMemcpyHostToDevice, G().stream));
+  }
+  if ((rc = iterate(t, t->d_eval, t->d_probs, to_play)) != CB200_OK) return rc;
+  if ((rc = scan(t, to_play)) != CB200_OK) return rc;
+  if ((rc = fetch_summary(t)) != CB200_OK) return rc;
+  return t->h_summary[1] == 0 ? 1 : 0;
+}
+
+static int fetch_ctl(cb200_trainer *t) {
+  t->h_ctl.resize((size_t)t->P.num_games * kCtlWords);
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaMemcpy(t->h_ctl.data(), t->P.ctl, t->h_ctl.size() * 4, cudaMemcpyDeviceToHost));
+  return CB200_OK;
+}
+
+int cb200_trainer_num_samples(cb200_trainer *t) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  long long n = 0;
+  for (int g = 0; g < t->P.num_games; ++g) n += t->h_ctl[(size_t)g * kCtlWords + CW_N_SAMPLES];
+  return (int)n;
+}
+
+int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eval_samples,
+                                float *prob_samples) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (!game_states || !eval_samples || !prob_samples) return set_error(CB200_ERR_ARG, "null buffer");
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  const int Gn = t->P.num_games;
+  std::vector<int32_t> soff(Gn);
+  long long ns = 0;
+  for (int g = 0; g < Gn; ++g) {
+    soff[g] = (int32_t)ns;
+    ns += t->h_ctl[(size_t)g * kCtlWords + CW_N_SAMPLES];
+  }
+  if (ns == 0) return CB200_OK;
+  float *d_gs = nullptr, *d_ev = nullptr, *d_pr = nullptr;
+  const size_t rows = (size_t)ns * 8;
+  rc = dmalloc(&d_gs, rows * CB200_STATE_SIZE);
+  if (rc == CB200_OK) rc = dmalloc(&d_ev, rows);
+  if (rc == CB200_OK) rc = dmalloc(&d_pr, rows * CB200_NUM_MOVES);
+  if (rc == CB200_OK) {
+    cudaStream_t s = G().stream;
+    cudaError_t e = cudaMemcpyAsync(t->d_soff, soff.data(), Gn * sizeof(int32_t),
+                                    cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+      const long long warps = (long long)Gn * kMaxSamples;
+      k_write_samples<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(t->P, t->d_soff, d_gs, d_ev, d_pr);
+      CB_LAUNCHED();
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(game_states, d_gs, rows * CB200_STATE_SIZE * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(eval_samples, d_ev, rows * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(prob_samples, d_pr, rows * CB200_NUM_MOVES * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = set_error(CB200_ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaFree(d_gs), cudaFree(d_ev), cudaFree(d_pr);
+  return rc;
+}
+
+static float game_score(int result) {  // SelfPlayer::score selfplayer.cpp:57-64
+  if (result == kResultLoss) return 0.0f;
+  if (result == kResultWin) return 1.0f;
+  return 0.5f;
+}
+
+float cb200_trainer_score(cb200_trainer *t) {  // trainer.cpp:59-68
+  if (guard(t) || fetch_ctl(t)) return NAN;
+  const int Gn = t->P.num_games;
+  float score = 0;
+  for (int g = 0; g < Gn; ++g)
+    if (((t->P.first_game + g) & 1) == 0) score += game_score(t->h_ctl[(size_t)g * kCtlWords + CW_RESULT]);
+  for (int g = 0; g < Gn; ++g)
+    if ((t->P.first_game + g) & 1)
+      score = (float)(score + (1.0 - game_score(t->h_ctl[(size_t)g * kCtlWords + CW_RESULT])));
+  return score / (float)(size_t)Gn;
+}
+
+float cb200_trainer_avg_mate_length(cb200_trainer *t) {  // trainer.cpp:70-77
+  if (guard(t) || fetch_ctl(t)) return NAN;
+  const int Gn = t->P.num_games;
+  int total = 0;
+  for (int g = 0; g < Gn; ++g) {
+    const int32_t *c = t->h_ctl.data() + (size_t)g * kCtlWords;
+    total += c[CW_MATE_TURN] == 0 ? 0 : c[CW_N_SAMPLES] - c[CW_MATE_TURN] + 1;  // selfplayer.cpp:66-71
+  }
+  return (float)total / (float)(size_t)Gn;
+}
+
+int cb200_trainer_write_scores(cb200_trainer *t, const char *file) {  // trainer.cpp:115-162
+  int rc = guard(t);
+  if (rc) return rc;
+  if (!file) return set_error(CB200_ERR_ARG, "null file");
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  const int Gn = t->P.num_games;
+  std::vector<float> scores(Gn);
+  for (int g = 0; g < Gn; ++g) {
+    float s = game_score(t->h_ctl[(size_t)g * kCtlWords + CW_RESULT]);
+    scores[g] = ((t->P.first_game + g) & 1) ? (float)(1.0 - s) : s;
+  }
+  std::ofstream f(file, std::ofstream::out);
+  if (!f) return set_error(CB200_ERR_ARG, std::string("cannot open ") + file);
+  const char *names[2] = {"First", "Second"};
+  const int half = Gn / 2;
+  for (int side = 0; side < 2; ++side) {
+    int wins = 0, draws = 0;
+    for (int g = side; g < Gn; g += 2) {
+      if (scores[g] == 1.0f) ++wins;
+      else if (scores[g] == 0.5f) ++draws;
+    }
+    f << names[side] << " player wins: " << wins << " / " << half << " = "
+      << static_cast<float>(wins) / half << "\n" << names[side] << " player draws: " << draws
+      << " / " << half << " = " << static_cast<float>(draws) / half << "\n" << names[side]
+      << " player losses: " << half - wins - draws << " / " << half << " = "
+      << static_cast<float>(half - wins - draws) / half << '\n';
+  }
+  return CB200_OK;
+}
+
+int cb200_trainer_counters(cb200_trainer *t, int64_t out[4]) {
+  int rc = guard(t);
+  if (rc) return rc;
+  std::vector<long long> h((size_t)t->P.num_games * 4);
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaMemcpy(h.data(), t->P.counters, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  out[0] = out[1] = out[2] = 0;
+  for (int g = 0; g < t->P.num_games; ++g) out[0] += h[4 * g], out[1] += h[4 * g + 1], out[2] += h[4 * g + 2];
+  out[3] = t->iterations_done;
+  return CB200_OK;
+}
+
+int cb200_trainer_game_results(cb200_trainer *t, int32_t *results) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  for (int g = 0; g < t->P.num_games; ++g) results[g] = t->h_ctl[(size_t)g * kCtlWords + CW_RESULT];
+  return CB200_OK;
+}
+
+int cb200_trainer_write_raw_samples(cb200_trainer *t, uint64_t *states, float *probs, float *labels,
+                                    int32_t *game_of) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  const int Gn = t->P.num_games;
+  std::vector<ulonglong2> hs;
+  std::vector<float> hp;
+  if (states) {
+    hs.resize((size_t)Gn * kMaxSamples);
+    CB_CUDA(cudaMemcpy(hs.data(), t->P.sample_state, hs.size() * sizeof(ulonglong2), cudaMemcpyDeviceToHost));
+  }
+  if (probs) {
+    hp.resize((size_t)Gn * kMaxSamples * CB200_NUM_MOVES);
+    CB_CUDA(cudaMemcpy(hp.data(), t->P.sample_probs, hp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  size_t row = 0;
+  for (int g = 0; g < Gn; ++g) {
+    const int32_t *c = t->h_ctl.data() + (size_t)g * kCtlWords;
+    const int ns = c[CW_N_SAMPLES];
+    for (int i = 0; i < ns; ++i, ++row) {
+      if (states) states[2 * row] = hs[(size_t)g * kMaxSamples + i].x, states[2 * row + 1] = hs[(size_t)g * kMaxSamples + i].y;
+      if (probs) memcpy(probs + row * CB200_NUM_MOVES, hp.data() + ((size_t)g * kMaxSamples + i) * CB200_NUM_MOVES, CB200_NUM_MOVES * sizeof(float));
+      if (labels) {
+        float ev = c[CW_RESULT] == kResultDraw ? 0.0f : 1.0f;
+        labels[row] = ((ns - 1 - i) & 1) ? -ev : ev;
+      }
+      if (game_of) game_of[row] = g;
+    }
+  }
+  return CB200_OK;
+}
+
+int cb200_trainer_set_weights(cb200_trainer *t, int model, const float *weights, size_t n_floats,
+                              int precision) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (model < 0 || model > 1 || !weights || n_floats != kNetWeightFloats ||
+      (precision != 0 && precision != 1))
+    return set_error(CB200_ERR_ARG, "cb200_trainer_set_weights: bad arguments (127997 floats, precision 0|1)");
+  rc = precision == 0 ? net_f32_upload(t->net32[model], weights) : net_tc_upload(t->nettc[model], weights);
+  if (rc == CB200_OK) t->precision[model] = precision;
+  return rc;
+}
+
+int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game_states,
+                           float *eval, float *probs) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (model < 0 || model > 1 || n < 0 || (size_t)n > t->cap || !game_states || !eval || !probs)
+    return set_error(CB200_ERR_ARG, "cb200_trainer_evaluate: bad arguments (n <= num_games*searches_per_eval)");
+  if (n == 0) return CB200_OK;
+  // pack the 70-float rows back into cstates on the host (rows hold only 0/1 and k/4 values)
+  std::vector<ulonglong2> hs(n);
+  for (int i = 0; i < n; ++i) {
+    const float *r = game_states + (size_t)i * CB200_STATE_SIZE;
+    uint64_t w0 = 0, w1 = 0;
+    for (int j = 0; j < 64; ++j)
+      if (r[j] != 0.0f) w0 |= 1ull << (16 * (j & 3) + (j >> 2));
+    // the encoding holds the mover's pieces first; keep that order with to_play = 0
+    for (int j = 0; j < 6; ++j) w1 |= (uint64_t)(int)(r[64 + j] * 4.0f + 0.5f) << (8 * j);
+    hs[i] = make_ulonglong2(w0, w1);
+  }
+  cudaStream_t s = G().stream;
+  CB_CUDA(cudaMemcpyAsync(t->d_packed, hs.data(), (size_t)n * sizeof(ulonglong2), cudaMemcpyHostToDevice, s));
+  if ((rc = run_net(t, model, t->d_packed, nullptr, n, n)) != CB200_OK) return rc;
+  CB_CUDA(cudaMemcpyAsync(eval, t->d_eval, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaMemcpyAsync(probs, t->d_probs, (size_t)n * CB200_NUM_MOVES * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  return CB200_OK;
+}
+
+int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger) {
+  int rc = guard(t);
+  if (rc) return rc;
+  const bool testing = t->P.testing != 0;
+  if (t->precision[0] < 0 || (testing && t->precision[1] < 0))
+    return set_error(CB200_ERR_STATE, "cb200_trainer_run_selfplay: set weights first");
+  const int saved_div = t->stagger_div;
+  if (!stagger) t->stagger_div = 0;
+  const int n_max = (int)t->cap;
+  int done_iters = 0;
+  int result = 0;
+  while (max_iterations <= 0 || done_iters < max_iterations) {
+    int batch = 32;
+    if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
+    for (int i = 0; i < batch && rc == CB200_OK; ++i) {
+      if (!testing) {
+        // answers for the requests of the previous step, then the step itself
+        rc = scan(t, -1);
+        if (rc == CB200_OK) rc = pack(t, -1, nullptr, t->d_packed);
+        if (rc == CB200_OK) rc = run_net(t, 0, t->d_packed, t->d_summary, 0, n_max);
+        if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, -1);
+      } else {
+        for (int tp = 0; tp < 2 && rc == CB200_OK; ++tp) {  // model 0 = "new" serves to_play 0
+          rc = scan(t, tp);
+          if (rc == CB200_OK) rc = pack(t, tp, nullptr, t->d_packed);
+          if (rc == CB200_OK) rc = run_net(t, tp == 0 ? 0 : 1, t->d_packed, t->d_summary, 0, n_max);
+          if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, tp);
+        }
+        ++t->iterations_done;
+      }
+    }
+    done_iters += batch;
+    if (rc == CB200_OK) rc = scan(t, -1);
+    if (rc == CB200_OK) rc = fetch_summary(t);
+    if (rc != CB200_OK) break;
+    if (t->h_summary[1] == 0) {
+      result = 1;
+      break;
+    }
+  }
+  t->stagger_div = saved_div;
+  return rc != CB200_OK ? rc : result;
+}
+
+int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[8],
+                            uint32_t *words, int cap) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (game < 0 || game >= t->P.num_games || player < 0 || player > 1)
+    return set_error(CB200_ERR_ARG, "bad game/player");
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  int32_t tw[kTreeCtlWords], cw[kCtlWords];
+  CB_CUDA(cudaMemcpy(tw, t->P.tree + ((size_t)game * 2 + player) * kTreeCtlWords, sizeof(tw), cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(cw, t->P.ctl + (size_t)game * kCtlWords, sizeof(cw), cudaMemcpyDeviceToHost));
+  out[0] = tw[TW_HAS_ROOT], out[1] = (uint32_t)tw[TW_USED], out[2] = tw[TW_ROOT_VISITS];
+  out[3] = tw[TW_ROOT_RESULT], out[4] = tw[TW_ROOT_ALLV], out[5] = tw[TW_SEARCHES_DONE];
+  out[6] = (uint32_t)tw[TW_ROOT_EVAL], out[7] = cw[CW_TO_PLAY];
+  const int used = tw[TW_USED];
+  if (tw[TW_HAS_ROOT] && words && cap > 0) {
+    const int n = used < cap ? used : cap;
+    CB_CUDA(cudaMemcpy(words, t->P.arenas + ((size_t)game * 3 + tw[TW_ARENA]) * t->P.arena_words,
+                       (size_t)n * 4, cudaMemcpyDeviceToHost));
+  }
+  return used;
+}
+
+}  // extern "C"

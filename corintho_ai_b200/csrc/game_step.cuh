@@ -1,0 +1,90 @@
+// K1: game-logic kernel (BASELINE.json configs[1]) -- one thread per state.
+// Per state: 16 B read (cstate), 16 B written (legal mask + flags), 16 B written (next state);
+// the optional 70-float NN encoding is written warp-cooperatively so stores stay coalesced.
+// HBM-bound by construction; see DESIGN.md "K1" for the roofline arithmetic.
+#ifndef CORINTHO_B200_GAME_STEP_CUH
+#define CORINTHO_B200_GAME_STEP_CUH
+
+#include "common.cuh"
+
+namespace cb200 {
+
+constexpr int kStepThreads = 256;
+
+template <bool kEncode>
+__global__ void __launch_bounds__(kStepThreads)
+    k_game_step(int64_t n, const ulonglong2 *__restrict__ states, uint64_t seed,
+                uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next,
+                float *__restrict__ enc) {
+  __shared__ ulonglong2 sm_states[kEncode ? kStepThreads : 1];
+  const int64_t stride = (int64_t)gridDim.x * kStepThreads;
+  // every warp runs the same number of trips so the cooperative encode stays convergent
+  const int64_t n_round = ((n + 31) / 32) * 32;
+  for (int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x; i < n_round; i += stride) {
+    const bool live = i < n;
+    CState s{0, 0};
+    if (live) {
+      const ulonglong2 v = __ldg(states + i);
+      s.w0 = v.x, s.w1 = v.y;
+      uint32_t m[3];
+      const bool lines = legal_moves(s, m, DeviceLB());
+      const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
+      const int result = terminal_result(nl, lines);
+      int chosen = 0x7f;
+      CState o = s;
+      if (nl > 0) {
+        chosen = nth_move(m, (int)(step_rnd(seed, (uint64_t)i) % (uint32_t)nl));
+        o = do_move(s, chosen);
+      }
+      mask_flags[i] = make_uint4(m[0], m[1], m[2],
+                                 (uint32_t)result | (lines ? 4u : 0u) | ((uint32_t)nl << 8) |
+                                     ((uint32_t)chosen << 16));
+      next[i] = make_ulonglong2(o.w0, o.w1);
+    }
+    if (kEncode) {
+      // warp-cooperative write of 32 x 70 contiguous floats (game.cpp:45-58 layout)
+      const int lane = threadIdx.x & 31;
+      ulonglong2 *ws = sm_states + (threadIdx.x & ~31);
+      ws[lane] = make_ulonglong2(s.w0, s.w1);
+      __syncwarp();
+      const int64_t base = i - lane;
+      const int64_t left = n - base;
+      const int cnt = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+      float *out = enc + base * CB200_STATE_SIZE;
+      for (int f = lane; f < cnt * CB200_STATE_SIZE; f += 32) {
+        const int si = f / CB200_STATE_SIZE, j = f - si * CB200_STATE_SIZE;
+        const ulonglong2 v = ws[si];
+        out[f] = encode_elem(CState{v.x, v.y}, j);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void *d_mask_flags,
+                            void *d_next, void *d_enc) {
+  if (n <= 0) return CB200_OK;
+  int rc = ensure_tables();
+  if (rc != CB200_OK) return rc;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // persistent-style grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
+  int64_t want = (n + kStepThreads - 1) / kStepThreads;
+  int64_t cap = (int64_t)sms * 8 * 4;
+  int grid = (int)(want < cap ? want : cap);
+  if (d_enc)
+    k_game_step<true><<<grid, kStepThreads, 0, G().stream>>>(
+        n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
+        (float *)d_enc);
+  else
+    k_game_step<false><<<grid, kStepThreads, 0, G().stream>>>(
+        n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
+        nullptr);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  return CB200_OK;
+}
+
+}  // namespace cb200
+#endif

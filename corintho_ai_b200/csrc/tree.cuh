@@ -1,0 +1,975 @@
+// K2-K6: the self-play game step -- one warp owns one game and executes
+// SelfPlayer::doIteration (corintho_ai/cpp/src/selfplayer.cpp:115-122) for it:
+//   eval ingest + backup   TrainMC::receiveEval      trainmc.cpp:269-296 (212-267)
+//   PUCT select / expand   TrainMC::search           trainmc.cpp:602-696 (chooseNext 540-600)
+//   terminal deduction     TrainMC::propagateTerminal trainmc.cpp:497-538
+//   move choice, re-root   TrainMC::chooseMove*      trainmc.cpp:110-137, 298-495
+//   turn hand-over         SelfPlayer::chooseMoveAndContinue selfplayer.cpp:246-291
+//
+// Data layout (HBM, per game): three node arenas (two trees + one spare for re-rooting), each a
+// bump-allocated array of 32-bit words holding node records
+//     header[8]  w0..w3 cstate, w4 = n_legal | depth<<8, w5 = denominator (f32 bits)
+//     slot[n][4] one 16-byte slot per legal move in ascending id order:
+//                {child evaluation_ f32, child visits_ i32, child record offset,
+//                 move | prior<<7 | result<<16 | all_visited<<19 | has_child<<20 |
+//                 child_n_legal<<21 | child_has_children<<28}
+// A node's statistics live in its parent's slot, so PUCT selection at a node is ONE coalesced
+// read of header+slots (lane e loads slot e as a uint4) and virtual loss is a plain store.
+// The root record is at word 0; root statistics are in the per-tree control block.
+// Float expression types follow the reference literally (double intermediates, no FMA
+// contraction): explicit __f*_rn / __d*_rn intrinsics are used for every rounded operation.
+#ifndef CORINTHO_B200_TREE_CUH
+#define CORINTHO_B200_TREE_CUH
+
+#include "common.cuh"
+
+namespace cb200 {
+
+constexpr int kMaxPath = 64;
+constexpr int kPendWords = 2 + kMaxPath;  // leaf_off, path_len, path[kMaxPath]
+constexpr int kMaxSamples = 64;
+constexpr int kTreeWarps = 4;  // games per CTA
+constexpr int kCtlWords = 16;
+constexpr int kTreeCtlWords = 8;
+
+enum CtlWord {
+  CW_TO_PLAY = 0, CW_PARITY, CW_RESULT, CW_MATE_TURN, CW_N_SAMPLES, CW_N_PENDING, CW_ERROR,
+  CW_DONE, CW_SPARE, CW_MT_IDX
+};
+enum TreeWord {
+  TW_ARENA = 0, TW_HAS_ROOT, TW_USED, TW_ROOT_EVAL, TW_ROOT_VISITS, TW_ROOT_RESULT, TW_ROOT_ALLV,
+  TW_SEARCHES_DONE
+};
+
+struct TreeParams {
+  int num_games, first_game, total_games;
+  int max_searches, spe;
+  float c_puct, epsilon;
+  int testing;
+  uint32_t arena_words;
+  uint32_t *arenas;          // [G][3][arena_words]
+  int32_t *ctl;              // [G][kCtlWords]
+  int32_t *tree;             // [G][2][kTreeCtlWords]
+  uint32_t *mt;              // [G][624]
+  uint32_t *pending;         // [G][spe][kPendWords]
+  ulonglong2 *leaf_state;    // [G][spe]
+  ulonglong2 *sample_state;  // [G][kMaxSamples]
+  float *sample_probs;       // [G][kMaxSamples][96]
+  long long *counters;       // [G][4] simulations, moves, leaf evals, (unused)
+};
+
+struct WarpSm {
+  float f[96];
+  uint32_t node[kMaxPath + 1];
+  uint32_t slot[kMaxPath + 1];
+};
+
+// ---- slot word 3 ---------------------------------------------------------------------------
+__device__ __forceinline__ int s3_move(uint32_t w) { return w & 0x7f; }
+__device__ __forceinline__ int s3_prior(uint32_t w) { return (w >> 7) & 0x1ff; }
+__device__ __forceinline__ int s3_result(uint32_t w) { return (w >> 16) & 7; }
+__device__ __forceinline__ bool s3_allv(uint32_t w) { return (w >> 19) & 1; }
+__device__ __forceinline__ bool s3_has(uint32_t w) { return (w >> 20) & 1; }
+__device__ __forceinline__ int s3_cnl(uint32_t w) { return (w >> 21) & 0x7f; }
+__device__ __forceinline__ bool s3_gc(uint32_t w) { return (w >> 28) & 1; }
+constexpr uint32_t kS3Allv = 1u << 19, kS3Has = 1u << 20, kS3Gc = 1u << 28;
+
+__device__ __forceinline__ bool r_known(int r) { return r != kResultNone; }
+__device__ __forceinline__ bool r_terminal(int r) { return r == kResultLoss || r == kResultDraw; }
+__device__ __forceinline__ bool r_won(int r) { return r == kDeducedWin; }
+__device__ __forceinline__ bool r_lost(int r) { return r == kResultLoss || r == kDeducedLoss; }
+__device__ __forceinline__ bool r_drawn(int r) { return r == kResultDraw || r == kDeducedDraw; }
+
+__device__ __forceinline__ uint4 ld4(const uint32_t *p) {
+  return *reinterpret_cast<const uint4 *>(p);
+}
+__device__ __forceinline__ void st4(uint32_t *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
+__device__ __forceinline__ uint32_t fkey(float f) {  // order-preserving float -> uint
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+constexpr uint32_t kKeyNegInf = 0x007FFFFFu;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// Per-warp view of one game. Every member is warp-uniform.
+struct Ctx {
+  int lane;
+  // game control (selfplayer.h:88-111)
+  int to_play, parity, result, mate_turn, n_samples, n_pending, error, spare, mt_idx;
+  long long d_sims, d_evals;
+  int d_moves;
+  // current tree (trainmc.h:160-188)
+  int cur_p, arena, has_root;
+  uint32_t used;
+  float root_eval;
+  int root_visits, root_result, root_allv, searches_done;
+  uint32_t *base;
+  // per-game storage
+  uint32_t *arenas, *mt, *pending;
+  int32_t *tree_ctl;
+  ulonglong2 *leaf_state, *sample_state;
+  float *sample_probs;
+};
+
+__device__ __forceinline__ void load_tree(Ctx &c, const TreeParams &P, int p) {
+  const int32_t *t = c.tree_ctl + p * kTreeCtlWords;
+  const int4 a = *reinterpret_cast<const int4 *>(t);
+  const int4 b = *reinterpret_cast<const int4 *>(t + 4);
+  c.cur_p = p;
+  c.arena = a.x, c.has_root = a.y, c.used = (uint32_t)a.z, c.root_eval = __int_as_float(a.w);
+  c.root_visits = b.x, c.root_result = b.y, c.root_allv = b.z, c.searches_done = b.w;
+  c.base = c.arenas + (size_t)c.arena * P.arena_words;
+}
+__device__ __forceinline__ void store_tree(Ctx &c) {
+  if (c.lane == 0) {
+    int32_t *t = c.tree_ctl + c.cur_p * kTreeCtlWords;
+    *reinterpret_cast<int4 *>(t) =
+        make_int4(c.arena, c.has_root, (int)c.used, __float_as_int(c.root_eval));
+    *reinterpret_cast<int4 *>(t + 4) =
+        make_int4(c.root_visits, c.root_result, c.root_allv, c.searches_done);
+  }
+  __syncwarp();
+}
+
+// ---- per-game MT19937 (std::mt19937 stream shared by both trees, selfplayer.h:88) -----------
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+__device__ __noinline__ void mt_twist(Ctx &c) {
+  uint32_t *mt = c.mt;
+  for (int cb = 0; cb < 624; cb += 32) {
+    const int i = cb + c.lane;
+    uint32_t v = 0;
+    if (i < 624) {
+      const uint32_t a = mt[i], b = mt[i + 1 == 624 ? 0 : i + 1];
+      const uint32_t m = mt[i + 397 >= 624 ? i + 397 - 624 : i + 397];
+      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      v = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+    if (i < 624) mt[i] = v;
+    __syncwarp();
+  }
+  c.mt_idx = 0;
+}
+// n (<=96) consecutive outputs; output e = lane + 32 j lands in out[j] of that lane
+__device__ __forceinline__ void rng_block(Ctx &c, int n, uint32_t out[3]) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    out[j] = 0;
+    const int e0 = 32 * j;
+    if (e0 < n) {
+      const int cnt = min(32, n - e0);
+      const int avail = 624 - c.mt_idx;
+      uint32_t y = 0;
+      if (cnt <= avail) {
+        if (c.lane < cnt) y = c.mt[c.mt_idx + c.lane];
+        c.mt_idx += cnt;
+      } else {
+        if (c.lane < avail) y = c.mt[c.mt_idx + c.lane];
+        mt_twist(c);
+        if (c.lane >= avail && c.lane < cnt) y = c.mt[c.lane - avail];
+        c.mt_idx = cnt - avail;
+      }
+      out[j] = mt_temper(y);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t rng_one(Ctx &c) {
+  if (c.mt_idx >= 624) mt_twist(c);
+  const uint32_t y = c.mt[c.mt_idx];
+  c.mt_idx += 1;
+  return mt_temper(y);
+}
+
+__device__ __forceinline__ void copy_words(uint32_t *dst, const uint32_t *src, uint32_t nwords,
+                                           int lane) {
+  const uint4 *s = reinterpret_cast<const uint4 *>(src);
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  for (uint32_t i = lane; i < (nwords >> 2); i += 32) d[i] = s[i];
+}
+
+// ---- node construction (Node ctor + initializeEdges, node.cpp:31-39, 256-283) ---------------
+__device__ __forceinline__ int make_record(Ctx &c, const TreeParams &P, const CState &st,
+                                           int depth, int &result) {
+  uint32_t m[3];
+  const bool lines = legal_moves(st, m, DeviceLB());
+  const int n0 = __popc(m[0]), n1 = __popc(m[1]), n2 = __popc(m[2]);
+  const int n = n0 + n1 + n2;
+  const uint32_t off = c.used;
+  result = kResultNone;
+  if (off + 8u + 4u * (uint32_t)n > P.arena_words) {
+    c.error = CB200_ERR_OVERFLOW;
+    return -1;
+  }
+  uint32_t *r = c.base + off;
+  if (c.lane == 0) {
+    st4(r, make_uint4((uint32_t)st.w0, (uint32_t)(st.w0 >> 32), (uint32_t)st.w1,
+                      (uint32_t)(st.w1 >> 32)));
+    st4(r + 4, make_uint4((uint32_t)n | ((uint32_t)depth << 8), 0u, 0u, 0u));
+  }
+  const uint32_t lt = (1u << c.lane) - 1u;
+  if ((m[0] >> c.lane) & 1u)
+    st4(r + 8 + 4 * __popc(m[0] & lt), make_uint4(0u, 0u, 0u, (uint32_t)c.lane));
+  if ((m[1] >> c.lane) & 1u)
+    st4(r + 8 + 4 * (n0 + __popc(m[1] & lt)), make_uint4(0u, 0u, 0u, 32u + c.lane));
+  if ((m[2] >> c.lane) & 1u)
+    st4(r + 8 + 4 * (n0 + n1 + __popc(m[2] & lt)), make_uint4(0u, 0u, 0u, 64u + c.lane));
+  c.used = off + 8u + 4u * (uint32_t)n;
+  result = terminal_result(n, lines);
+  __syncwarp();
+  return n;
+}
+
+__device__ __forceinline__ CState rec_state(const uint32_t *r) {
+  const uint4 h = ld4(r);
+  CState s;
+  s.w0 = (uint64_t)h.x | ((uint64_t)h.y << 32);
+  s.w1 = (uint64_t)h.z | ((uint64_t)h.w << 32);
+  return s;
+}
+
+// Single-node tree (Node(game, depth) node.cpp:25-29; reset paths trainmc.cpp:397-404,461-468)
+__device__ __forceinline__ void fresh_tree(Ctx &c, const TreeParams &P, const CState &st,
+                                           int depth) {
+  c.used = 0;
+  int result;
+  make_record(c, P, st, depth, result);
+  c.has_root = 1;
+  c.root_eval = 0.0f;
+  c.root_visits = 1;
+  c.root_result = result;
+  c.root_allv = 1;
+}
+
+// queue the root for evaluation (trainmc.cpp:150-152, 160-162, 198-200)
+__device__ __forceinline__ void request_root(Ctx &c) {
+  if (c.lane == 0) {
+    uint32_t *pd = c.pending + c.n_pending * kPendWords;
+    pd[0] = 0, pd[1] = 0;
+    const uint4 h = ld4(c.base);
+    c.leaf_state[c.n_pending] = make_ulonglong2((uint64_t)h.x | ((uint64_t)h.y << 32),
+                                                (uint64_t)h.z | ((uint64_t)h.w << 32));
+  }
+  c.n_pending += 1;
+  __syncwarp();
+}
+
+// ---- TrainMC::moveDown (trainmc.cpp:475-495): child behind root slot e becomes the root -----
+// Breadth-first copy of the kept subtree into the spare arena; only records that have
+// children are queued for scanning (queue grows down from the top of the target arena).
+__device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
+  const uint32_t *src = c.base;
+  uint32_t *dst = c.arenas + (size_t)c.spare * P.arena_words;
+  const uint4 s = ld4(src + 8 + 4 * e);
+  c.root_eval = __uint_as_float(s.x);
+  c.root_visits = (int)s.y;
+  c.root_result = s3_result(s.w);
+  c.root_allv = s3_allv(s.w) ? 1 : 0;
+  const uint32_t sz = 8u + 4u * (uint32_t)s3_cnl(s.w);
+  copy_words(dst, src + s.z, sz, c.lane);
+  uint32_t alloc = sz;
+  int q_head = 0, q_tail = 0;
+  uint32_t *q = dst + (P.arena_words - 1);
+  if (s3_gc(s.w)) {
+    if (c.lane == 0) q[0] = 0;
+    q_tail = 1;
+  }
+  __syncwarp();
+  const uint32_t lt = (1u << c.lane) - 1u;
+  while (q_head < q_tail) {
+    const uint32_t roff = *(volatile uint32_t *)(q - q_head);
+    ++q_head;
+    uint32_t *r = dst + roff;
+    const int rn = (int)(r[4] & 0xffu);
+    for (int e0 = 0; e0 < rn; e0 += 32) {
+      const int ee = e0 + c.lane;
+      bool has = false, gc = false;
+      uint32_t coff = 0, csz = 0;
+      if (ee < rn) {
+        const uint4 cs = ld4(r + 8 + 4 * ee);
+        has = s3_has(cs.w);
+        if (has) csz = 8u + 4u * (uint32_t)s3_cnl(cs.w), coff = cs.z, gc = s3_gc(cs.w);
+      }
+      const uint32_t incl = warp_incl_scan(csz, c.lane);
+      const uint32_t excl = incl - csz;
+      const uint32_t total = __shfl_sync(kFull, incl, 31);
+      const unsigned gm = __ballot_sync(kFull, gc);
+      const int ngc = __popc(gm);
+      if (alloc + total + (uint32_t)(q_tail + ngc) > P.arena_words) {
+        c.error = CB200_ERR_OVERFLOW;
+        return;
+      }
+      if (has) r[8 + 4 * ee + 2] = alloc + excl;
+      if (gc) *(q - (q_tail + __popc(gm & lt))) = alloc + excl;
+      q_tail += ngc;
+      unsigned hm = __ballot_sync(kFull, has);
+      while (hm) {
+        const int sl = __ffs((int)hm) - 1;
+        hm &= hm - 1;
+        const uint32_t so = __shfl_sync(kFull, coff, sl);
+        const uint32_t sw = __shfl_sync(kFull, csz, sl);
+        const uint32_t dof = alloc + __shfl_sync(kFull, excl, sl);
+        copy_words(dst + dof, src + so, sw, c.lane);
+      }
+      alloc += total;
+    }
+    __syncwarp();
+  }
+  const int old = c.arena;
+  c.arena = c.spare;
+  c.spare = old;
+  c.base = dst;
+  c.used = alloc;
+  c.searches_done = 0;
+}
+
+// ---- TrainMC::receiveEval (trainmc.cpp:269-296) ---------------------------------------------
+__device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &sm,
+                                          const float *eval, const float *probs) {
+  const int np = c.n_pending;
+  for (int k = 0; k < np; ++k) {
+    const uint32_t *pd = c.pending + k * kPendWords;
+    const uint32_t leaf_off = pd[0];
+    const int path_len = (int)pd[1];
+    uint32_t *r = c.base + leaf_off;
+    const int n = (int)(r[4] & 0xffu);
+    const float *pk = probs + (size_t)k * CB200_NUM_MOVES;
+    // getFilteredProbs (trainmc.cpp:212-234): gather legal priors, float sum in edge order
+    uint32_t w3[3];
+    float fv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int e = c.lane + 32 * j;
+      w3[j] = 0, fv[j] = 0.0f;
+      if (e < n) {
+        w3[j] = r[8 + 4 * e + 3];
+        fv[j] = pk[s3_move(w3[j])];
+        sm.f[e] = fv[j];
+      }
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    for (int j = 0; j < n; ++j) sum = __fadd_rn(sum, sm.f[j]);
+    float scalar = __double2float_rn(
+        __dmul_rn(__ddiv_rn(1.0, (double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
+    __syncwarp();
+    // generateDirichlet (trainmc.cpp:236-246): one MT draw per legal move, in edge order
+    uint32_t rnd[3];
+    rng_block(c, n, rnd);
+    float dv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int e = c.lane + 32 * j;
+      dv[j] = 0.0f;
+      if (e < n) {
+        dv[j] = d_gamma[rnd[j] & 1023u];
+        sm.f[e] = dv[j];
+      }
+    }
+    __syncwarp();
+    float dsum = 0.0f;
+    for (int j = 0; j < n; ++j) dsum = __fadd_rn(dsum, sm.f[j]);
+    const float dscalar =
+        __double2float_rn(__dmul_rn(__ddiv_rn(1.0, (double)dsum), (double)P.epsilon));
+    __syncwarp();
+    // setProbs (trainmc.cpp:248-267)
+    float wv[3];
+    float mx = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int e = c.lane + 32 * j;
+      wv[j] = 0.0f;
+      if (e < n) {
+        wv[j] = __fadd_rn(__fmul_rn(fv[j], scalar), __fmul_rn(dv[j], dscalar));
+        mx = fmaxf(mx, wv[j]);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, d));
+    const float denom = __fdiv_rn(511.0f, mx);
+    int qsum = 0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int e = c.lane + 32 * j;
+      if (e < n) {
+        // lround(): round half away from zero; exact in double for |x| < 2^51
+        const double x = (double)__fmul_rn(wv[j], denom);
+        const long long q = (long long)floor(x + 0.5);
+        const int prob = q < 1 ? 1 : (int)q;
+        r[8 + 4 * e + 3] = (w3[j] & ~(0x1ffu << 7)) | (((uint32_t)prob & 0x1ffu) << 7);
+        qsum += prob;
+      }
+    }
+    qsum = __reduce_add_sync(kFull, qsum);
+    if (c.lane == 0)
+      r[5] = __float_as_uint(__double2float_rn(__ddiv_rn(1.0, (double)(float)qsum)));
+    // backup (trainmc.cpp:281-292): the leaf takes e-1, its parent -e-1, ... up to the root
+    const float ev = eval[k];
+    for (int l0 = 0; l0 < path_len; l0 += 32) {
+      const int lvl = l0 + c.lane;  // index into path: 0 = child of root .. path_len-1 = leaf
+      if (lvl < path_len) {
+        const int dist = path_len - 1 - lvl;
+        const float ce = (dist & 1) ? -ev : ev;
+        const float d = __double2float_rn(__dsub_rn((double)ce, 1.0));
+        uint32_t *s = c.base + pd[2 + lvl];
+        s[0] = __float_as_uint(__fadd_rn(__uint_as_float(s[0]), d));
+        s[3] = s[3] & ~kS3Allv;
+      }
+    }
+    {
+      const float ce = (path_len & 1) ? -ev : ev;
+      c.root_eval = __fadd_rn(c.root_eval, __double2float_rn(__dsub_rn((double)ce, 1.0)));
+    }
+    __syncwarp();
+  }
+  c.root_allv = 0;
+  c.d_evals += np;
+  c.n_pending = 0;
+}
+
+// ---- TrainMC::search (trainmc.cpp:602-696) --------------------------------------------------
+__device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
+  ++c.searches_done;
+  int level = 0;
+  uint32_t node = 0;
+  int cur_result = c.root_result;
+  int cur_visits = c.root_visits;
+  float cur_eval = c.root_eval;
+  uint32_t cur_w3 = 0;
+  if (c.lane == 0) sm.node[0] = 0;
+  CState leaf_state{0, 0};
+  while (!r_terminal(cur_result)) {
+    const uint32_t *r = c.base + node;
+    const uint4 h0 = ld4(r);
+    const uint4 h1 = ld4(r + 4);
+    const int n = (int)(h1.x & 0xffu);
+    const int depth = (int)((h1.x >> 8) & 0xffu);
+    const float denominator = __uint_as_float(h1.y);
+    // chooseNext (trainmc.cpp:540-600). sqrt(float) binds to double sqrt(double).
+    const float v_sqrt =
+        __double2float_rn(__dmul_rn((double)P.c_puct, sqrt((double)(float)cur_visits)));
+    float best_u = -INFINITY;
+    int best_e = 0x7fffffff;
+    uint4 best_s = make_uint4(0, 0, 0, 0);
+    for (int e = c.lane; e < n; e += 32) {
+      const uint4 s = ld4(r + 8 + 4 * e);
+      const float prob = __fmul_rn((float)s3_prior(s.w), denominator);
+      float u = -INFINITY;
+      if (s3_has(s.w)) {
+        const int cr = s3_result(s.w);
+        if ((!r_known(cr) || r_drawn(cr)) && !s3_allv(s.w)) {
+          if (r_drawn(cr)) {
+            u = __fmul_rn(prob, v_sqrt);
+          } else {
+            const double cv = (double)(float)(int)s.y;
+            const double a = __ddiv_rn(-(double)__uint_as_float(s.x), cv);
+            const double b = __ddiv_rn((double)__fmul_rn(prob, v_sqrt), __dadd_rn(cv, 1.0));
+            u = __double2float_rn(__dadd_rn(a, b));
+          }
+        }
+      } else {
+        u = __fmul_rn(prob, v_sqrt);
+      }
+      u = __fadd_rn(u, 0.0f);  // -0.0 -> +0.0 so the integer key orders like operator>
+      if (u > best_u) best_u = u, best_e = e, best_s = s;
+    }
+    const uint32_t key = fkey(best_u);
+    const uint32_t kmax = __reduce_max_sync(kFull, key);
+    const bool none = (kmax == kKeyNegInf);
+    // virtual loss on the node we stand on (trainmc.cpp:611,625)
+    if (level == 0) {
+      c.root_visits += 1;
+      c.root_eval = __fadd_rn(c.root_eval, 1.0f);
+    } else if (c.lane == 0) {
+      uint32_t *s = c.base + sm.slot[level];
+      s[0] = __float_as_uint(__fadd_rn(cur_eval, 1.0f));
+      s[1] = (uint32_t)(cur_visits + 1);
+    }
+    if (none) {  // kNone (trainmc.cpp:629-643): flag, roll the whole path back, uncount
+      if (level == 0) {
+        c.root_allv = 1;
+      } else if (c.lane == 0) {
+        c.base[sm.slot[level] + 3] = cur_w3 | kS3Allv;
+      }
+      if (c.lane == 0) {
+        for (int l = level; l >= 1; --l) {
+          uint32_t *s = c.base + sm.slot[l];
+          s[0] = __float_as_uint(__fsub_rn(__uint_as_float(s[0]), 1.0f));
+          s[1] = s[1] - 1u;
+        }
+      }
+      c.root_visits -= 1;
+      c.root_eval = __fsub_rn(c.root_eval, 1.0f);
+      --c.searches_done;
+      __syncwarp();
+      return;
+    }
+    const int emin = __reduce_min_sync(kFull, key == kmax ? best_e : 0x7fffffff);
+    const int owner = emin & 31;
+    const uint32_t so = node + 8u + 4u * (uint32_t)emin;
+    const uint32_t ch_w3 = __shfl_sync(kFull, best_s.w, owner);
+    if (!s3_has(ch_w3)) {  // kNew: expand (trainmc.cpp:645-660)
+      if (level + 1 >= kMaxPath) {
+        c.error = CB200_ERR_OVERFLOW;
+        return;
+      }
+      CState ps;
+      ps.w0 = (uint64_t)h0.x | ((uint64_t)h0.y << 32);
+      ps.w1 = (uint64_t)h0.z | ((uint64_t)h0.w << 32);
+      leaf_state = do_move(ps, s3_move(ch_w3));
+      const uint32_t coff = c.used;
+      int result;
+      const int cn = make_record(c, P, leaf_state, depth + 1, result);
+      if (cn < 0) return;
+      if (c.lane == 0) {
+        const float e0 = r_terminal(result) ? (result == kResultDraw ? 0.0f : -1.0f) : 1.0f;
+        st4(c.base + so, make_uint4(__float_as_uint(e0), 1u, coff,
+                                    (ch_w3 & 0xffffu) | ((uint32_t)result << 16) | kS3Allv |
+                                        kS3Has | ((uint32_t)cn << 21)));
+        if (level > 0 && !s3_gc(cur_w3)) c.base[sm.slot[level] + 3] = cur_w3 | kS3Gc;
+        sm.node[level + 1] = coff;
+        sm.slot[level + 1] = so;
+      }
+      ++level;
+      node = coff;
+      cur_result = result;
+      __syncwarp();
+      break;
+    }
+    // existing child: descend
+    const uint32_t ch_off = __shfl_sync(kFull, best_s.z, owner);
+    cur_eval = __uint_as_float(__shfl_sync(kFull, best_s.x, owner));
+    cur_visits = (int)__shfl_sync(kFull, best_s.y, owner);
+    cur_w3 = ch_w3;
+    cur_result = s3_result(ch_w3);
+    ++level;
+    if (c.lane == 0) {
+      sm.node[level] = ch_off;
+      sm.slot[level] = so;
+    }
+    node = ch_off;
+    __syncwarp();
+  }
+  if (r_terminal(cur_result)) {
+    // propagateTerminal (trainmc.cpp:497-538) along the explicit path
+    int l = level;
+    int res_l = cur_result;
+    while (l != 0) {
+      if (r_lost(res_l)) {
+        --l;
+        if (l == 0) {
+          c.root_result = kDeducedWin;
+        } else if (c.lane == 0) {
+          uint32_t *w = c.base + sm.slot[l] + 3;
+          *w = (*w & ~(7u << 16)) | ((uint32_t)kDeducedWin << 16);
+        }
+      } else {
+        --l;
+        const uint32_t *pr = c.base + sm.node[l];
+        const int pn = (int)(pr[4] & 0xffu);
+        bool ok = true;
+        for (int e = c.lane; e < pn; e += 32) {
+          const uint32_t w = pr[8 + 4 * e + 3];
+          if (!s3_has(w) || !r_known(s3_result(w))) ok = false;
+        }
+        if (!__all_sync(kFull, ok)) break;
+        // Q4: the drawn() test is on the parent itself
+        const int pres = (l == 0) ? c.root_result : s3_result(c.base[sm.slot[l] + 3]);
+        const int nr = r_drawn(pres) ? kDeducedDraw : kDeducedLoss;
+        if (l == 0) {
+          c.root_result = nr;
+        } else if (c.lane == 0) {
+          uint32_t *w = c.base + sm.slot[l] + 3;
+          *w = (*w & ~(7u << 16)) | ((uint32_t)nr << 16);
+        }
+      }
+      __syncwarp();
+      res_l = (l == 0) ? c.root_result : s3_result(c.base[sm.slot[l] + 3]);
+    }
+    // terminal backup (trainmc.cpp:666-682): leaf value was stored at creation
+    float ce = (cur_result == kResultDraw) ? 0.0f : -1.0f;
+    for (int lv = level - 1; lv >= 1; --lv) {
+      if (c.lane == 0) {
+        uint32_t *s = c.base + sm.slot[lv];
+        s[0] = __float_as_uint(
+            __fadd_rn(__uint_as_float(s[0]), __double2float_rn(__dsub_rn((double)ce, 1.0))));
+      }
+      ce = -ce;
+    }
+    c.root_eval = __fadd_rn(c.root_eval, __double2float_rn(__dsub_rn((double)ce, 1.0)));
+    __syncwarp();
+  } else {
+    // request an evaluation (trainmc.cpp:684-691): remember the leaf and the path to it
+    uint32_t *pd = c.pending + c.n_pending * kPendWords;
+    if (c.lane == 0) {
+      pd[0] = node, pd[1] = (uint32_t)level;
+      c.leaf_state[c.n_pending] = make_ulonglong2(leaf_state.w0, leaf_state.w1);
+    }
+    for (int lv = 1 + c.lane; lv <= level; lv += 32) pd[2 + lv - 1] = sm.slot[lv];
+    c.n_pending += 1;
+    __syncwarp();
+  }
+}
+
+// ---- TrainMC::doIteration (trainmc.cpp:139-178) ---------------------------------------------
+__device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, WarpSm &sm,
+                                                  const float *eval, const float *probs) {
+  if (!c.has_root) {
+    fresh_tree(c, P, start_state(), 0);
+    c.searches_done = 1;
+    request_root(c);
+    return false;
+  }
+  if (c.searches_done == 0 && c.root_visits == 1 && c.root_allv) {
+    c.searches_done = 1;
+    request_root(c);
+    return false;
+  }
+  if (c.n_pending > 0) receive_eval(c, P, sm, eval, probs);
+  while (c.n_pending < P.spe && c.searches_done < P.max_searches && !r_known(c.root_result) &&
+         !c.root_allv && !c.error) {
+    search(c, P, sm);
+  }
+  return (c.searches_done == P.max_searches || r_known(c.root_result)) && c.n_pending == 0;
+}
+
+// TrainMC::chooseHighProbMove (trainmc.cpp:298-308) incl. the int32 max_prob quirk (Q3)
+__device__ __forceinline__ int choose_high_prob(Ctx &c, WarpSm &sm) {
+  const uint32_t *r = c.base;
+  const int n = (int)(r[4] & 0xffu);
+  const float denominator = __uint_as_float(r[5]);
+  for (int e = c.lane; e < n; e += 32)
+    sm.f[e] = __fmul_rn((float)s3_prior(r[8 + 4 * e + 3]), denominator);
+  __syncwarp();
+  int max_prob = 0, idx = -1;
+  for (int i = 0; i < n; ++i) {
+    const float pr = sm.f[i];
+    if (pr > (float)max_prob) max_prob = (int)pr, idx = i;
+  }
+  __syncwarp();
+  return idx < 0 ? 0 : s3_move(r[8 + 4 * idx + 3]);
+}
+
+// "Reset tree" (trainmc.cpp:397-404, 461-468): single node reached by `move` from the root
+__device__ __forceinline__ void reset_tree_after(Ctx &c, const TreeParams &P, int move) {
+  const CState st = do_move(rec_state(c.base), move);
+  const int depth = (int)((c.base[4] >> 8) & 0xffu) + 1;
+  __syncwarp();
+  fresh_tree(c, P, st, depth);
+  c.searches_done = 0;
+}
+
+// first slot index (ascending) whose lane predicate holds; -1 if none. Warp-uniform result.
+#define CB_FOR_SLOTS(n, e, j) \
+  for (int j = 0, e = c.lane; j < 3 && 32 * j < (n); ++j, e += 32)
+
+// ---- TrainMC::chooseMove (trainmc.cpp:110-137, 310-473) -------------------------------------
+__device__ __noinline__ int choose_move(Ctx &c, const TreeParams &P, WarpSm &sm,
+                                        float *prob_sample) {
+  const uint32_t *r = c.base;
+  const int n = (int)(r[4] & 0xffu);
+  const int depth = (int)((r[4] >> 8) & 0xffu);
+  uint4 sl[3];
+  CB_FOR_SLOTS(96, e, j) sl[j] = (e < n) ? ld4(r + 8 + 4 * e) : make_uint4(0, 0, 0, 0);
+  const bool root_lost = r_lost(c.root_result);
+  if (r_won(c.root_result) || root_lost || r_drawn(c.root_result)) {
+    // chooseMoveWon: first lost child. chooseMoveLostDrawn: most visited (first on ties),
+    // skipping won children unless the root is lost.
+    const bool won = r_won(c.root_result);
+    int best_key = -1, best_e = 0x7fffffff;
+    CB_FOR_SLOTS(96, e, j) {
+      if (e < n && s3_has(sl[j].w)) {
+        const int cr = s3_result(sl[j].w);
+        int key = -1;
+        if (won) {
+          if (r_lost(cr)) key = 1;
+        } else if ((int)sl[j].y > 0 && (root_lost || !r_won(cr))) {
+          key = (int)sl[j].y;
+        }
+        if (key > best_key) best_key = key, best_e = e;
+      }
+    }
+    const int kmax = __reduce_max_sync(kFull, best_key);
+    if (kmax < 0) {  // unreachable in the reference (null dereference there); fail loudly
+      c.error = CB200_ERR_STATE;
+      return 0;
+    }
+    const int emin = __reduce_min_sync(kFull, best_key == kmax ? best_e : 0x7fffffff);
+    const int choice = s3_move(r[8 + 4 * emin + 3]);
+    if (prob_sample && c.lane == 0) prob_sample[choice] = 1.0f;
+    move_down(c, P, emin);
+    return choice;
+  }
+  if (depth < 6 && !P.testing) {  // chooseMoveOpening (trainmc.cpp:375-436)
+    int choice = choose_high_prob(c, sm);
+    int vis = 0;
+    CB_FOR_SLOTS(96, e, j)
+    if (e < n && s3_has(sl[j].w) && !r_won(s3_result(sl[j].w))) vis += (int)sl[j].y;
+    const int visits = __reduce_add_sync(kFull, vis);
+    const float denominator = __double2float_rn(__ddiv_rn(1.0, (double)(float)visits));
+    CB_FOR_SLOTS(96, e, j)
+    if (e < n && s3_has(sl[j].w) && !r_won(s3_result(sl[j].w)))
+      prob_sample[s3_move(sl[j].w)] = __fmul_rn((float)(int)sl[j].y, denominator);
+    if (visits == 0) {
+      if (c.lane == 0) prob_sample[choice] = 1.0f;
+      reset_tree_after(c, P, choice);
+      return choice;
+    }
+    const int target = (int)(rng_one(c) % (uint32_t)visits);
+    int carry = 0, found = -1;
+    for (int j = 0; j < 3 && 32 * j < n && found < 0; ++j) {
+      const int e = c.lane + 32 * j;
+      const bool elig = e < n && s3_has(sl[j].w) && !r_won(s3_result(sl[j].w));
+      const uint32_t v = elig ? sl[j].y : 0u;
+      const uint32_t incl = warp_incl_scan(v, c.lane) + (uint32_t)carry;
+      const unsigned hit = __ballot_sync(kFull, elig && (int)incl > target);
+      if (hit) found = 32 * j + (__ffs((int)hit) - 1);
+      carry = (int)__shfl_sync(kFull, incl, 31);
+    }
+    choice = s3_move(r[8 + 4 * found + 3]);
+    move_down(c, P, found);
+    return choice;
+  }
+  // chooseMoveNormal (trainmc.cpp:438-473): most visited non-won child, ties by evaluation
+  // (draws count 0), first wins; start values (0, 0.0)
+  int choice = choose_high_prob(c, sm);
+  int bv = 0, be = 0x7fffffff;
+  float bf = 0.0f;
+  CB_FOR_SLOTS(96, e, j) {
+    if (e < n && s3_has(sl[j].w) && !r_won(s3_result(sl[j].w))) {
+      const int cr = s3_result(sl[j].w);
+      float ev = __uint_as_float(sl[j].x);
+      if (cr == kResultDraw || cr == kDeducedDraw) ev = 0.0f;
+      ev = __fadd_rn(ev, 0.0f);
+      const int cv = (int)sl[j].y;
+      if (cv > bv || (cv == bv && ev > bf)) bv = cv, bf = ev, be = e;
+    }
+  }
+  const int vmax = __reduce_max_sync(kFull, bv);
+  const uint32_t fk = (bv == vmax && be != 0x7fffffff) ? fkey(bf) : 0u;
+  const uint32_t fmax = __reduce_max_sync(kFull, fk);
+  const int emin =
+      __reduce_min_sync(kFull, (bv == vmax && be != 0x7fffffff && fk == fmax) ? be : 0x7fffffff);
+  if (emin != 0x7fffffff) choice = s3_move(r[8 + 4 * emin + 3]);
+  if (prob_sample && c.lane == 0) prob_sample[choice] = 1.0f;
+  if (vmax == 0 || emin == 0x7fffffff) {
+    reset_tree_after(c, P, choice);
+    return choice;
+  }
+  move_down(c, P, emin);
+  return choice;
+}
+
+// ---- TrainMC::receiveOpponentMove (trainmc.cpp:180-204) -------------------------------------
+__device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &P, int move,
+                                                      const CState &st, int depth) {
+  const uint32_t *r = c.base;
+  const int n = (int)(r[4] & 0xffu);
+  int found = 0x7fffffff;
+  for (int e = c.lane; e < n; e += 32) {
+    const uint32_t w = r[8 + 4 * e + 3];
+    if (s3_has(w) && s3_move(w) == move) found = e;
+  }
+  found = __reduce_min_sync(kFull, found);
+  if (found != 0x7fffffff) {
+    move_down(c, P, found);
+    return false;
+  }
+  fresh_tree(c, P, st, depth);
+  request_root(c);
+  c.searches_done = 1;
+  return true;
+}
+
+// ---- SelfPlayer::chooseMoveAndContinue (selfplayer.cpp:246-291) -----------------------------
+__device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &P, WarpSm &sm) {
+  bool need_eval = false;
+  while (!need_eval) {
+    if (r_known(c.root_result) && c.mate_turn == 0) c.mate_turn = c.n_samples + 1;
+    c.d_sims += c.searches_done;
+    c.d_moves += 1;
+    int choice;
+    if (!P.testing) {  // SelfPlayer::chooseMove (selfplayer.cpp:234-244)
+      if (c.n_samples >= kMaxSamples) {
+        c.error = CB200_ERR_OVERFLOW;
+        return true;
+      }
+      float *ps = c.sample_probs + (size_t)c.n_samples * CB200_NUM_MOVES;
+      for (int j = c.lane; j < CB200_NUM_MOVES; j += 32) ps[j] = 0.0f;
+      if (c.lane == 0) {
+        const uint4 h = ld4(c.base);
+        c.sample_state[c.n_samples] = make_ulonglong2((uint64_t)h.x | ((uint64_t)h.y << 32),
+                                                      (uint64_t)h.z | ((uint64_t)h.w << 32));
+      }
+      __syncwarp();
+      choice = choose_move(c, P, sm, ps);
+      c.n_samples += 1;
+    } else {
+      choice = choose_move(c, P, sm, nullptr);
+    }
+    if (c.error) return true;
+    __syncwarp();
+    if (r_terminal(c.root_result)) {  // endGame (selfplayer.cpp:206-232)
+      if (c.root_result == kResultDraw)
+        c.result = kResultDraw;
+      else if (c.to_play == 1)
+        c.result = kResultLoss;
+      else
+        c.result = kResultWin;
+      c.has_root = 0;
+      store_tree(c);
+      load_tree(c, P, 1 - c.cur_p);
+      c.has_root = 0;
+      return true;
+    }
+    const CState st = rec_state(c.base);
+    const int depth = (int)((c.base[4] >> 8) & 0xffu);
+    c.to_play = 1 - c.to_play;
+    store_tree(c);
+    load_tree(c, P, c.to_play);
+    if (!c.has_root) {
+      fresh_tree(c, P, st, depth);
+      c.searches_done = 0;
+      return tree_do_iteration(c, P, sm, nullptr, nullptr);  // false: the root needs an eval
+    }
+    need_eval = receive_opponent_move(c, P, choice, st, depth);
+    if (c.error) return true;
+    if (!need_eval) need_eval = !tree_do_iteration(c, P, sm, nullptr, nullptr);
+    if (c.error) return true;
+  }
+  return false;
+}
+
+// Which games take part in this call (trainer.cpp:39-49, 79-101, 164-236)
+__device__ __forceinline__ bool game_selected(const int32_t *ctl, int to_play) {
+  if (ctl[CW_DONE]) return false;
+  if (to_play != 0 && to_play != 1) return true;
+  return ctl[CW_TO_PLAY] == ((to_play + ctl[CW_PARITY]) & 1);
+}
+
+// One SelfPlayer::doIteration per warp. offs[g] = index of game g's first answer row in
+// eval/probs (exclusive prefix sum of the request counts the answers were produced for).
+__global__ void __launch_bounds__(kTreeWarps * 32)
+    k_iterate(TreeParams P, const float *__restrict__ eval, const float *__restrict__ probs,
+              const int32_t *__restrict__ offs, int to_play, int iteration, int stagger_div) {
+  __shared__ WarpSm sm_all[kTreeWarps];
+  const int warp = threadIdx.x >> 5;
+  const int g = blockIdx.x * kTreeWarps + warp;
+  if (g >= P.num_games) return;
+  int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+  if (!game_selected(ctl, to_play)) return;
+  const bool training = (to_play != 0 && to_play != 1);
+  // staggered start (trainer.cpp:184-186), on the global game index
+  if (training && stagger_div > 0 && (P.first_game + g) / stagger_div > iteration) return;
+  WarpSm &sm = sm_all[warp];
+  Ctx c;
+  c.lane = threadIdx.x & 31;
+  c.to_play = ctl[CW_TO_PLAY], c.parity = ctl[CW_PARITY], c.result = ctl[CW_RESULT];
+  c.mate_turn = ctl[CW_MATE_TURN], c.n_samples = ctl[CW_N_SAMPLES];
+  c.n_pending = ctl[CW_N_PENDING], c.error = ctl[CW_ERROR], c.spare = ctl[CW_SPARE];
+  c.mt_idx = ctl[CW_MT_IDX];
+  c.d_sims = 0, c.d_evals = 0, c.d_moves = 0;
+  c.arenas = P.arenas + (size_t)g * 3 * P.arena_words;
+  c.mt = P.mt + (size_t)g * 624;
+  c.pending = P.pending + (size_t)g * P.spe * kPendWords;
+  c.tree_ctl = P.tree + (size_t)g * 2 * kTreeCtlWords;
+  c.leaf_state = P.leaf_state + (size_t)g * P.spe;
+  c.sample_state = P.sample_state + (size_t)g * kMaxSamples;
+  c.sample_probs = P.sample_probs + (size_t)g * kMaxSamples * CB200_NUM_MOVES;
+  load_tree(c, P, c.to_play);
+  const int off = offs[g];
+  // SelfPlayer::doIteration (selfplayer.cpp:115-122)
+  bool done = tree_do_iteration(c, P, sm, eval + off, probs + (size_t)off * CB200_NUM_MOVES);
+  if (!c.error && done) done = choose_move_and_continue(c, P, sm);
+  if (c.error) done = true;
+  store_tree(c);
+  if (c.lane == 0) {
+    ctl[CW_TO_PLAY] = c.to_play, ctl[CW_RESULT] = c.result, ctl[CW_MATE_TURN] = c.mate_turn;
+    ctl[CW_N_SAMPLES] = c.n_samples, ctl[CW_N_PENDING] = c.n_pending, ctl[CW_ERROR] = c.error;
+    ctl[CW_SPARE] = c.spare, ctl[CW_MT_IDX] = c.mt_idx;
+    if (done) ctl[CW_DONE] = 1;
+    long long *cnt = P.counters + (size_t)g * 4;
+    cnt[0] += c.d_sims, cnt[1] += c.d_moves, cnt[2] += c.d_evals;
+  }
+}
+
+// Exclusive prefix sum of the request counts of the selected games (single CTA).
+// summary = {total requests, games not done, error code of any game}
+__global__ void __launch_bounds__(1024)
+    k_scan_requests(TreeParams P, int to_play, int32_t *__restrict__ offs,
+                    int32_t *__restrict__ summary) {
+  __shared__ int s_part[1024];
+  __shared__ int s_live, s_err;
+  const int t = threadIdx.x;
+  if (t == 0) s_live = 0, s_err = 0;
+  __syncthreads();
+  const int per = (P.num_games + 1023) / 1024;
+  const int g0 = t * per, g1 = min(P.num_games, g0 + per);
+  int sum = 0, live = 0, err = 0;
+  for (int g = g0; g < g1; ++g) {
+    const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+    if (game_selected(ctl, to_play)) sum += ctl[CW_N_PENDING];
+    if (!ctl[CW_DONE]) ++live;
+    if (ctl[CW_ERROR]) err = ctl[CW_ERROR];
+  }
+  s_part[t] = sum;
+  if (live) atomicAdd(&s_live, live);
+  if (err) atomicMin(&s_err, err);
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 1024 partials
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = (t >= d) ? s_part[t - d] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = s_part[t] - sum;
+  for (int g = g0; g < g1; ++g) {
+    const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+    offs[g] = run;
+    if (game_selected(ctl, to_play)) run += ctl[CW_N_PENDING];
+  }
+  if (t == 1023) summary[0] = s_part[1023];
+  if (t == 0) summary[1] = s_live, summary[2] = s_err;
+}
+
+// Trainer::writeRequests (trainer.cpp:79-101): expand the queued leaf states of the selected
+// games to 70-float rows, game-index-major; also emits the packed cstates for the fused net.
+__global__ void __launch_bounds__(256)
+    k_pack_requests(TreeParams P, int to_play, const int32_t *__restrict__ offs,
+                    float *__restrict__ rows, ulonglong2 *__restrict__ packed) {
+  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= P.num_games) return;
+  const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+  if (!game_selected(ctl, to_play)) return;
+  const int np = ctl[CW_N_PENDING];
+  const ulonglong2 *ls = P.leaf_state + (size_t)g * P.spe;
+  const size_t off = (size_t)offs[g];
+  if (packed)
+    for (int k = lane; k < np; k += 32) packed[off + k] = ls[k];
+  if (rows) {
+    float *out = rows + off * CB200_STATE_SIZE;
+    for (int f = lane; f < np * CB200_STATE_SIZE; f += 32) {
+      const int k = f / CB200_STATE_SIZE, j = f - k * CB200_STATE_SIZE;
+      const ulonglong2 v = ls[k];
+      out[f] = encode_elem(CState{v.x, v.y}, j);
+    }
+  }
+}
+
+}  // namespace cb200
+#endif

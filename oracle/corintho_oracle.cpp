@@ -7,8 +7,8 @@
 //                  node.cpp:273-282) and, once the move has been tried, the statistics of the
 //                  child reached through it (the reference keeps those in the child Node,
 //                  node.h:150-186):
-//                  s0 = child record offset, s1 = child evaluation_ (f32 bits),
-//                  s2 = child visits_, s3 = move | prior<<7 | result<<16 | all_visited<<19 |
+//                  s0 = child evaluation_ (f32 bits), s1 = child visits_,
+//                  s2 = child record offset, s3 = move | prior<<7 | result<<16 | all_visited<<19 |
 //                       has_child<<20 | child_n_legal<<21
 // The root record sits at offset 0; the root's own statistics live in the Tree struct.
 // Re-rooting (TrainMC::moveDown, trainmc.cpp:475-495) copies the kept subtree breadth-first
@@ -272,6 +272,8 @@ struct MT {
 };
 
 // ------------------------------------------------------------------------------------------
+// Slot word order (same as the CUDA engine, corintho_ai_b200/csrc/tree.cuh)
+constexpr int kSEval = 0, kSVis = 1, kSOff = 2;
 // Slot word s3 bit fields
 inline int s3_move(uint32_t w) { return w & 0x7f; }
 inline int s3_prior(uint32_t w) { return (w >> 7) & 0x1ff; }
@@ -364,7 +366,7 @@ int make_record(GameRec &g, Tree &t, const Params &p, const State &st, int depth
   for (int i = 0; i < kNumMoves; ++i)
     if (m.get(i)) {
       uint32_t *s = r + 8 + 4 * e++;
-      s[0] = 0, s[1] = 0, s[2] = 0, s[3] = (uint32_t)i;
+      s[kSOff] = 0, s[kSEval] = 0, s[kSVis] = 0, s[3] = (uint32_t)i;
     }
   t.used = off + 8 + 4 * n;
   *result = n == 0 ? (lines ? kResultLoss : kResultDraw) : kResultNone;
@@ -408,12 +410,12 @@ void move_down(GameRec &g, Tree &t, int e) {
   uint32_t *slot = src + 8 + 4 * e;
   int dst_id = g.spare;
   uint32_t *dst = g.arena[dst_id].data();
-  t.root_eval = bits_f(slot[1]);
-  t.root_visits = (int)slot[2];
+  t.root_eval = bits_f(slot[kSEval]);
+  t.root_visits = (int)slot[kSVis];
   t.root_result = s3_result(slot[3]);
   t.root_allv = s3_allv(slot[3]);
   uint32_t sz = 8 + 4 * (uint32_t)s3_cnl(slot[3]);
-  memcpy(dst, src + slot[0], sz * 4);
+  memcpy(dst, src + slot[kSOff], sz * 4);
   uint32_t scan = 0, alloc = sz;
   while (scan < alloc) {
     uint32_t *r = dst + scan;
@@ -422,8 +424,8 @@ void move_down(GameRec &g, Tree &t, int e) {
       uint32_t *s = r + 8 + 4 * k;
       if (s3_has(s[3])) {
         uint32_t csz = 8 + 4 * (uint32_t)s3_cnl(s[3]);
-        memcpy(dst + alloc, src + s[0], csz * 4);
-        s[0] = alloc;
+        memcpy(dst + alloc, src + s[kSOff], csz * 4);
+        s[kSOff] = alloc;
         alloc += csz;
       }
     }
@@ -479,7 +481,7 @@ void receive_eval(GameRec &g, Tree &t, const Params &p, const float *eval, const
     for (int lvl = pd.path_len - 1; lvl >= 0; --lvl) {
       uint32_t *s = base + pd.path[lvl];
       float d = cur_eval - 1.0;
-      s[1] = f_bits(bits_f(s[1]) + d);
+      s[kSEval] = f_bits(bits_f(s[kSEval]) + d);
       s[3] = s3_set_allv(s[3], false);
       cur_eval *= -1.0;
     }
@@ -521,8 +523,8 @@ void search(GameRec &g, Tree &t, const Params &p) {
           if (r_drawn(cr)) {
             u = prob * v_sqrt;
           } else {
-            int cv = (int)s[2];
-            u = -1.0 * bits_f(s[1]) / static_cast<float>(cv) +
+            int cv = (int)s[kSVis];
+            u = -1.0 * bits_f(s[kSEval]) / static_cast<float>(cv) +
                 prob * v_sqrt / (static_cast<float>(cv) + 1.0);
           }
         }
@@ -541,8 +543,8 @@ void search(GameRec &g, Tree &t, const Params &p) {
         t.root_eval += de;
       } else {
         uint32_t *s = base + slot_off[lvl];
-        s[2] = (uint32_t)((int)s[2] + dv);
-        s[1] = f_bits(bits_f(s[1]) + de);
+        s[kSVis] = (uint32_t)((int)s[kSVis] + dv);
+        s[kSEval] = f_bits(bits_f(s[kSEval]) + de);
       }
     };
     bump(level, +1, 1.0f);
@@ -569,9 +571,9 @@ void search(GameRec &g, Tree &t, const Params &p) {
       if (cn < 0) return;
       base = g.arena[t.arena].data();
       s = base + so;
-      s[0] = coff;
-      s[1] = f_bits(0.0f);
-      s[2] = 1;
+      s[kSOff] = coff;
+      s[kSEval] = f_bits(0.0f);
+      s[kSVis] = 1;
       s[3] = (s[3] & 0xffffu) | ((uint32_t)result << 16) | (1u << 19) | (1u << 20) |
              ((uint32_t)cn << 21);
       ++level;
@@ -582,10 +584,10 @@ void search(GameRec &g, Tree &t, const Params &p) {
       break;
     }
     ++level;
-    node_off[level] = s[0];
+    node_off[level] = s[kSOff];
     slot_off[level] = so;
     cur_result = s3_result(s[3]);
-    cur_visits = (int)s[2];
+    cur_visits = (int)s[kSVis];
   }
   if (r_terminal(cur_result)) {
     // ---- propagateTerminal (trainmc.cpp:497-538)
@@ -627,17 +629,17 @@ void search(GameRec &g, Tree &t, const Params &p) {
     // ---- terminal backup (trainmc.cpp:666-682)
     float cur_eval = -1.0;
     if (r_drawn(cur_result)) cur_eval = 0.0;
-    base[slot_off[level] + 1] = f_bits(cur_eval);
+    base[slot_off[level] + kSEval] = f_bits(cur_eval);
     for (int l = level - 1; l >= 0; --l) {
       float d = cur_eval - 1.0;
       if (l == 0)
         t.root_eval += d;
       else
-        base[slot_off[l] + 1] = f_bits(bits_f(base[slot_off[l] + 1]) + d);
+        base[slot_off[l] + kSEval] = f_bits(bits_f(base[slot_off[l] + kSEval]) + d);
       cur_eval *= -1.0;
     }
   } else {
-    base[slot_off[level] + 1] = f_bits(1.0f);
+    base[slot_off[level] + kSEval] = f_bits(1.0f);
     Pending pd;
     pd.leaf_off = node_off[level];
     pd.path_len = level;
@@ -720,7 +722,7 @@ int choose_move(GameRec &g, Tree &t, const Params &p, float *prob_sample) {
     int max_visits = 0, choice = 0, best = -1;
     for (int e = 0; e < n; ++e) {
       if (!s3_has(slot(e)[3])) continue;
-      int cv = (int)slot(e)[2];
+      int cv = (int)slot(e)[kSVis];
       if (cv > max_visits && (r_lost(t.root_result) || !r_won(s3_result(slot(e)[3])))) {
         choice = s3_move(slot(e)[3]);
         best = e;
@@ -739,12 +741,12 @@ int choose_move(GameRec &g, Tree &t, const Params &p, float *prob_sample) {
     int choice = choose_high_prob(g, t);
     int visits = 0;
     for (int e = 0; e < n; ++e)
-      if (s3_has(slot(e)[3]) && !r_won(s3_result(slot(e)[3]))) visits += (int)slot(e)[2];
+      if (s3_has(slot(e)[3]) && !r_won(s3_result(slot(e)[3]))) visits += (int)slot(e)[kSVis];
     float denominator = 1.0 / static_cast<float>(visits);
     if (prob_sample)
       for (int e = 0; e < n; ++e)
         if (s3_has(slot(e)[3]) && !r_won(s3_result(slot(e)[3])))
-          prob_sample[s3_move(slot(e)[3])] = static_cast<float>((int)slot(e)[2]) * denominator;
+          prob_sample[s3_move(slot(e)[3])] = static_cast<float>((int)slot(e)[kSVis]) * denominator;
     if (visits == 0) {
       prob_sample[choice] = 1.0;
       reset_tree_after(g, t, p, choice);
@@ -754,7 +756,7 @@ int choose_move(GameRec &g, Tree &t, const Params &p, float *prob_sample) {
     int total = 0, best = -1;
     for (int e = 0; e < n; ++e)
       if (s3_has(slot(e)[3]) && !r_won(s3_result(slot(e)[3]))) {
-        total += (int)slot(e)[2];
+        total += (int)slot(e)[kSVis];
         if (total > target) {
           choice = s3_move(slot(e)[3]);
           best = e;
@@ -773,9 +775,9 @@ int choose_move(GameRec &g, Tree &t, const Params &p, float *prob_sample) {
     if (!s3_has(slot(e)[3])) continue;
     int cr = s3_result(slot(e)[3]);
     if (r_won(cr)) continue;
-    float ev = bits_f(slot(e)[1]);
+    float ev = bits_f(slot(e)[kSEval]);
     if (cr == kResultDraw || cr == kDeducedDraw) ev = 0.0;
-    int cv = (int)slot(e)[2];
+    int cv = (int)slot(e)[kSVis];
     if (cv > max_visits || (cv == max_visits && ev > max_eval)) {
       choice = s3_move(slot(e)[3]);
       best = e;

@@ -236,7 +236,8 @@ def synth_eval(game_states):
     return ev.astype(np.float32), np.ascontiguousarray(pr, np.float32)
 
 
-def play_out(trainer, evaluator=synth_eval, to_play=-1, record=None, max_iters=10_000_000):
+def play_out(trainer, evaluator=synth_eval, to_play=-1, record=None, max_iters=10_000_000,
+             allow_empty=False):
     """Drive a Trainer-like object exactly like main.pyx:142-170 (play_games).
 
     ``record``: optional list receiving (n_requests, request_rows.copy()) per iteration.
@@ -253,6 +254,8 @@ def play_out(trainer, evaluator=synth_eval, to_play=-1, record=None, max_iters=1
         if n == 0:
             if to_play != -1:
                 to_play = 1 - to_play
+                continue
+            if allow_empty:  # a shard whose staggered games have not started yet
                 continue
             raise RuntimeError("No requests during training")
         req = trainer.write_requests(to_play)

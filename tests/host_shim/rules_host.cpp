@@ -1,0 +1,30 @@
+// TEST INFRASTRUCTURE: compiles the product's SWAR rules header (corintho_ai_b200/csrc/rules.cuh)
+// for the HOST so its logic can be checked against the oracle on machines without a GPU.
+// This is not a CPU fallback: nothing in the product links it.
+#include <stdint.h>
+#include "../../corintho_ai_b200/csrc/corintho_tables.h"
+#include "../../corintho_ai_b200/csrc/rules.cuh"
+
+extern "C" void shim_step_batch(int64_t n, const uint64_t *states, uint64_t seed, uint32_t *maskflags,
+                                uint64_t *next, float *enc) {
+  using namespace cb200;
+  auto LB = [](int idx) { return kCLineBreakers[idx]; };
+  for (int64_t i = 0; i < n; ++i) {
+    CState s{states[2 * i], states[2 * i + 1]};
+    uint32_t m[3];
+    bool lines = legal_moves(s, m, LB);
+    int nl = cb_popc(m[0]) + cb_popc(m[1]) + cb_popc(m[2]);
+    int result = terminal_result(nl, lines);
+    int chosen = 0x7f;
+    CState o = s;
+    if (nl > 0) {
+      chosen = nth_move(m, (int)(step_rnd(seed, (uint64_t)i) % (uint32_t)nl));
+      o = do_move(s, chosen);
+    }
+    maskflags[4 * i] = m[0], maskflags[4 * i + 1] = m[1], maskflags[4 * i + 2] = m[2];
+    maskflags[4 * i + 3] = (uint32_t)result | (lines ? 4u : 0u) | ((uint32_t)nl << 8) | ((uint32_t)chosen << 16);
+    next[2 * i] = o.w0, next[2 * i + 1] = o.w1;
+    if (enc) for (int j = 0; j < 70; ++j) enc[70 * i + j] = encode_elem(s, j);
+  }
+}
+extern "C" uint32_t shim_step_rnd(uint64_t seed, uint64_t i) { return cb200::step_rnd(seed, i); }

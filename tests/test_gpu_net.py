@@ -1,0 +1,101 @@
+"""Network kernels and the fused (device-resident) self-play loop."""
+import numpy as np
+import pytest
+
+import corintho_ai_b200 as cb
+from netref import forward_folded
+from oracle.pyoracle import synth_eval
+from util import run_trainer
+
+pytestmark = pytest.mark.gpu
+
+
+def sample_positions(oracle, n, seed=1):
+    rng = np.random.default_rng(seed)
+    rows = []
+    while len(rows) < n:
+        st = oracle.start()
+        for _ in range(40):
+            rows.append(oracle.encode(st))
+            mask, _ = oracle.legal(st)
+            ids = [m for m in range(96) if (mask[m >> 5] >> (m & 31)) & 1]
+            if not ids:
+                break
+            st = oracle.do_move(st, int(rng.choice(ids)))
+    return np.stack(rows[:n])
+
+
+def test_fp32_network_matches_numpy(oracle):
+    """Stated tolerance (BASELINE.json north_star): 1e-5 relative in fp32."""
+    x = sample_positions(oracle, 1000)
+    flat = cb.fold_batchnorm(cb.random_weights(11))
+    t = cb.Trainer(64, "", 1, 32, 16)
+    t.set_weights(flat, 0, "fp32")
+    ev, pr = t.evaluate(x)
+    v64, p64 = forward_folded(flat, x, np.float64)
+    assert np.max(np.abs(ev - v64) / np.maximum(np.abs(v64), 1e-3)) < 1e-5
+    assert np.max(np.abs(pr - p64) / p64) < 1e-5
+    assert np.allclose(pr.sum(1), 1.0, atol=1e-5)
+
+
+def test_fp32_network_ragged_batches(oracle):
+    x = sample_positions(oracle, 300, seed=3)
+    flat = cb.fold_batchnorm(cb.random_weights(12))
+    t = cb.Trainer(32, "", 1, 32, 16)
+    t.set_weights(flat, 0, "fp32")
+    full_e, full_p = t.evaluate(x)
+    for n in (1, 127, 128, 129, 255):
+        e, p = t.evaluate(x[:n])
+        assert e.tobytes() == full_e[:n].tobytes() and p.tobytes() == full_p[:n].tobytes()
+
+
+def test_fused_selfplay_equals_oracle_driven_by_the_same_network(oracle):
+    """Fused mode keeps everything on the device. Driving the ORACLE with the engine's own
+    network outputs (same kernel, so bit-identical evaluations) must reproduce the fused run:
+    samples, results and exact simulation counters."""
+    flat = cb.fold_batchnorm(cb.random_weights(21))
+    cfg = dict(num_games=24, seed=9, max_searches=64, searches_per_eval=16, c_puct=1.0, epsilon=0.25)
+    fused = cb.Trainer(cfg["num_games"], "", cfg["seed"], cfg["max_searches"], cfg["searches_per_eval"],
+                       cfg["c_puct"], cfg["epsilon"])
+    fused.set_weights(flat, 0, "fp32")
+    assert fused.run_selfplay(0, stagger=True)
+    helper = cb.Trainer(cfg["num_games"], "", 1, 16, cfg["searches_per_eval"])
+    helper.set_weights(flat, 0, "fp32")
+    o = oracle.trainer(**cfg)
+    r = run_trainer(o, lambda req: helper.evaluate(req))
+    gs, ev, pr = fused.write_samples()
+    assert fused.num_samples() == r["num_samples"]
+    assert gs.tobytes() == r["samples"][0].tobytes()
+    assert ev.tobytes() == r["samples"][1].tobytes()
+    assert pr.tobytes() == r["samples"][2].tobytes()
+    assert fused.score().tobytes() == r["score"].tobytes()
+    oc, ec = oracle.counters(o), fused.counters()
+    assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
+
+
+def test_fused_testing_mode_two_models(oracle):
+    fa, fb = cb.fold_batchnorm(cb.random_weights(1)), cb.fold_batchnorm(cb.random_weights(2))
+    t = cb.Trainer(16, "", 4, 32, 8, 1.0, 0.0, 0, 1, True)
+    t.set_weights(fa, 0, "fp32")
+    t.set_weights(fb, 1, "fp32")
+    assert t.run_selfplay(0)
+    assert t.num_samples() == 0 and 0.0 <= float(t.score()) <= 1.0
+    h = [cb.Trainer(16, "", 1, 16, 8) for _ in range(2)]
+    h[0].set_weights(fa, 0, "fp32")
+    h[1].set_weights(fb, 0, "fp32")
+    o = oracle.trainer(num_games=16, seed=4, max_searches=32, searches_per_eval=8, c_puct=1.0, epsilon=0.0, testing=True)
+    # main.pyx:74-81: the "new" model (0) answers to_play==0 requests
+    from oracle.pyoracle import play_out
+    state = {"tp": 0}
+    ev = np.zeros(16 * 8, np.float32)
+    pr = np.zeros((16 * 8, 96), np.float32)
+    tp = 0
+    while not o.do_iteration(ev, pr, tp):
+        n = o.num_requests(tp)
+        if n == 0:
+            tp = 1 - tp
+            continue
+        e, p = h[0 if tp == 0 else 1].evaluate(o.write_requests(tp))
+        ev[:n], pr[:n] = e, p
+    assert t.score().tobytes() == o.score().tobytes()
+    assert (t.game_results() != 0).all()

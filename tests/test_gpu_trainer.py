@@ -1,0 +1,105 @@
+"""Self-play engine (external-evaluator mode, through the C ABI) vs the golden transcripts that
+were generated from the compiled reference, and vs the oracle on further configurations.
+Bit-exact: every request row of every round, all samples, score and mate length."""
+import os
+
+import numpy as np
+import pytest
+
+import corintho_ai_b200 as cb
+from diag import first_divergence
+from oracle.pyoracle import synth_eval
+from test_oracle_trainer import check_against_golden
+from util import TRAINER_GRID, grid_key, run_trainer
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(cfg, **kw):
+    g, s, ms, spe, cp, eps, testing = cfg
+    return cb.Trainer(g, "", s, ms, spe, cp, eps, 0, 1, testing, **kw)
+
+
+def make_oracle(oracle, cfg):
+    g, s, ms, spe, cp, eps, testing = cfg
+    return oracle.trainer(num_games=g, seed=s, max_searches=ms, searches_per_eval=spe, c_puct=cp,
+                          epsilon=eps, testing=testing)
+
+
+def explain(oracle, cfg):
+    return first_divergence(lambda: make_engine(cfg), lambda: make_oracle(oracle, cfg), oracle,
+                            synth_eval, cfg[6])
+
+
+@pytest.mark.parametrize("cfg", TRAINER_GRID, ids=grid_key)
+def test_engine_matches_golden_transcripts(oracle, cfg):
+    r = run_trainer(make_engine(cfg), synth_eval, cfg[6])
+    try:
+        check_against_golden(r, cfg)
+    except AssertionError:
+        pytest.fail("engine != reference transcript; first divergence: " + explain(oracle, cfg))
+
+
+EXTRA = [
+    (64, 12345, 200, 16, 1.0, 0.25, False),   # BASELINE.json configs[0] shape
+    (40, 77, 8, 4, 1.0, 0.25, False),         # staggered start: 40 games / 8 searches -> div 5
+    (33, 5, 50, 50, 3.0, 0.25, False),        # spe == max_searches, >32 games (ragged CTA)
+    (10, 2, 1600, 16, 1.0, 0.0, True),        # evaluation-match shape: 1600 sims, no noise
+]
+
+
+@pytest.mark.parametrize("cfg", EXTRA, ids=grid_key)
+def test_engine_matches_oracle(oracle, cfg):
+    a = run_trainer(make_oracle(oracle, cfg), synth_eval, cfg[6])
+    e = make_engine(cfg)
+    b = run_trainer(e, synth_eval, cfg[6])
+    ok = (a["rounds"] == b["rounds"] and (a["counts"] == b["counts"]).all() and a["req_hash"] == b["req_hash"]
+          and a["score"].tobytes() == b["score"].tobytes() and a["mate"].tobytes() == b["mate"].tobytes()
+          and (cfg[6] or a["samples_hash"] == b["samples_hash"]))
+    if not ok:
+        pytest.fail("engine != oracle; first divergence: " + explain(oracle, cfg))
+    o = make_oracle(oracle, cfg)
+    run_trainer(o, synth_eval, cfg[6])
+    oc, ec = oracle.counters(o), e.counters()
+    assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
+
+
+def test_sharded_trainers_equal_single_trainer():
+    """Multi-GPU partitioning rule: shards of one seed stream reproduce the
+    single-trainer run game by game."""
+    cfg = (12, 31, 32, 8, 1.0, 0.25, False)
+    whole = make_engine(cfg)
+    run_trainer(whole, synth_eval)
+    st_w, pr_w, lb_w, go_w = whole.raw_samples()
+    parts = []
+    for first, cnt in ((0, 5), (5, 7)):
+        t = cb.Trainer(cnt, "", 31, 32, 8, 1.0, 0.25, 0, 1, False, total_games=12, first_game=first)
+        # shards of a staggered run start later; drive them with the same loop
+        run_trainer(t, synth_eval, allow_empty=True)
+        st, pr, lb, go = t.raw_samples()
+        parts.append((st, pr, lb, go + first))
+    st = np.concatenate([p[0] for p in parts])
+    assert st.tobytes() == st_w.tobytes()
+    assert np.concatenate([p[1] for p in parts]).tobytes() == pr_w.tobytes()
+    assert np.concatenate([p[2] for p in parts]).tobytes() == lb_w.tobytes()
+    assert (np.concatenate([p[3] for p in parts]) == go_w).all()
+
+
+def test_write_scores_and_errors(tmp_path):
+    t = make_engine((4, 3, 16, 4, 1.0, 0.25, False))
+    run_trainer(t, synth_eval)
+    f = tmp_path / "score_verbose.txt"
+    t.writeScores(str(f))
+    txt = f.read_text().splitlines()
+    assert txt[0].startswith("First player wins: ") and len(txt) == 6
+    with pytest.raises(cb.Corintho200Error):
+        cb.Trainer(0, "", 1, 16, 4)
+    with pytest.raises(cb.Corintho200Error):
+        cb.Trainer(2, "", 1, 4, 16)  # max_searches < searches_per_eval (trainer.cpp:30)
+
+
+def test_arena_overflow_fails_loudly(monkeypatch):
+    monkeypatch.setenv("CB200_ARENA_NODES", "20")
+    t = make_engine((2, 3, 200, 16, 1.0, 0.25, False))
+    with pytest.raises(cb.Corintho200Error):
+        run_trainer(t, synth_eval)
