@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Corintho self-play engine.
+
+Metric (BASELINE.json): MCTS simulations/sec (plus self-play moves/sec) per box.
+Workload at every N: BASELINE.json configs[2] per GPU -- 4096 concurrent games x 800
+sims/move, searches_per_eval 16, c_puct 1.0, epsilon 0.25, random-init network of the
+reference architecture -- run to completion of all games ("step" = one such self-play pass).
+For N > 1 the games of one seed stream are sharded contiguously across ranks (weak scaling,
+no collective on the hot path) and the finished samples are all-gathered over NCCL
+(configs[3] uses the same code with --games-per-gpu 32768).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          engine arm
+  python bench.py --impl reference ...                         reference CPU arm
+Under torchrun (N > 1) every rank runs; rank 0 prints the single JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_SIM = 1670.0      # algorithmic bytes per simulation @800 sims
+FLOP_PER_EVAL = 253400.0         # unpadded dense FLOPs per leaf evaluation
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def workload_desc(args, n_gpus):
+    return {
+        "workload": ("BASELINE.json configs[2] per GPU: batched self-play, %d concurrent games x %d sims/move, "
+                     "searches_per_eval %d, c_puct %.1f, epsilon %.2f, all games to completion"
+                     % (args.games_per_gpu, args.sims, args.spe, args.c_puct, args.epsilon)),
+        "games_per_gpu": args.games_per_gpu, "total_games": args.games_per_gpu * n_gpus,
+        "max_searches": args.sims, "searches_per_eval": args.spe,
+        "network": "70 -> 12x[Dense100,ReLU,BN folded] -> {tanh 1, softmax 96}, random init (Glorot-uniform)",
+        "staggered_start": False,
+        "parallelism": "games sharded contiguously across %d GPU(s); no collective on the hot path; "
+                       "samples all-gathered (NCCL) after the run" % n_gpus,
+        "l2_policy": "inputs larger than L2: per-GPU node arenas are several GB (>> 126 MB L2); "
+                     "every step starts from re-initialised game state",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_mlp(flat):
+    """fp32 CPU evaluator with the engine's weights (stands in for the reference's Keras predict,
+    main.pyx:70-83; Keras/TensorFlow are not installable here)."""
+    import torch
+    dims = [70] + [100] * 12 + [97]
+    Ws, bs, off = [], [], 0
+    for l in range(13):
+        K, N = dims[l], dims[l + 1]
+        Ws.append(torch.from_numpy(flat[off:off + K * N].reshape(K, N).copy()))
+        off += K * N
+        bs.append(torch.from_numpy(flat[off:off + N].copy()))
+        off += N
+
+    def f(rows):
+        with torch.no_grad():
+            h = torch.from_numpy(np.ascontiguousarray(rows, np.float32))
+            for l in range(13):
+                h = torch.addmm(bs[l], h, Ws[l])
+                if l < 12:
+                    h = torch.relu_(h)
+            ev = torch.tanh(h[:, 0])
+            pr = torch.softmax(h[:, 1:], 1)
+        return ev.numpy(), pr.numpy()
+    return f
+
+
+def time_cpu_reference(args, flat, games, budget_s=None):
+    """Time the reference's own CPU implementation of the path (oracle/_ref when it was built
+    from /root/reference, else the oracle port) on `games` games of the engine's workload.
+    Returns dict(value sims/s, moves/s, cores, kind, sample, seconds, play_s, predict_s)."""
+    from oracle.pyoracle import OracleLib, RefLib, have_ref
+    kind = "reference" if have_ref() else "port"
+    L = RefLib() if kind == "reference" else OracleLib()
+    cores = os.cpu_count() or 1
+    import torch
+    torch.set_num_threads(cores)
+    ev_fn = cpu_mlp(flat)
+    cfg = dict(num_games=games, seed=12345, max_searches=args.sims, searches_per_eval=args.spe,
+               c_puct=args.c_puct, epsilon=args.epsilon, num_threads=cores)
+    t = L.trainer(**cfg)
+    evals = np.zeros(games * args.spe, np.float32)
+    probs = np.zeros((games * args.spe, 96), np.float32)
+    served, play_s, pred_s = 0, 0.0, 0.0
+    t0 = time.perf_counter()
+    complete = True
+    while True:
+        a = time.perf_counter()
+        done = t.do_iteration(evals, probs, -1)
+        play_s += time.perf_counter() - a
+        if done:
+            break
+        n = t.num_requests(-1)
+        req = t.write_requests(-1)
+        a = time.perf_counter()
+        e, p = ev_fn(req)
+        evals[:n], probs[:n] = e, p
+        pred_s += time.perf_counter() - a
+        served += n
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            complete = False
+            break
+    secs = time.perf_counter() - t0
+    moves = t.num_samples()
+    # every simulation either queues a leaf evaluation or ends in a terminal node; the exact
+    # simulation count of the identical run comes from the oracle port's counter (bit-identical
+    # search), measured outside the timed region when the run completed.
+    sims = served
+    sims_exact = False
+    if complete and games <= 64:
+        O = OracleLib()
+        o = O.trainer(**cfg)
+        from oracle.pyoracle import play_out
+        play_out(o, evaluator=ev_fn)
+        c = O.counters(o)
+        if c["leaf_evals"] == served:
+            sims, sims_exact = c["simulations"], True
+    return {"value": sims / secs, "unit": "sims/s", "moves_per_sec": moves / secs, "cores": cores,
+            "kind": kind, "seconds": secs, "play_seconds": play_s, "predict_seconds": pred_s,
+            "simulations": int(sims), "simulations_exact": sims_exact, "leaf_evals": int(served),
+            "moves": int(moves), "complete": complete,
+            "sample": "%d games x %d sims/move (spe %d) of the same workload, %s; C++/OpenMP tree with %d "
+                      "threads + torch-CPU fp32 network (Keras unavailable)"
+                      % (games, args.sims, args.spe, "to completion" if complete else "time-bounded", cores)}
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    import corintho_ai_b200 as cb
+    flat = cb.fold_batchnorm(cb.random_weights(0))
+    for _ in range(args.warmup):
+        time_cpu_reference(args, flat, 4)
+    sims = secs = moves = 0.0
+    last = None
+    for _ in range(args.steps):
+        last = time_cpu_reference(args, flat, args.ref_games)
+        sims += last["simulations"]
+        secs += last["seconds"]
+        moves += last["moves"]
+    value = sims / secs
+    line = {
+        "impl": "reference", "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "moves_per_sec": moves / secs,
+        "config": dict(workload_desc(args, args.gpus), reference_sample_games=args.ref_games),
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": last["cores"], "kind": last["kind"],
+                         "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_engine_arm(args, rank, world, local_rank):
+    import torch
+    import corintho_ai_b200 as cb
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    L = cb.lib()
+    if L.cb200_set_device(local_rank) != 0:
+        raise SystemExit("cb200_set_device failed: " + L.cb200_last_error().decode())
+    dev = torch.device("cuda", local_rank)
+    G = args.games_per_gpu
+    flat = cb.fold_batchnorm(cb.random_weights(0))
+    pinned_w = torch.from_numpy(flat).pin_memory()
+    tr = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
+                    total_games=G * world, first_game=rank * G)
+    tr.set_weights(flat, 0, args.precision)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (untimed)
+    for w in range(args.warmup):
+        tr.reset(1000 + w)
+        tr.run_selfplay(0, stagger=False)
+    barrier()
+
+    # ---- device-timed steps: game state re-initialised (untimed), inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.cb200_launch_count()
+    tr.set_profiling(True)
+    dev_ms, sims, moves, evals, iters = 0.0, 0, 0, 0, 0
+    for k in range(args.steps):
+        tr.reset(2000 + k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.run_selfplay(0, stagger=False)
+        e1.record()
+        barrier()
+        dev_ms += e0.elapsed_time(e1)
+        c = tr.counters()
+        sims += c["simulations"]; moves += c["moves"]; evals += c["leaf_evals"]; iters += c["iterations"]
+    kt = tr.kernel_times()
+    tr.set_profiling(False)
+    launches = L.cb200_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end-to-end steps through the public API with host buffers:
+    # pinned weights -> device, seeds/control blocks -> device, self-play, samples (8 symmetries) -> host
+    e2e_s, e2e_sims, h2d, d2h, gather_s = 0.0, 0, 0, 0, 0.0
+    for k in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        tr.set_weights(pinned_w.numpy(), 0, args.precision)
+        tr.reset(3000 + k)
+        tr.run_selfplay(0, stagger=False)
+        gs, ev, pr = tr.write_samples()
+        if dist is not None:  # all-gather the finished (un-augmented) samples + stats over NCCL
+            g0 = time.perf_counter()
+            st, prb, lb, go = tr.raw_samples()
+            n_loc = torch.tensor([st.shape[0]], device=dev, dtype=torch.int64)
+            counts = [torch.zeros_like(n_loc) for _ in range(world)]
+            dist.all_gather(counts, n_loc)
+            n_max = int(max(int(c.item()) for c in counts))
+            pad = torch.zeros((n_max, 2 * 2 + 96 + 1), device=dev, dtype=torch.float32)
+            row = np.concatenate([st.view(np.float32).reshape(-1, 4), prb, lb[:, None]], 1)
+            pad[:row.shape[0]] = torch.from_numpy(row).to(dev)
+            out = torch.empty((world * n_max, pad.shape[1]), device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(out, pad)
+            torch.cuda.synchronize()
+            gather_s += time.perf_counter() - g0
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+        e2e_sims += tr.counters()["simulations"]
+        h2d += flat.nbytes + G * (16 + 16 + 624) * 4
+        d2h += gs.nbytes + ev.nbytes + pr.nbytes
+
+    # ---- aggregate over ranks: max time, summed work
+    if dist is not None:
+        tt = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(tt[0]), float(tt[1])
+        ww = torch.tensor([sims, moves, evals, e2e_sims, launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+        sims, moves, evals, e2e_sims, launches = (int(x) for x in ww)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    value = sims / (dev_ms * 1e-3)
+    # dominant kernel = the class with the largest summed device time
+    dom = max(kt, key=lambda k: kt[k]["ms"])
+    share = {k: kt[k]["ms"] / max(1e-9, sum(v["ms"] for v in kt.values())) for k in kt}
+    sims_r0 = tr.counters()  # rank-0 counters of the last e2e step are not used for the roofline
+    if dom == "network":
+        per_launch_flop = FLOP_PER_EVAL * (evals / world) / max(1, kt["network"]["launches"])
+        ach = per_launch_flop / (kt["network"]["ms"] / kt["network"]["launches"] * 1e-3) / 1e12
+        peak = pk["bf16_tflops_sustained"]
+        roof = {"kernel": "k_mlp (policy/value network)", "bound": "tensor", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
+    else:
+        per_launch_bytes = ALGO_BYTES_PER_SIM * (sims / world) / max(1, kt["game_step"]["launches"])
+        ach = per_launch_bytes / (kt["game_step"]["ms"] / kt["game_step"]["launches"] * 1e-3) / 1e9
+        peak = pk["hbm_gbs"]
+        roof = {"kernel": "k_iterate (tree search game step)", "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None}
+    roof["peak_source"] = pk["source"]
+    roof["kernel_time_share"] = share
+    roof["kernel_ms"] = {k: kt[k]["ms"] for k in kt}
+    roof["kernel_launches"] = {k: kt[k]["launches"] for k in kt}
+    # secondary roofline of the other heavy kernel, for the record
+    if kt["network"]["launches"]:
+        roof["network_tflops"] = (FLOP_PER_EVAL * (evals / world) / (kt["network"]["ms"] * 1e-3)) / 1e12
+    if kt["game_step"]["launches"]:
+        roof["game_step_gbs"] = (ALGO_BYTES_PER_SIM * (sims / world) / (kt["game_step"]["ms"] * 1e-3)) / 1e9
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_cpu_reference(args, flat, args.ref_games)
+        cpu = {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+               "moves_per_sec": r["moves_per_sec"], "play_seconds": r["play_seconds"],
+               "predict_seconds": r["predict_seconds"], "simulations_exact": r["simulations_exact"]}
+
+    line = {
+        "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_desc(args, world),
+        "moves_per_sec": moves / (dev_ms * 1e-3), "leaf_evals_per_sec": evals / (dev_ms * 1e-3),
+        "simulations_per_step": sims / args.steps, "iterations_per_step": iters / args.steps,
+        "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": d2h // args.steps, "seconds_per_step": e2e_s / args.steps,
+                "nccl_gather_seconds_per_step": gather_s / args.steps if world > 1 else 0.0},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--games-per-gpu", type=int, default=4096)
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--spe", type=int, default=16)
+    ap.add_argument("--c-puct", type=float, default=1.0)
+    ap.add_argument("--epsilon", type=float, default=0.25)
+    ap.add_argument("--precision", default=os.environ.get("CB200_PRECISION", "fp32"), choices=["bf16", "fp32"])
+    ap.add_argument("--ref-games", type=int, default=32, help="games in one CPU-reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus != 1:
+        # launched without torchrun: run the requested shape on this one process' GPU count
+        args.gpus = 1
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_engine_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

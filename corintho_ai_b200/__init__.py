@@ -82,6 +82,9 @@ def lib():
         "cb200_trainer_evaluate": (i32, [vp, i32, i32, vp, vp, vp]),
         "cb200_trainer_run_selfplay": (i32, [vp, i32, i32]),
         "cb200_trainer_dump_tree": (i32, [vp, i32, i32, vp, vp, i32]),
+        "cb200_trainer_reset": (i32, [vp, i32]),
+        "cb200_trainer_set_profiling": (i32, [vp, i32]),
+        "cb200_trainer_kernel_times": (i32, [vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -294,6 +297,19 @@ class Trainer:
 
     def run_selfplay(self, max_iterations=0, stagger=False):
         return bool(_check(lib().cb200_trainer_run_selfplay(self._h, max_iterations, int(stagger))))
+
+    def reset(self, seed):
+        _check(lib().cb200_trainer_reset(self._h, int(seed)))
+
+    def set_profiling(self, enable=True):
+        _check(lib().cb200_trainer_set_profiling(self._h, int(enable)))
+
+    def kernel_times(self):
+        ms = np.zeros(4, np.float64)
+        ln = np.zeros(4, np.int64)
+        _check(lib().cb200_trainer_kernel_times(self._h, _ptr(ms), _ptr(ln)))
+        names = ["scan", "pack", "network", "game_step"]
+        return {n: {"ms": float(ms[i]), "launches": int(ln[i])} for i, n in enumerate(names)}
 
     def raw_samples(self):
         n = self.num_samples()

@@ -71,8 +71,15 @@ struct cb200_trainer {
   NetF32 net32[2];
   NetTC nettc[2];
   int precision[2] = {-1, -1};
-  int last_to_play_scanned = -2;
   std::vector<int32_t> h_ctl;
+  int seed = 0;
+  // per-kernel-class CUDA-event timing (bench.py roofline): 0 scan, 1 pack, 2 network, 3 iterate
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_class;  // class of the pair starting at ev_pool[2*i]
+  size_t ev_used = 0;
+  double class_ms[4] = {0, 0, 0, 0};
+  long long class_launches[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -123,7 +130,42 @@ int dmalloc(T **p, size_t count) {
   return CB200_OK;
 }
 
+// ---- optional per-launch timing ---------------------------------------------------------------
+int prof_drain(cb200_trainer *t) {  // caller has synchronised the stream
+  for (size_t i = 0; i < t->ev_used; ++i) {
+    float ms = 0.f;
+    CB_CUDA(cudaEventElapsedTime(&ms, t->ev_pool[2 * i], t->ev_pool[2 * i + 1]));
+    t->class_ms[t->ev_class[i]] += ms;
+    t->class_launches[t->ev_class[i]] += 1;
+  }
+  t->ev_used = 0;
+  return CB200_OK;
+}
+struct ProfScope {
+  cb200_trainer *t;
+  bool on;
+  size_t idx = 0;
+  ProfScope(cb200_trainer *t_, int cls) : t(t_), on(t_->profiling) {
+    if (!on) return;
+    if (2 * (t->ev_used + 1) > t->ev_pool.size()) {
+      for (int k = 0; k < 2; ++k) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        t->ev_pool.push_back(e);
+      }
+      t->ev_class.push_back(cls);
+    }
+    idx = t->ev_used++;
+    t->ev_class[idx] = cls;
+    cudaEventRecord(t->ev_pool[2 * idx], G().stream);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(t->ev_pool[2 * idx + 1], G().stream);
+  }
+};
+
 int scan(cb200_trainer *t, int to_play) {
+  ProfScope ps(t, 0);
   k_scan_requests<<<1, 1024, 0, G().stream>>>(t->P, to_play, t->d_offs, t->d_summary);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
@@ -134,6 +176,10 @@ int fetch_summary(cb200_trainer *t) {
   CB_CUDA(cudaMemcpyAsync(t->h_summary, t->d_summary, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
                           G().stream));
   CB_CUDA(cudaStreamSynchronize(G().stream));
+  if (t->profiling) {
+    int rc = prof_drain(t);
+    if (rc != CB200_OK) return rc;
+  }
   if (t->h_summary[2] != 0)
     return set_error(t->h_summary[2],
                      "a game overflowed its node arena / path / sample buffer (raise "
@@ -143,6 +189,7 @@ int fetch_summary(cb200_trainer *t) {
 
 int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_play) {
   const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
+  ProfScope ps(t, 3);
   k_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, t->d_offs, to_play,
                                                        t->iterations_done, t->stagger_div);
   CB_LAUNCHED();
@@ -153,6 +200,7 @@ int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_
 
 int pack(cb200_trainer *t, int to_play, float *d_rows, ulonglong2 *d_packed) {
   const int grid = (t->P.num_games + 7) / 8;
+  ProfScope ps(t, 1);
   k_pack_requests<<<grid, 256, 0, G().stream>>>(t->P, to_play, t->d_offs, d_rows, d_packed);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
@@ -161,6 +209,7 @@ int pack(cb200_trainer *t, int to_play, float *d_rows, ulonglong2 *d_packed) {
 
 int run_net(cb200_trainer *t, int model, const ulonglong2 *d_states, const int32_t *d_n,
             int n_static, int n_max) {
+  ProfScope ps(t, 2);
   if (t->precision[model] == 0)
     return launch_mlp_f32(t->net32[model], d_states, d_n, n_static, n_max, t->d_eval, t->d_probs);
   if (t->precision[model] == 1)
@@ -175,6 +224,45 @@ int guard(cb200_trainer *t) {
 }
 
 }  // namespace
+
+
+// host-side initialisation: per-game seeds (trainer.cpp:238-256) and control blocks
+static int init_state(cb200_trainer *t) {
+  TreeParams &P = t->P;
+  const size_t Gn = (size_t)P.num_games;
+  std::vector<int32_t> ctl(Gn * kCtlWords, 0), tree(Gn * 2 * kTreeCtlWords, 0);
+  std::vector<uint32_t> mt(Gn * 624);
+  HostMT gen;
+  gen.seed((uint32_t)t->seed);
+  for (int i = 0; i < P.first_game; ++i) gen.next();
+  for (size_t g = 0; g < Gn; ++g) {
+    uint32_t *m = mt.data() + g * 624;
+    m[0] = gen.next();
+    for (int i = 1; i < 624; ++i) m[i] = mt_seed_word(m[i - 1], i);
+    int32_t *c = ctl.data() + g * kCtlWords;
+    c[CW_PARITY] = (int)((P.first_game + g) & 1);
+    c[CW_SPARE] = 2;
+    c[CW_MT_IDX] = 624;
+    for (int p = 0; p < 2; ++p) {
+      int32_t *tw = tree.data() + (g * 2 + p) * kTreeCtlWords;
+      tw[TW_ARENA] = p;
+      tw[TW_ROOT_VISITS] = 1;
+      tw[TW_ROOT_ALLV] = 1;
+    }
+  }
+  cudaStream_t s = G().stream;
+  CB_CUDA(cudaMemcpyAsync(P.ctl, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(P.tree, tree.data(), tree.size() * 4, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemcpyAsync(P.mt, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, s));
+  CB_CUDA(cudaMemsetAsync(P.counters, 0, Gn * 4 * sizeof(long long), s));
+  CB_CUDA(cudaMemsetAsync(t->d_offs, 0, Gn * sizeof(int32_t), s));
+  CB_CUDA(cudaMemsetAsync(t->d_summary, 0, 4 * sizeof(int32_t), s));
+  CB_CUDA(cudaMemsetAsync(t->d_eval, 0, t->cap * sizeof(float), s));
+  CB_CUDA(cudaMemsetAsync(t->d_probs, 0, t->cap * CB200_NUM_MOVES * sizeof(float), s));
+  CB_CUDA(cudaStreamSynchronize(s));
+  t->iterations_done = 0;
+  return CB200_OK;
+}
 
 // ==============================================================================================
 extern "C" {
@@ -292,35 +380,8 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     cb200_trainer_destroy(t);
     return nullptr;
   }
-  // host-side initialisation: seeds (trainer.cpp:238-256), control blocks
-  std::vector<int32_t> ctl(Gn * kCtlWords, 0), tree(Gn * 2 * kTreeCtlWords, 0);
-  std::vector<uint32_t> mt(Gn * 624);
-  HostMT gen;
-  gen.seed((uint32_t)seed);
-  for (int i = 0; i < first_game; ++i) gen.next();
-  for (size_t g = 0; g < Gn; ++g) {
-    uint32_t *m = mt.data() + g * 624;
-    m[0] = gen.next();
-    for (int i = 1; i < 624; ++i) m[i] = mt_seed_word(m[i - 1], i);
-    int32_t *c = ctl.data() + g * kCtlWords;
-    c[CW_PARITY] = (int)((first_game + g) & 1);
-    c[CW_SPARE] = 2;
-    c[CW_MT_IDX] = 624;
-    for (int p = 0; p < 2; ++p) {
-      int32_t *tw = tree.data() + (g * 2 + p) * kTreeCtlWords;
-      tw[TW_ARENA] = p;
-      tw[TW_ROOT_VISITS] = 1;
-      tw[TW_ROOT_ALLV] = 1;
-    }
-  }
-  cudaError_t e = cudaMemcpy(P.ctl, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(P.tree, tree.data(), tree.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(P.mt, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemset(P.counters, 0, Gn * 4 * sizeof(long long));
-  if (e == cudaSuccess) e = cudaMemset(t->d_offs, 0, Gn * sizeof(int32_t));
-  if (e == cudaSuccess) e = cudaMemset(t->d_summary, 0, 4 * sizeof(int32_t));
-  if (e != cudaSuccess) {
-    set_error(CB200_ERR_CUDA, std::string("init upload: ") + cudaGetErrorString(e));
+  t->seed = seed;
+  if (init_state(t) != CB200_OK) {
     cb200_trainer_destroy(t);
     return nullptr;
   }
@@ -335,9 +396,36 @@ cb200_trainer *cb200_trainer_create(int num_games, const char *log_folder, int s
                                     searches_per_eval, c_puct, epsilon, num_logged, testing);
 }
 
+int cb200_trainer_reset(cb200_trainer *t, int seed) {
+  int rc = guard(t);
+  if (rc) return rc;
+  t->seed = seed;
+  return init_state(t);
+}
+
+int cb200_trainer_set_profiling(cb200_trainer *t, int enable) {
+  int rc = guard(t);
+  if (rc) return rc;
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  if ((rc = prof_drain(t)) != CB200_OK) return rc;
+  t->profiling = enable != 0;
+  for (int i = 0; i < 4; ++i) t->class_ms[i] = 0, t->class_launches[i] = 0;
+  return CB200_OK;
+}
+
+int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[4], int64_t out_launches[4]) {
+  int rc = guard(t);
+  if (rc) return rc;
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  if ((rc = prof_drain(t)) != CB200_OK) return rc;
+  for (int i = 0; i < 4; ++i) out_ms[i] = t->class_ms[i], out_launches[i] = t->class_launches[i];
+  return CB200_OK;
+}
+
 void cb200_trainer_destroy(cb200_trainer *t) {
   if (!t) return;
   cudaSetDevice(t->device);
+  for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   TreeParams &P = t->P;
   cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
   cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);

@@ -801,6 +801,10 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
     if (r_known(c.root_result) && c.mate_turn == 0) c.mate_turn = c.n_samples + 1;
     c.d_sims += c.searches_done;
     c.d_moves += 1;
+    if (c.d_moves > 128) {  // no Corintho game has this many plies: refuse to spin
+      c.error = CB200_ERR_STATE;
+      return true;
+    }
     int choice;
     if (!P.testing) {  // SelfPlayer::chooseMove (selfplayer.cpp:234-244)
       if (c.n_samples >= kMaxSamples) {

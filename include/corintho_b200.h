@@ -149,6 +149,13 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
  * Returns 1 when all games are done, 0 if stopped by max_iterations, <0 on error. */
 int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger);
 
+/* Re-initialise every game for a new run with `seed` (same shape, allocations reused). */
+int cb200_trainer_reset(cb200_trainer *t, int seed);
+/* Per-kernel-class device timing with CUDA events on the launch stream (bench.py roofline):
+ * classes 0 request scan, 1 request pack, 2 network, 3 game step (tree). */
+int cb200_trainer_set_profiling(cb200_trainer *t, int enable);
+int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[4], int64_t out_launches[4]);
+
 /* White-box dump of one search tree for engine-vs-oracle debugging (same layout as
  * oracle/corintho_oracle.h orc_trainer_dump_tree). */
 int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[8],

@@ -74,28 +74,35 @@ def test_fused_selfplay_equals_oracle_driven_by_the_same_network(oracle):
 
 
 def test_fused_testing_mode_two_models(oracle):
+    """Two-model (gating-match) mode, fused. The device loop evaluates every pending request
+    with the model that owns it before the owning side iterates (tp = 0, 1, 0, 1, ...). The
+    reference's Python caller instead re-enters doIteration with STALE answer buffers right
+    after it flips to_play (main.pyx:151-154) -- a caller-side quirk the external-evaluator
+    API reproduces by construction (test_gpu_trainer.py); here the oracle is driven with the
+    same clean alternation."""
     fa, fb = cb.fold_batchnorm(cb.random_weights(1)), cb.fold_batchnorm(cb.random_weights(2))
-    t = cb.Trainer(16, "", 4, 32, 8, 1.0, 0.0, 0, 1, True)
+    G, MS, SPE = 16, 32, 8
+    t = cb.Trainer(G, "", 4, MS, SPE, 1.0, 0.25, 0, 1, True)
     t.set_weights(fa, 0, "fp32")
     t.set_weights(fb, 1, "fp32")
     assert t.run_selfplay(0)
     assert t.num_samples() == 0 and 0.0 <= float(t.score()) <= 1.0
-    h = [cb.Trainer(16, "", 1, 16, 8) for _ in range(2)]
+    h = [cb.Trainer(G, "", 1, 16, SPE) for _ in range(2)]
     h[0].set_weights(fa, 0, "fp32")
     h[1].set_weights(fb, 0, "fp32")
-    o = oracle.trainer(num_games=16, seed=4, max_searches=32, searches_per_eval=8, c_puct=1.0, epsilon=0.0, testing=True)
-    # main.pyx:74-81: the "new" model (0) answers to_play==0 requests
-    from oracle.pyoracle import play_out
-    state = {"tp": 0}
-    ev = np.zeros(16 * 8, np.float32)
-    pr = np.zeros((16 * 8, 96), np.float32)
-    tp = 0
-    while not o.do_iteration(ev, pr, tp):
+    o = oracle.trainer(num_games=G, seed=4, max_searches=MS, searches_per_eval=SPE, c_puct=1.0,
+                       epsilon=0.25, testing=True)
+    ev = np.zeros(G * SPE, np.float32)
+    pr = np.zeros((G * SPE, 96), np.float32)
+    done, tp = False, 0
+    while not done:
         n = o.num_requests(tp)
-        if n == 0:
-            tp = 1 - tp
-            continue
-        e, p = h[0 if tp == 0 else 1].evaluate(o.write_requests(tp))
-        ev[:n], pr[:n] = e, p
+        if n:  # main.pyx:74-81: the "new" model (0) answers to_play==0 requests
+            e, p = h[tp].evaluate(o.write_requests(tp))
+            ev[:n], pr[:n] = e, p
+        done = o.do_iteration(ev, pr, tp)
+        tp = 1 - tp
     assert t.score().tobytes() == o.score().tobytes()
+    oc, ec = oracle.counters(o), t.counters()
+    assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
     assert (t.game_results() != 0).all()
