@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--spe", type=int, default=16)
     ap.add_argument("--c-puct", type=float, default=1.0)
     ap.add_argument("--epsilon", type=float, default=0.25)
-    ap.add_argument("--precision", default=os.environ.get("CB200_PRECISION", "fp32"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("CB200_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--ref-games", type=int, default=32, help="games in one CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

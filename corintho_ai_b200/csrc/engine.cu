@@ -187,11 +187,16 @@ int fetch_summary(cb200_trainer *t) {
   return CB200_OK;
 }
 
-int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_play) {
+// probs_move_major: answers were written by the tensor-core network as [96][cap]
+int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_play,
+            bool probs_move_major = false) {
   const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
+  const long prs = probs_move_major ? 1 : CB200_NUM_MOVES;
+  const long pcs = probs_move_major ? (long)t->cap : 1;
   ProfScope ps(t, 3);
-  k_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, t->d_offs, to_play,
-                                                       t->iterations_done, t->stagger_div);
+  k_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
+                                                       to_play, t->iterations_done,
+                                                       t->stagger_div);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   if (to_play != 0 && to_play != 1) ++t->iterations_done;
@@ -213,7 +218,8 @@ int run_net(cb200_trainer *t, int model, const ulonglong2 *d_states, const int32
   if (t->precision[model] == 0)
     return launch_mlp_f32(t->net32[model], d_states, d_n, n_static, n_max, t->d_eval, t->d_probs);
   if (t->precision[model] == 1)
-    return launch_mlp_tc(t->nettc[model], d_states, d_n, n_static, n_max, t->d_eval, t->d_probs);
+    return launch_mlp_tc(t->nettc[model], d_states, d_n, n_static, n_max, t->d_eval, t->d_probs,
+                         (int)t->cap);
   return set_error(CB200_ERR_STATE, "no weights set for this model (cb200_trainer_set_weights)");
 }
 
@@ -687,6 +693,15 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
   CB_CUDA(cudaMemcpyAsync(t->d_packed, hs.data(), (size_t)n * sizeof(ulonglong2), cudaMemcpyHostToDevice, s));
   if ((rc = run_net(t, model, t->d_packed, nullptr, n, n)) != CB200_OK) return rc;
   CB_CUDA(cudaMemcpyAsync(eval, t->d_eval, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (t->precision[model] == 1) {  // move-major [96][cap] on the device -> row-major for the caller
+    std::vector<float> tmp((size_t)CB200_NUM_MOVES * n);
+    CB_CUDA(cudaMemcpy2DAsync(tmp.data(), (size_t)n * sizeof(float), t->d_probs, t->cap * sizeof(float),
+                              (size_t)n * sizeof(float), CB200_NUM_MOVES, cudaMemcpyDeviceToHost, s));
+    CB_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i)
+      for (int m = 0; m < CB200_NUM_MOVES; ++m) probs[(size_t)i * CB200_NUM_MOVES + m] = tmp[(size_t)m * n + i];
+    return CB200_OK;
+  }
   CB_CUDA(cudaMemcpyAsync(probs, t->d_probs, (size_t)n * CB200_NUM_MOVES * sizeof(float), cudaMemcpyDeviceToHost, s));
   CB_CUDA(cudaStreamSynchronize(s));
   return CB200_OK;
@@ -712,13 +727,13 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
         rc = scan(t, -1);
         if (rc == CB200_OK) rc = pack(t, -1, nullptr, t->d_packed);
         if (rc == CB200_OK) rc = run_net(t, 0, t->d_packed, t->d_summary, 0, n_max);
-        if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, -1);
+        if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, -1, t->precision[0] == 1);
       } else {
         for (int tp = 0; tp < 2 && rc == CB200_OK; ++tp) {  // model 0 = "new" serves to_play 0
           rc = scan(t, tp);
           if (rc == CB200_OK) rc = pack(t, tp, nullptr, t->d_packed);
           if (rc == CB200_OK) rc = run_net(t, tp == 0 ? 0 : 1, t->d_packed, t->d_summary, 0, n_max);
-          if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, tp);
+          if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, tp, t->precision[tp == 0 ? 0 : 1] == 1);
         }
         ++t->iterations_done;
       }

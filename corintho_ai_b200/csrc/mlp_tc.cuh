@@ -1,21 +1,353 @@
-// K5 (bf16 tensor-core variant) -- placeholder until the tcgen05 kernel lands (next commit).
+// K5 (tensor-core variant): the policy/value network on tcgen05 with TMEM accumulators.
+// Architecture = corintho_ai/python/wrapper.py:256-271 (BatchNorm folded by the caller):
+// 70 -> 12 x [Dense 100, ReLU] -> {tanh value, softmax 96 policy}; replaces the Keras predict
+// call of the reference loop (corintho_ai/python/main.pyx:70-83).
+//
+// One CTA (256 threads = 2 warpgroups) pushes TWO tiles of 128 positions through all 13
+// layers without touching HBM in between:
+//   * A operand (activations, bf16) lives in shared memory in the UMMA canonical K-major
+//     no-swizzle layout: 16-byte k-chunks (8 bf16) of all 128 rows are contiguous
+//     (chunk stride 2048 B = LBO, 8-row core-matrix stride 128 B = SBO);
+//   * B operand (weights of one layer, bf16, [N=112][K=112] K-major, same canonical layout
+//     with chunk stride 1792 B) plus the fp32 bias is ONE 25.5 KB image per layer, fetched by
+//     a single cp.async.bulk (UBLKCP) per layer into a double buffer, mbarrier-tracked;
+//   * D (fp32) lives in TMEM: 112 columns per tile, 7 x tcgen05.mma (M128 N112 K16) per layer,
+//     issued by one thread per warpgroup and committed to an mbarrier;
+//   * epilogue: tcgen05.ld (32 lanes x 16 columns) -> +bias, ReLU, bf16 -> written straight
+//     back as the next layer's A operand. Input encoding (game.cpp:45-58) is expanded from
+//     the packed cstate inside the kernel; tanh / softmax are done from TMEM in the last layer.
+// All dimensions are padded with zeros: K 70/100 -> 112, N 100/97 -> 112.
 #ifndef CORINTHO_B200_MLP_TC_CUH
 #define CORINTHO_B200_MLP_TC_CUH
+
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+
 namespace cb200 {
+
+constexpr int kTcLayers = 13;
+constexpr int kTcN = 112;                                // padded out features
+constexpr int kTcChunks = 14;                            // padded in features / 8
+constexpr int kTcAChunkBytes = 128 * 16;                 // 2048: one k-chunk of 128 rows
+constexpr int kTcWChunkBytes = kTcN * 16;                // 1792: one k-chunk of 112 rows
+constexpr int kTcABytes = kTcChunks * kTcAChunkBytes;    // 28672
+constexpr int kTcWBytes = kTcChunks * kTcWChunkBytes;    // 25088
+constexpr int kTcLayerBytes = kTcWBytes + kTcN * 4;      // 25536 (weights + fp32 bias)
+constexpr int kTcThreads = 256;
+constexpr int kTcTmemCols = 256;                         // 2 tiles x 128 columns
+constexpr size_t kTcSmemBytes = 2 * kTcABytes + 2 * kTcLayerBytes + 64;
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 (bits 4-5 = 1),
+// A=B=BF16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
+                              ((uint32_t)(128 >> 4) << 24);
+
 struct NetTC {
-  void *w = nullptr;
+  void *w = nullptr;  // device: kTcLayers images of kTcLayerBytes
   bool ready = false;
 };
-inline int net_tc_upload(NetTC &, const float *) {
-  return set_error(CB200_ERR_STATE, "bf16 tcgen05 evaluator not built yet");
+
+// ---- raw PTX helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor), K-major,
+// SWIZZLE_NONE: start>>4 [0,14), LBO>>4 [16,30) = k-chunk stride, SBO>>4 [32,46) = 8-row group
+// stride, version 1 at [46,48)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+    k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
+             const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
+             float *__restrict__ probs, int probs_ld) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t *sA = smem;                                // 2 x kTcABytes
+  uint8_t *sW = smem + 2 * kTcABytes;                // 2 x kTcLayerBytes
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sW + 2 * kTcLayerBytes);  // wbar[2], mbar[2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+  const int t = threadIdx.x, warp = t >> 5;
+  const int wg = t >> 7;                             // warpgroup = tile within the CTA
+  const int row = t & 127;                           // row of the tile owned by this thread
+  const int n = n_ptr ? *n_ptr : n_static;
+  const uint32_t wbar0 = smem_u32(bars), mbar0 = smem_u32(bars + 2);
+  if (t == 0) {
+    mbar_init(wbar0, 1), mbar_init(wbar0 + 8, 1);
+    mbar_init(mbar0, 1), mbar_init(mbar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(kTcTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_tile = tmem_base + (uint32_t)wg * 128u;                  // column offset
+  const uint32_t tmem_row = tmem_tile + ((uint32_t)((warp & 3) * 32) << 16);   // lane offset
+  uint8_t *myA = sA + wg * kTcABytes;
+  const uint32_t aaddr = smem_u32(myA);
+  uint32_t wcount[2] = {0, 0};  // completed waits per weight buffer
+  uint32_t mcount = 0;          // completed waits on this warpgroup's MMA barrier
+
+  const int n_pairs = (n + 255) / 256;
+  for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
+    if (t == 0) {  // both weight buffers are free here: fetch layers 0 and 1
+      for (int b = 0; b < 2; ++b) {
+        mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
+        bulk_g2s(smem_u32(sW + b * kTcLayerBytes), W + (size_t)b * kTcLayerBytes, kTcLayerBytes,
+                 wbar0 + 8 * b);
+      }
+    }
+    // ---- input encoding straight from the packed state into the A operand (bf16 exact)
+    const int p = pair * 256 + wg * 128 + row;
+    {
+      CState st{0, 0};
+      if (p < n) {
+        const ulonglong2 v = states[p];
+        st.w0 = v.x, st.w1 = v.y;
+      }
+#pragma unroll
+      for (int c = 0; c < kTcChunks; ++c) {
+        uint32_t q[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int j = 8 * c + 2 * h;
+          const float a = j < CB200_STATE_SIZE ? encode_elem(st, j) : 0.0f;
+          const float b = j + 1 < CB200_STATE_SIZE ? encode_elem(st, j + 1) : 0.0f;
+          q[h] = pack_bf16(a, b);
+        }
+        *reinterpret_cast<uint4 *>(myA + c * kTcAChunkBytes + row * 16) =
+            make_uint4(q[0], q[1], q[2], q[3]);
+      }
+    }
+    // make this thread's generic-proxy writes of A visible to the tensor core, then sync
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    for (int layer = 0; layer < kTcLayers; ++layer) {
+      const int b = layer & 1;
+      uint8_t *wbuf = sW + b * kTcLayerBytes;
+      mbar_wait(wbar0 + 8 * b, wcount[b] & 1);
+      wcount[b] += 1;
+      if (row == 0) {  // one thread per warpgroup issues the 7 MMAs of its tile
+        const uint32_t waddr = smem_u32(wbuf);
+#pragma unroll
+        for (int kk = 0; kk < kTcChunks / 2; ++kk) {
+          const uint64_t ad = umma_desc(aaddr + kk * 2 * kTcAChunkBytes, kTcAChunkBytes, 128);
+          const uint64_t bd = umma_desc(waddr + kk * 2 * kTcWChunkBytes, kTcWChunkBytes, 128);
+          umma_bf16(tmem_tile, ad, bd, kTcIdesc, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(mbar0 + 8 * wg);
+      }
+      mbar_wait(mbar0 + 8 * wg, mcount & 1);
+      mcount += 1;
+      tc_fence_after();
+      const float *bias = reinterpret_cast<const float *>(wbuf + kTcWBytes);
+      if (layer < kTcLayers - 1) {
+        // ---- hidden-layer epilogue: +bias, ReLU, bf16, becomes the next A operand
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_row + c0, v);
+          uint32_t q[8];
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const float x0 = fmaxf(__uint_as_float(v[2 * h]) + bias[c0 + 2 * h], 0.0f);
+            const float x1 = fmaxf(__uint_as_float(v[2 * h + 1]) + bias[c0 + 2 * h + 1], 0.0f);
+            q[h] = pack_bf16(x0, x1);
+          }
+          uint8_t *dst = myA + (c0 >> 3) * kTcAChunkBytes + row * 16;
+          *reinterpret_cast<uint4 *>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
+          *reinterpret_cast<uint4 *>(dst + kTcAChunkBytes) = make_uint4(q[4], q[5], q[6], q[7]);
+        }
+      } else {
+        // ---- heads: column 0 = value (tanh), columns 1..96 = policy logits (softmax)
+        float mx = -INFINITY, v0 = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const int col = c0 + h;
+            const float x = __uint_as_float(v[h]) + bias[col];
+            if (col == 0) v0 = x;
+            if (col >= 1 && col <= CB200_NUM_MOVES) mx = fmaxf(mx, x);
+          }
+        }
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const int col = c0 + h;
+            if (col >= 1 && col <= CB200_NUM_MOVES)
+              sum += __expf(__uint_as_float(v[h]) + bias[col] - mx);
+          }
+        }
+        const float inv = 1.0f / sum;
+        if (p < n) eval[p] = tanhf(v0);
+        // probabilities are written move-major ([96][ld]) so that a warp's stores coalesce
+#pragma unroll 1
+        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const int col = c0 + h;
+            if (col >= 1 && col <= CB200_NUM_MOVES && p < n)
+              probs[(size_t)(col - 1) * probs_ld + p] =
+                  __expf(__uint_as_float(v[h]) + bias[col] - mx) * inv;
+          }
+        }
+      }
+      // A (next layer's operand) is written, both tiles are done with this layer's
+      // weights/bias: publish, sync, refill the weight buffer two layers ahead
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (t == 0 && layer + 2 < kTcLayers) {
+        mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
+        bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kTcLayerBytes, kTcLayerBytes,
+                 wbar0 + 8 * b);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(kTcTmemCols)
+                 : "memory");
+  }
+}
+
+// Re-layout the C-ABI weight vector into per-layer UMMA images (bf16, zero padded) and upload.
+inline int net_tc_upload(NetTC &net, const float *weights) {
+  std::vector<uint8_t> host((size_t)kTcLayers * kTcLayerBytes, 0);
+  const float *src = weights;
+  for (int l = 0; l < kTcLayers; ++l) {
+    const int K = l == 0 ? CB200_STATE_SIZE : 100;
+    const int N = l == kTcLayers - 1 ? 97 : 100;
+    uint8_t *img = host.data() + (size_t)l * kTcLayerBytes;
+    for (int k = 0; k < K; ++k)
+      for (int o = 0; o < N; ++o) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(src[(size_t)k * N + o]);
+        // B operand is [N][K] K-major: chunk k/8, row o, element k%8
+        memcpy(img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2, &h, 2);
+      }
+    src += (size_t)K * N;
+    memcpy(img + kTcWBytes, src, (size_t)N * sizeof(float));
+    src += N;
+  }
+  if (!net.w) CB_CUDA(cudaMalloc(&net.w, host.size()));
+  CB_CUDA(cudaMemcpy(net.w, host.data(), host.size(), cudaMemcpyHostToDevice));
+  net.ready = true;
+  return CB200_OK;
+}
+
 inline void net_tc_free(NetTC &net) {
   if (net.w) cudaFree(net.w);
   net.w = nullptr;
 }
-inline int launch_mlp_tc(const NetTC &, const ulonglong2 *, const int32_t *, int, int, float *, float *) {
-  return set_error(CB200_ERR_STATE, "bf16 tcgen05 evaluator not built yet");
+
+inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int32_t *d_n,
+                         int n_static, int n_max, float *d_eval, float *d_probs, int probs_ld) {
+  static bool attr_set[16] = {false};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev < 16 && !attr_set[dev]) {
+    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kTcSmemBytes));
+    attr_set[dev] = true;
+  }
+  if (n_max <= 0) return CB200_OK;
+  const int pairs = (n_max + 255) / 256;
+  const int grid = pairs < 2 * sms ? pairs : 2 * sms;
+  k_mlp_tc<<<grid, kTcThreads, kTcSmemBytes, G().stream>>>((const uint8_t *)net.w, d_states, d_n,
+                                                           n_static, d_eval, d_probs, probs_ld);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  return CB200_OK;
 }
+
 }  // namespace cb200
 #endif

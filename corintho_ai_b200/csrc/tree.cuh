@@ -337,8 +337,11 @@ __device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
 }
 
 // ---- TrainMC::receiveEval (trainmc.cpp:269-296) ---------------------------------------------
+// probs element (answer row k, move m) = probs[k * prs + m * pcs]: row-major [n][96] from the
+// host API (prs 96, pcs 1), move-major [96][ld] from the tensor-core network (prs 1, pcs ld)
 __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &sm,
-                                          const float *eval, const float *probs) {
+                                          const float *eval, const float *probs, long prs,
+                                          long pcs) {
   const int np = c.n_pending;
   for (int k = 0; k < np; ++k) {
     const uint32_t *pd = c.pending + k * kPendWords;
@@ -346,7 +349,7 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
     const int path_len = (int)pd[1];
     uint32_t *r = c.base + leaf_off;
     const int n = (int)(r[4] & 0xffu);
-    const float *pk = probs + (size_t)k * CB200_NUM_MOVES;
+    const float *pk = probs + (long)k * prs;
     // getFilteredProbs (trainmc.cpp:212-234): gather legal priors, float sum in edge order
     uint32_t w3[3];
     float fv[3];
@@ -356,7 +359,7 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
       w3[j] = 0, fv[j] = 0.0f;
       if (e < n) {
         w3[j] = r[8 + 4 * e + 3];
-        fv[j] = pk[s3_move(w3[j])];
+        fv[j] = pk[(long)s3_move(w3[j]) * pcs];
         sm.f[e] = fv[j];
       }
     }
@@ -626,7 +629,8 @@ __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
 
 // ---- TrainMC::doIteration (trainmc.cpp:139-178) ---------------------------------------------
 __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, WarpSm &sm,
-                                                  const float *eval, const float *probs) {
+                                                  const float *eval, const float *probs,
+                                                  long prs = 0, long pcs = 0) {
   if (!c.has_root) {
     fresh_tree(c, P, start_state(), 0);
     c.searches_done = 1;
@@ -638,7 +642,7 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
     request_root(c);
     return false;
   }
-  if (c.n_pending > 0) receive_eval(c, P, sm, eval, probs);
+  if (c.n_pending > 0) receive_eval(c, P, sm, eval, probs, prs, pcs);
   while (c.n_pending < P.spe && c.searches_done < P.max_searches && !r_known(c.root_result) &&
          !c.root_allv && !c.error) {
     search(c, P, sm);
@@ -868,7 +872,8 @@ __device__ __forceinline__ bool game_selected(const int32_t *ctl, int to_play) {
 // eval/probs (exclusive prefix sum of the request counts the answers were produced for).
 __global__ void __launch_bounds__(kTreeWarps * 32)
     k_iterate(TreeParams P, const float *__restrict__ eval, const float *__restrict__ probs,
-              const int32_t *__restrict__ offs, int to_play, int iteration, int stagger_div) {
+              long prs, long pcs, const int32_t *__restrict__ offs, int to_play, int iteration,
+              int stagger_div) {
   __shared__ WarpSm sm_all[kTreeWarps];
   const int warp = threadIdx.x >> 5;
   const int g = blockIdx.x * kTreeWarps + warp;
@@ -896,7 +901,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32)
   load_tree(c, P, c.to_play);
   const int off = offs[g];
   // SelfPlayer::doIteration (selfplayer.cpp:115-122)
-  bool done = tree_do_iteration(c, P, sm, eval + off, probs + (size_t)off * CB200_NUM_MOVES);
+  bool done = tree_do_iteration(c, P, sm, eval + off, probs + (long)off * prs, prs, pcs);
   if (!c.error && done) done = choose_move_and_continue(c, P, sm);
   if (c.error) done = true;
   store_tree(c);

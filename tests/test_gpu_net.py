@@ -106,3 +106,50 @@ def test_fused_testing_mode_two_models(oracle):
     oc, ec = oracle.counters(o), t.counters()
     assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
     assert (t.game_results() != 0).all()
+
+
+def test_bf16_tensor_core_network(oracle):
+    """tcgen05 bf16 kernel. Stated tolerance (BASELINE.json north_star): 2e-2 in bf16 against
+    the fp32 network; against a numpy emulation that rounds weights and activations to bf16 the
+    same way (fp32 accumulation) it must be much tighter."""
+    x = sample_positions(oracle, 1500, seed=7)
+    flat = cb.fold_batchnorm(cb.random_weights(11))
+    t = cb.Trainer(128, "", 1, 32, 16)
+    t.set_weights(flat, 0, "bf16")
+    ev, pr = t.evaluate(x)
+    assert np.isfinite(ev).all() and np.isfinite(pr).all()
+    assert np.allclose(pr.sum(1), 1.0, atol=1e-3)
+    vb, pb = forward_folded(flat, x, np.float64, round_bf16=True)
+    v64, p64 = forward_folded(flat, x, np.float64)
+    e_emul = np.max(np.abs(pr - pb) / pb), np.max(np.abs(ev - vb))
+    e_fp32 = np.max(np.abs(pr - p64) / p64), np.max(np.abs(ev - v64))
+    print("bf16 kernel vs bf16 emulation: probs rel %.3e value abs %.3e; vs fp64 net: probs rel %.3e value abs %.3e"
+          % (e_emul + e_fp32))
+    assert e_emul[0] < 5e-3 and e_emul[1] < 5e-3
+    assert e_fp32[0] < 2e-2 and e_fp32[1] < 2e-2
+    # ragged batch sizes and row independence
+    for n in (1, 127, 129, 255, 257, 1000):
+        e2, p2 = t.evaluate(x[:n])
+        assert e2.tobytes() == ev[:n].tobytes() and p2.tobytes() == pr[:n].tobytes()
+
+
+def test_fused_selfplay_bf16_equals_oracle_driven_by_the_same_network(oracle):
+    """Same as the fp32 fused test with the tensor-core evaluator: the kernel is deterministic
+    per position, so the oracle fed with its outputs must reproduce the fused run exactly."""
+    flat = cb.fold_batchnorm(cb.random_weights(33))
+    cfg = dict(num_games=40, seed=5, max_searches=48, searches_per_eval=16, c_puct=1.0, epsilon=0.25)
+    fused = cb.Trainer(cfg["num_games"], "", cfg["seed"], cfg["max_searches"], cfg["searches_per_eval"],
+                       cfg["c_puct"], cfg["epsilon"])
+    fused.set_weights(flat, 0, "bf16")
+    assert fused.run_selfplay(0, stagger=True)
+    helper = cb.Trainer(cfg["num_games"], "", 1, 16, cfg["searches_per_eval"])
+    helper.set_weights(flat, 0, "bf16")
+    o = oracle.trainer(**cfg)
+    r = run_trainer(o, lambda req: helper.evaluate(req))
+    gs, ev, pr = fused.write_samples()
+    assert fused.num_samples() == r["num_samples"]
+    assert gs.tobytes() == r["samples"][0].tobytes()
+    assert ev.tobytes() == r["samples"][1].tobytes()
+    assert pr.tobytes() == r["samples"][2].tobytes()
+    oc, ec = oracle.counters(o), fused.counters()
+    assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
