@@ -189,6 +189,39 @@ def time_cpu_reference(args, flat, games, budget_s=None):
                       % (games, args.sims, args.spe, "to completion" if complete else "time-bounded", cores)}
 
 
+def measure_game_logic(torch, cb, dev, n=1 << 26, reps=10):
+    """BASELINE.json configs[1]: legal-move generation + terminal test + do_move on reachable
+    states, device-resident (cb200_game_step_device). 64 Mi states per launch (>> L2: 1 GiB in,
+    2 GiB out); the states are produced on the device by the kernel itself from the start
+    position (next states fed back), so they are reachable. Returns states/s and the HBM
+    roofline with the algorithmic 46 B/state of SURVEY.md 8(d) (48 B actually moved)."""
+    import ctypes as C
+    L = cb.lib()
+    a = torch.zeros((n, 2), dtype=torch.int64, device=dev)
+    a[:, 1] = 0x0000040404040404  # start position
+    b = torch.empty_like(a)
+    mf = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    for r in range(12):  # random legal play: every state gets its own random move sequence
+        rc = L.cb200_game_step_device(n, C.c_void_p(a.data_ptr()), 1000 + r, C.c_void_p(mf.data_ptr()),
+                                      C.c_void_p(b.data_ptr()), None)
+        assert rc == 0
+        a, b = b, a
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(reps):
+        L.cb200_game_step_device(n, C.c_void_p(a.data_ptr()), 77 + r, C.c_void_p(mf.data_ptr()),
+                                 C.c_void_p(b.data_ptr()), None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    pk = peaks()
+    gbs = 46.0 * n / (ms * 1e-3) / 1e9
+    return {"states_per_sec": n / (ms * 1e-3), "states_per_launch": n, "ms_per_launch": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / pk["hbm_gbs"], "algorithmic_bytes_per_state": 46, "moved_bytes_per_state": 48}}
+
+
 # ----------------------------------------------------------------------------------------------
 def run_reference_arm(args, rank, world):
     if rank != 0:
@@ -257,7 +290,6 @@ def run_engine_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = L.cb200_launch_count()
-    tr.set_profiling(True)
     dev_ms, sims, moves, evals, iters = 0.0, 0, 0, 0, 0
     for k in range(args.steps):
         tr.reset(2000 + k)
@@ -270,10 +302,27 @@ def run_engine_arm(args, rank, world, local_rank):
         dev_ms += e0.elapsed_time(e1)
         c = tr.counters()
         sims += c["simulations"]; moves += c["moves"]; evals += c["leaf_evals"]; iters += c["iterations"]
+    launches = L.cb200_launch_count() - launches0
+    # ---- same steps again with a CUDA-event pair around every kernel launch (on the launching
+    # streams) for the per-kernel durations of the roofline; the event records cost host time,
+    # so `value` comes from the pass above and this pass is reported as ms_per_step_profiled
+    tr.set_profiling(True)
+    prof_ms, prof_sims, prof_evals = 0.0, 0, 0
+    for k in range(args.steps):
+        tr.reset(2000 + k)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.run_selfplay(0, stagger=False)
+        e1.record()
+        barrier()
+        prof_ms += e0.elapsed_time(e1)
+        c = tr.counters()
+        prof_sims += c["simulations"]; prof_evals += c["leaf_evals"]
     kt = tr.kernel_times()
     tr.set_profiling(False)
-    launches = L.cb200_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    game_logic = measure_game_logic(torch, cb, dev) if rank == 0 else None
 
     # ---- end-to-end steps through the public API with host buffers:
     # pinned weights -> device, seeds/control blocks -> device, self-play, samples (8 symmetries) -> host
@@ -323,15 +372,14 @@ def run_engine_arm(args, rank, world, local_rank):
     # dominant kernel = the class with the largest summed device time
     dom = max(kt, key=lambda k: kt[k]["ms"])
     share = {k: kt[k]["ms"] / max(1e-9, sum(v["ms"] for v in kt.values())) for k in kt}
-    sims_r0 = tr.counters()  # rank-0 counters of the last e2e step are not used for the roofline
     if dom == "network":
-        per_launch_flop = FLOP_PER_EVAL * (evals / world) / max(1, kt["network"]["launches"])
+        per_launch_flop = FLOP_PER_EVAL * prof_evals / max(1, kt["network"]["launches"])
         ach = per_launch_flop / (kt["network"]["ms"] / kt["network"]["launches"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roof = {"kernel": "k_mlp (policy/value network)", "bound": "tensor", "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
     else:
-        per_launch_bytes = ALGO_BYTES_PER_SIM * (sims / world) / max(1, kt["game_step"]["launches"])
+        per_launch_bytes = ALGO_BYTES_PER_SIM * prof_sims / max(1, kt["game_step"]["launches"])
         ach = per_launch_bytes / (kt["game_step"]["ms"] / kt["game_step"]["launches"] * 1e-3) / 1e9
         peak = pk["hbm_gbs"]
         roof = {"kernel": "k_iterate (tree search game step)", "bound": "hbm", "achieved": ach, "peak": peak,
@@ -340,11 +388,16 @@ def run_engine_arm(args, rank, world, local_rank):
     roof["kernel_time_share"] = share
     roof["kernel_ms"] = {k: kt[k]["ms"] for k in kt}
     roof["kernel_launches"] = {k: kt[k]["launches"] for k in kt}
+    roof["note"] = ("per-launch durations from CUDA events recorded on the launching streams during a second "
+                    "pass of the same K steps; kernels of different stream groups overlap, so the summed kernel "
+                    "time exceeds the step time. Whole-step algorithmic rates: %.1f GB/s tree traffic, %.2f "
+                    "TFLOP/s network" % (ALGO_BYTES_PER_SIM * prof_sims / (prof_ms * 1e-3) / 1e9,
+                                         FLOP_PER_EVAL * prof_evals / (prof_ms * 1e-3) / 1e12))
     # secondary roofline of the other heavy kernel, for the record
     if kt["network"]["launches"]:
-        roof["network_tflops"] = (FLOP_PER_EVAL * (evals / world) / (kt["network"]["ms"] * 1e-3)) / 1e12
+        roof["network_tflops"] = (FLOP_PER_EVAL * prof_evals / (kt["network"]["ms"] * 1e-3)) / 1e12
     if kt["game_step"]["launches"]:
-        roof["game_step_gbs"] = (ALGO_BYTES_PER_SIM * (sims / world) / (kt["game_step"]["ms"] * 1e-3)) / 1e9
+        roof["game_step_gbs"] = (ALGO_BYTES_PER_SIM * prof_sims / (kt["game_step"]["ms"] * 1e-3)) / 1e9
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -361,6 +414,8 @@ def run_engine_arm(args, rank, world, local_rank):
         "config": workload_desc(args, world),
         "moves_per_sec": moves / (dev_ms * 1e-3), "leaf_evals_per_sec": evals / (dev_ms * 1e-3),
         "simulations_per_step": sims / args.steps, "iterations_per_step": iters / args.steps,
+        "ms_per_step_profiled": prof_ms / args.steps, "stream_groups": int(os.environ.get("CB200_GROUPS", "8")),
+        "game_logic": game_logic,
         "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "seconds_per_step": e2e_s / args.steps,
                 "nccl_gather_seconds_per_step": gather_s / args.steps if world > 1 else 0.0},

@@ -83,6 +83,7 @@ def lib():
         "cb200_trainer_run_selfplay": (i32, [vp, i32, i32]),
         "cb200_trainer_dump_tree": (i32, [vp, i32, i32, vp, vp, i32]),
         "cb200_trainer_reset": (i32, [vp, i32]),
+        "cb200_trainer_phase_profile": (i32, [vp, i32, vp]),
         "cb200_trainer_set_profiling": (i32, [vp, i32]),
         "cb200_trainer_kernel_times": (i32, [vp, vp, vp]),
     }
@@ -297,6 +298,11 @@ class Trainer:
 
     def run_selfplay(self, max_iterations=0, stagger=False):
         return bool(_check(lib().cb200_trainer_run_selfplay(self._h, max_iterations, int(stagger))))
+
+    def phase_profile(self, enable=True):
+        out = np.zeros(8, np.uint64)
+        _check(lib().cb200_trainer_phase_profile(self._h, int(enable), _ptr(out)))
+        return out
 
     def reset(self, seed):
         _check(lib().cb200_trainer_reset(self._h, int(seed)))

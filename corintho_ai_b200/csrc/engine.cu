@@ -67,12 +67,19 @@ struct cb200_trainer {
   float *d_eval = nullptr, *d_probs = nullptr, *d_rows = nullptr;
   ulonglong2 *d_packed = nullptr;
   int32_t *d_offs = nullptr, *d_summary = nullptr, *d_soff = nullptr;
+  float *d_vsqrt = nullptr;
   int32_t *h_summary = nullptr;  // pinned
   NetF32 net32[2];
   NetTC nettc[2];
   int precision[2] = {-1, -1};
   std::vector<int32_t> h_ctl;
   int seed = 0;
+  // fused mode: games are split into independent stream groups (no lock-step across groups)
+  int n_groups = 1;
+  std::vector<cudaStream_t> g_stream;
+  std::vector<int> g_begin, g_end;
+  int32_t *d_gctr = nullptr;  // [n_groups][8] device counters (TreeParams::group_ctr)
+  int32_t *h_gctr = nullptr;  // pinned mirror
   // per-kernel-class CUDA-event timing (bench.py roofline): 0 scan, 1 pack, 2 network, 3 iterate
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -120,6 +127,12 @@ int upload_tables_once() {
   if (dev < 16 && sym_ready[dev]) return CB200_OK;
   CB_CUDA(cudaMemcpyToSymbol(d_space_sym, kCSpaceSym, sizeof(kCSpaceSym)));
   CB_CUDA(cudaMemcpyToSymbol(d_move_sym, kCMoveSym, sizeof(kCMoveSym)));
+  {
+    static double rcp[kTabSize + 1];
+    rcp[0] = 0.0;
+    for (int i = 1; i <= kTabSize; ++i) rcp[i] = 1.0 / (double)i;
+    CB_CUDA(cudaMemcpyToSymbol(d_rcp_tab, rcp, sizeof(rcp)));
+  }
   if (dev < 16) sym_ready[dev] = true;
   return CB200_OK;
 }
@@ -145,7 +158,9 @@ struct ProfScope {
   cb200_trainer *t;
   bool on;
   size_t idx = 0;
-  ProfScope(cb200_trainer *t_, int cls) : t(t_), on(t_->profiling) {
+  cudaStream_t st;
+  ProfScope(cb200_trainer *t_, int cls, cudaStream_t stream = G().stream)
+      : t(t_), on(t_->profiling), st(stream) {
     if (!on) return;
     if (2 * (t->ev_used + 1) > t->ev_pool.size()) {
       for (int k = 0; k < 2; ++k) {
@@ -157,10 +172,10 @@ struct ProfScope {
     }
     idx = t->ev_used++;
     t->ev_class[idx] = cls;
-    cudaEventRecord(t->ev_pool[2 * idx], G().stream);
+    cudaEventRecord(t->ev_pool[2 * idx], st);
   }
   ~ProfScope() {
-    if (on) cudaEventRecord(t->ev_pool[2 * idx + 1], G().stream);
+    if (on) cudaEventRecord(t->ev_pool[2 * idx + 1], st);
   }
 };
 
@@ -194,7 +209,7 @@ int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_
   const long prs = probs_move_major ? 1 : CB200_NUM_MOVES;
   const long pcs = probs_move_major ? (long)t->cap : 1;
   ProfScope ps(t, 3);
-  k_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
+  k_iterate<false><<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
                                                        to_play, t->iterations_done,
                                                        t->stagger_div);
   CB_LAUNCHED();
@@ -265,6 +280,7 @@ static int init_state(cb200_trainer *t) {
   CB_CUDA(cudaMemsetAsync(t->d_summary, 0, 4 * sizeof(int32_t), s));
   CB_CUDA(cudaMemsetAsync(t->d_eval, 0, t->cap * sizeof(float), s));
   CB_CUDA(cudaMemsetAsync(t->d_probs, 0, t->cap * CB200_NUM_MOVES * sizeof(float), s));
+  CB_CUDA(cudaMemsetAsync(t->d_gctr, 0, (size_t)t->n_groups * 8 * sizeof(int32_t), s));
   CB_CUDA(cudaStreamSynchronize(s));
   t->iterations_done = 0;
   return CB200_OK;
@@ -380,12 +396,55 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
             dmalloc(&t->d_rows, t->cap * CB200_STATE_SIZE) == CB200_OK &&
             dmalloc(&t->d_packed, t->cap) == CB200_OK && dmalloc(&t->d_offs, Gn) == CB200_OK &&
             dmalloc(&t->d_soff, Gn) == CB200_OK && dmalloc(&t->d_summary, 4) == CB200_OK &&
+            dmalloc(&t->d_vsqrt, kTabSize) == CB200_OK &&
             cudaMallocHost((void **)&t->h_summary, 4 * sizeof(int32_t)) == cudaSuccess;
   if (!ok) {
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
     cb200_trainer_destroy(t);
     return nullptr;
   }
+  // stream groups for the fused loop
+  int ng = 8;
+  if (const char *env = getenv("CB200_GROUPS")) ng = atoi(env);
+  if (ng < 1) ng = 1;
+  while (ng > 1 && num_games / ng < 64) ng /= 2;
+  t->n_groups = ng;
+  int per = ((num_games + ng - 1) / ng + kTreeWarps - 1) / kTreeWarps * kTreeWarps;
+  for (int g = 0; g < ng; ++g) {
+    int b = g * per, e = b + per < num_games ? b + per : num_games;
+    if (b >= num_games) {
+      t->n_groups = g;
+      break;
+    }
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error(CB200_ERR_CUDA, "cudaStreamCreate failed");
+      cb200_trainer_destroy(t);
+      return nullptr;
+    }
+    t->g_stream.push_back(st), t->g_begin.push_back(b), t->g_end.push_back(e);
+  }
+  if (dmalloc(&t->d_gctr, (size_t)t->n_groups * 8) != CB200_OK ||
+      cudaMallocHost((void **)&t->h_gctr, (size_t)t->n_groups * 8 * sizeof(int32_t)) != cudaSuccess) {
+    if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
+    cb200_trainer_destroy(t);
+    return nullptr;
+  }
+  {
+    // v_sqrt = c_puct * sqrt(float(visits)) exactly as the reference evaluates it
+    // (trainmc.cpp:549: float * double sqrt(double) -> float), tabulated on the host
+    std::vector<float> tab(kTabSize);
+    for (int v = 0; v < kTabSize; ++v) tab[v] = (float)((double)c_puct * sqrt((double)(float)v));
+    if (cudaMemcpy(t->d_vsqrt, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error(CB200_ERR_CUDA, "vsqrt table upload failed");
+      cb200_trainer_destroy(t);
+      return nullptr;
+    }
+    P.vsqrt_tab = t->d_vsqrt;
+  }
+  P.game_begin = 0, P.game_end = num_games, P.group_row0 = 0, P.group_ctr = nullptr;
+  P.packed = t->d_packed;
+  P.phase_prof = nullptr;
   t->seed = seed;
   if (init_state(t) != CB200_OK) {
     cb200_trainer_destroy(t);
@@ -400,6 +459,25 @@ cb200_trainer *cb200_trainer_create(int num_games, const char *log_folder, int s
   (void)num_threads;
   return cb200_trainer_create_shard(num_games, 0, num_games, log_folder, seed, max_searches,
                                     searches_per_eval, c_puct, epsilon, num_logged, testing);
+}
+
+// debug: straggler instrumentation of the game-step kernel (see TreeParams::phase_prof)
+int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[8]) {
+  int rc = guard(t);
+  if (rc) return rc;
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  if (t->P.phase_prof && out) {
+    CB_CUDA(cudaMemcpy(out, t->P.phase_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemset(t->P.phase_prof, 0, 8 * sizeof(uint64_t)));
+  }
+  if (enable && !t->P.phase_prof) {
+    CB_CUDA(cudaMalloc((void **)&t->P.phase_prof, 8 * sizeof(uint64_t)));
+    CB_CUDA(cudaMemset(t->P.phase_prof, 0, 8 * sizeof(uint64_t)));
+  } else if (!enable && t->P.phase_prof) {
+    cudaFree(t->P.phase_prof);
+    t->P.phase_prof = nullptr;
+  }
+  return CB200_OK;
 }
 
 int cb200_trainer_reset(cb200_trainer *t, int seed) {
@@ -436,8 +514,12 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
   cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);
   cudaFree(t->d_eval), cudaFree(t->d_probs), cudaFree(t->d_rows), cudaFree(t->d_packed);
-  cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary);
+  cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
+  cudaFree(t->d_vsqrt);
   if (t->h_summary) cudaFreeHost(t->h_summary);
+  if (t->h_gctr) cudaFreeHost(t->h_gctr);
+  cudaFree(t->d_gctr);
+  for (cudaStream_t st : t->g_stream) cudaStreamDestroy(st);
   for (int m = 0; m < 2; ++m) {
     cudaFree(t->net32[m].w);
     net_tc_free(t->nettc[m]);
@@ -707,6 +789,82 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
   return CB200_OK;
 }
 
+// Fused training-mode loop: every stream group runs [network -> game step] per iteration on its
+// own stream; groups never wait for each other, so one slow game (a long re-rooting) only delays
+// its own group while the other groups keep the SMs and the tensor cores busy.
+static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
+  const int model = 0;
+  const bool tc = t->precision[model] == 1;
+  const long prs = tc ? 1 : CB200_NUM_MOVES, pcs = tc ? (long)t->cap : 1;
+  const int ng = t->n_groups;
+  std::vector<char> active(ng, 1);
+  // work queued on the default stream (weights, reset) must be visible to the group streams
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  int done_iters = 0, result = 0;
+  while (max_iterations <= 0 || done_iters < max_iterations) {
+    int batch = 32;
+    if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
+    for (int i = 0; i < batch; ++i) {
+      const int it = t->iterations_done;
+      for (int g = 0; g < ng; ++g) {
+        if (!active[g]) continue;
+        cudaStream_t st = t->g_stream[g];
+        const int gb = t->g_begin[g], ge = t->g_end[g];
+        const int row0 = gb * t->P.spe, rows = (ge - gb) * t->P.spe;
+        int32_t *ctr = t->d_gctr + g * 8;
+        int rc;
+        {
+          ProfScope ps(t, 2, st);
+          if (tc)
+            rc = launch_mlp_tc(t->nettc[model], t->d_packed + row0, ctr + (it & 1), 0, rows, t->d_eval + row0,
+                               t->d_probs + row0, (int)t->cap, ctr + ((it + 1) & 1), st, true);
+          else
+            rc = launch_mlp_f32(t->net32[model], t->d_packed + row0, ctr + (it & 1), 0, rows, t->d_eval + row0,
+                                t->d_probs + (size_t)row0 * CB200_NUM_MOVES, ctr + ((it + 1) & 1), st, true);
+        }
+        if (rc != CB200_OK) return rc;
+        TreeParams P = t->P;
+        P.game_begin = gb, P.game_end = ge, P.group_row0 = row0, P.group_ctr = ctr;
+        {
+          ProfScope ps(t, 3, st);
+          k_iterate<true><<<(ge - gb + kTreeWarps - 1) / kTreeWarps, kTreeWarps * 32, 0, st>>>(
+              P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, t->stagger_div);
+          CB_LAUNCHED();
+        }
+        CB_CUDA(cudaGetLastError());
+      }
+      ++t->iterations_done;
+    }
+    done_iters += batch;
+    for (int g = 0; g < ng; ++g)
+      if (active[g])
+        CB_CUDA(cudaMemcpyAsync(t->h_gctr + g * 8, t->d_gctr + g * 8, 8 * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, t->g_stream[g]));
+    for (int g = 0; g < ng; ++g)
+      if (active[g]) CB_CUDA(cudaStreamSynchronize(t->g_stream[g]));
+    if (t->profiling) {
+      int rc = prof_drain(t);
+      if (rc != CB200_OK) return rc;
+    }
+    const int par = t->iterations_done & 1;
+    long long live = 0;
+    for (int g = 0; g < ng; ++g) {
+      if (!active[g]) continue;
+      const int32_t *c = t->h_gctr + g * 8;
+      if (c[4] != 0)
+        return set_error(c[4], "a game overflowed its node arena / path / sample buffer (raise "
+                               "CB200_ARENA_NODES) or reached an impossible state");
+      if (c[2 + par] == 0 && c[par] == 0) active[g] = 0;
+      live += c[2 + par];
+    }
+    if (live == 0) {
+      result = 1;
+      break;
+    }
+  }
+  return result;
+}
+
 int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger) {
   int rc = guard(t);
   if (rc) return rc;
@@ -715,6 +873,12 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
     return set_error(CB200_ERR_STATE, "cb200_trainer_run_selfplay: set weights first");
   const int saved_div = t->stagger_div;
   if (!stagger) t->stagger_div = 0;
+  if (!testing) {
+    rc = run_selfplay_groups(t, max_iterations);
+    t->stagger_div = saved_div;
+    return rc;
+  }
+  // two-model (gating match) mode: single lock-step group, requests packed per side
   const int n_max = (int)t->cap;
   int done_iters = 0;
   int result = 0;
@@ -722,21 +886,13 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
     int batch = 32;
     if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
     for (int i = 0; i < batch && rc == CB200_OK; ++i) {
-      if (!testing) {
-        // answers for the requests of the previous step, then the step itself
-        rc = scan(t, -1);
-        if (rc == CB200_OK) rc = pack(t, -1, nullptr, t->d_packed);
-        if (rc == CB200_OK) rc = run_net(t, 0, t->d_packed, t->d_summary, 0, n_max);
-        if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, -1, t->precision[0] == 1);
-      } else {
-        for (int tp = 0; tp < 2 && rc == CB200_OK; ++tp) {  // model 0 = "new" serves to_play 0
-          rc = scan(t, tp);
-          if (rc == CB200_OK) rc = pack(t, tp, nullptr, t->d_packed);
-          if (rc == CB200_OK) rc = run_net(t, tp == 0 ? 0 : 1, t->d_packed, t->d_summary, 0, n_max);
-          if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, tp, t->precision[tp == 0 ? 0 : 1] == 1);
-        }
-        ++t->iterations_done;
+      for (int tp = 0; tp < 2 && rc == CB200_OK; ++tp) {  // model 0 = "new" serves to_play 0
+        rc = scan(t, tp);
+        if (rc == CB200_OK) rc = pack(t, tp, nullptr, t->d_packed);
+        if (rc == CB200_OK) rc = run_net(t, tp == 0 ? 0 : 1, t->d_packed, t->d_summary, 0, n_max);
+        if (rc == CB200_OK) rc = iterate(t, t->d_eval, t->d_probs, tp, t->precision[tp == 0 ? 0 : 1] == 1);
       }
+      ++t->iterations_done;
     }
     done_iters += batch;
     if (rc == CB200_OK) rc = scan(t, -1);

@@ -36,7 +36,7 @@ constexpr size_t kMlpSmemBytes =
 __global__ void __launch_bounds__(kNetThreads, 1)
     k_mlp_f32(const float *__restrict__ W, const ulonglong2 *__restrict__ states,
               const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
-              float *__restrict__ probs) {
+              float *__restrict__ probs, int32_t *__restrict__ zero2) {
   extern __shared__ float smf[];
   float *act0 = smf;                              // [100][128]
   float *act1 = act0 + kNetHidden * kNetTile;     // [100][128]
@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(kNetThreads, 1)
   float *rmax = bsm + kNetNPad;                   // [128]
   float *rsum = rmax + kNetTile;                  // [128]
   const int n = n_ptr ? *n_ptr : n_static;
+  if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int tile = blockIdx.x; tile * kNetTile < n; tile += gridDim.x) {
     const int p0 = tile * kNetTile;
@@ -158,7 +159,9 @@ inline int net_f32_upload(NetF32 &net, const float *weights) {
 }
 
 inline int launch_mlp_f32(const NetF32 &net, const ulonglong2 *d_states, const int32_t *d_n,
-                          int n_static, int n_max, float *d_eval, float *d_probs) {
+                          int n_static, int n_max, float *d_eval, float *d_probs,
+                          int32_t *zero2 = nullptr, cudaStream_t stream = nullptr,
+                          bool use_stream = false) {
   static bool attr_set[16] = {false};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -171,8 +174,8 @@ inline int launch_mlp_f32(const NetF32 &net, const ulonglong2 *d_states, const i
   if (n_max <= 0) return CB200_OK;
   int tiles = (n_max + kNetTile - 1) / kNetTile;
   int grid = tiles < sms ? tiles : sms;
-  k_mlp_f32<<<grid, kNetThreads, kMlpSmemBytes, G().stream>>>(net.w, d_states, d_n, n_static,
-                                                              d_eval, d_probs);
+  k_mlp_f32<<<grid, kNetThreads, kMlpSmemBytes, use_stream ? stream : G().stream>>>(
+      net.w, d_states, d_n, n_static, d_eval, d_probs, zero2);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;

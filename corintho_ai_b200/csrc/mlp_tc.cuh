@@ -128,7 +128,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __global__ void __launch_bounds__(kTcThreads, 2)
     k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
              const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
-             float *__restrict__ probs, int probs_ld) {
+             float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sA = smem;                                // 2 x kTcABytes
   uint8_t *sW = smem + 2 * kTcABytes;                // 2 x kTcLayerBytes
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int wg = t >> 7;                             // warpgroup = tile within the CTA
   const int row = t & 127;                           // row of the tile owned by this thread
   const int n = n_ptr ? *n_ptr : n_static;
+  if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;  // next parity's counters
   const uint32_t wbar0 = smem_u32(bars), mbar0 = smem_u32(bars + 2);
   if (t == 0) {
     mbar_init(wbar0, 1), mbar_init(wbar0 + 8, 1);
@@ -329,7 +330,9 @@ inline void net_tc_free(NetTC &net) {
 }
 
 inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int32_t *d_n,
-                         int n_static, int n_max, float *d_eval, float *d_probs, int probs_ld) {
+                         int n_static, int n_max, float *d_eval, float *d_probs, int probs_ld,
+                         int32_t *zero2 = nullptr, cudaStream_t stream = nullptr,
+                         bool use_stream = false) {
   static bool attr_set[16] = {false};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -342,8 +345,8 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   if (n_max <= 0) return CB200_OK;
   const int pairs = (n_max + 255) / 256;
   const int grid = pairs < 2 * sms ? pairs : 2 * sms;
-  k_mlp_tc<<<grid, kTcThreads, kTcSmemBytes, G().stream>>>((const uint8_t *)net.w, d_states, d_n,
-                                                           n_static, d_eval, d_probs, probs_ld);
+  k_mlp_tc<<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+      (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;

@@ -149,33 +149,46 @@ CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
       }
     }
   }
-  // ---- long diagonals (game.cpp:317-360): main then anti; long > upper > lower
+  // ---- diagonals. Three equal tops with square step 5 (bases 0,5 = main diagonal upper/lower,
+  // 1 = S1, 4 = S3) or step 3 (bases 3,6 = anti-diagonal upper/lower, 2 = S0, 7 = S2).
   {
-    auto match = [&](uint32_t M) -> int {
-      return ((T0 & M) == M) ? 0 : ((T1 & M) == M) ? 1 : ((T2 & M) == M) ? 2 : -1;
-    };
-    int t, D = -1;
-    if ((t = match(0x8421u)) >= 0) D = 2;        // D0B
-    else if ((t = match(0x0421u)) >= 0) D = 0;   // D0U
-    else if ((t = match(0x8420u)) >= 0) D = 1;   // D0D
-    else if ((t = match(0x1248u)) >= 0) D = 5;   // D1B
-    else if ((t = match(0x0248u)) >= 0) D = 3;   // D1U
-    else if ((t = match(0x1240u)) >= 0) D = 4;   // D1D
-    if (D >= 0) {
-      lines = true;
-      const uint32_t *lb = LB(72 + D * 3 + t);
-      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
-    }
-    // ---- short diagonals (game.cpp:362-391): S0..S3
-    D = -1;
-    if ((t = match(0x0124u)) >= 0) D = 6;
-    else if ((t = match(0x0842u)) >= 0) D = 7;
-    else if ((t = match(0x2480u)) >= 0) D = 8;
-    else if ((t = match(0x4210u)) >= 0) D = 9;
-    if (D >= 0) {
-      lines = true;
-      const uint32_t *lb = LB(72 + D * 3 + t);
-      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+    const uint32_t A5 = T0 & (T0 >> 5) & (T0 >> 10), B5 = T1 & (T1 >> 5) & (T1 >> 10),
+                   C5 = T2 & (T2 >> 5) & (T2 >> 10);
+    const uint32_t A3 = T0 & (T0 >> 3) & (T0 >> 6), B3 = T1 & (T1 >> 3) & (T1 >> 6),
+                   C3 = T2 & (T2 >> 3) & (T2 >> 6);
+    const uint32_t D5 = (A5 | B5 | C5) & 0x33u, D3 = (A3 | B3 | C3) & 0xCCu;
+    if (D5 | D3) {
+      // long diagonals (game.cpp:317-360): main then anti; long > upper > lower
+      int D = -1, base = 0, step5 = 1;
+      if (D5 & 0x21u) {
+        const bool up = D5 & 0x01u, lo = D5 & 0x20u;
+        D = (up && lo) ? 2 : (up ? 0 : 1);  // D0B, D0U, D0D
+        base = up ? 0 : 5;
+      } else if (D3 & 0x48u) {
+        const bool up = D3 & 0x08u, lo = D3 & 0x40u;
+        D = (up && lo) ? 5 : (up ? 3 : 4);  // D1B, D1U, D1D
+        base = up ? 3 : 6, step5 = 0;
+      }
+      if (D >= 0) {
+        const uint32_t b1 = step5 ? B5 : B3, b2 = step5 ? C5 : C3;
+        const int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
+        lines = true;
+        const uint32_t *lb = LB(72 + D * 3 + t);
+        m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+      }
+      // short diagonals (game.cpp:362-391): S0..S3, first found
+      D = -1;
+      if (D3 & 0x04u) D = 6, base = 2, step5 = 0;
+      else if (D5 & 0x02u) D = 7, base = 1, step5 = 1;
+      else if (D3 & 0x80u) D = 8, base = 7, step5 = 0;
+      else if (D5 & 0x10u) D = 9, base = 4, step5 = 1;
+      if (D >= 0) {
+        const uint32_t b1 = step5 ? B5 : B3, b2 = step5 ? C5 : C3;
+        const int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
+        lines = true;
+        const uint32_t *lb = LB(72 + D * 3 + t);
+        m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+      }
     }
   }
   m[0] = m0, m[1] = m1, m[2] = m2;

@@ -31,10 +31,14 @@ constexpr int kMaxSamples = 64;
 constexpr int kTreeWarps = 4;  // games per CTA
 constexpr int kCtlWords = 16;
 constexpr int kTreeCtlWords = 8;
+constexpr int kTabSize = 4096;  // visit counts served by the sqrt / reciprocal tables
+
+// RN(1.0 / i) as doubles, i in [0, kTabSize]; uploaded by ensure_tree_tables()
+__device__ double d_rcp_tab[kTabSize + 1];
 
 enum CtlWord {
   CW_TO_PLAY = 0, CW_PARITY, CW_RESULT, CW_MATE_TURN, CW_N_SAMPLES, CW_N_PENDING, CW_ERROR,
-  CW_DONE, CW_SPARE, CW_MT_IDX
+  CW_DONE, CW_SPARE, CW_MT_IDX, CW_REQ_BASE
 };
 enum TreeWord {
   TW_ARENA = 0, TW_HAS_ROOT, TW_USED, TW_ROOT_EVAL, TW_ROOT_VISITS, TW_ROOT_RESULT, TW_ROOT_ALLV,
@@ -56,12 +60,32 @@ struct TreeParams {
   ulonglong2 *sample_state;  // [G][kMaxSamples]
   float *sample_probs;       // [G][kMaxSamples][96]
   long long *counters;       // [G][4] simulations, moves, leaf evals, (unused)
+  const float *vsqrt_tab;    // [kTabSize] (float)(c_puct * sqrt((double)(float)v)), host-computed
+  // fused (device-resident) mode: the kernel instance covers games [game_begin, game_end) of one
+  // stream group; request rows are handed out with one atomicAdd per game
+  int game_begin, game_end;
+  int group_row0;            // first request row owned by this group
+  int32_t *group_ctr;        // [0..1] request count per parity, [2..3] live games per parity, [4] error
+  ulonglong2 *packed;        // [num_games*spe] leaf cstates in request-row order
+  // optional straggler instrumentation (null = off): [0..2] max cycles of one warp in ingest /
+  // search / move phases, [3..5] summed cycles, [6] rolled-back searches, [7] words re-rooted
+  unsigned long long *phase_prof;
 };
 
+constexpr int kFlatCap = 448;  // legal-move slots processed per flat ingest chunk
 struct WarpSm {
-  float f[96];
+  __align__(16) float f[100];
   uint32_t node[kMaxPath + 1];
   uint32_t slot[kMaxPath + 1];
+  // flat eval-ingest scratch (receive_eval): per-element and per-leaf arrays
+  float fval[kFlatCap];
+  float dval[kFlatCap];
+  uint8_t mv[kFlatCap];
+  uint32_t l_off[32];
+  int l_n[32];
+  int l_pre[33];
+  float l_a[32];
+  float l_b[32];
 };
 
 // ---- slot word 3 ---------------------------------------------------------------------------
@@ -90,6 +114,15 @@ __device__ __forceinline__ uint32_t fkey(float f) {  // order-preserving float -
 }
 constexpr uint32_t kKeyNegInf = 0x007FFFFFu;
 
+// 1/x for a positive normal double: rcp.approx.ftz.f64 (>= 20 good bits) refined twice
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -106,6 +139,7 @@ struct Ctx {
   int to_play, parity, result, mate_turn, n_samples, n_pending, error, spare, mt_idx;
   long long d_sims, d_evals;
   int d_moves;
+  long long t_ingest, t_search, t_move, n_none, n_copy;
   // current tree (trainmc.h:160-188)
   int cur_p, arena, has_root;
   uint32_t used;
@@ -147,19 +181,32 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 18;
   return y;
 }
+// In-place regeneration of the 624-word state in three batches (new[i] depends on old[i],
+// old[i+1] and, for i >= 227, on new[i-227]): [0,224) uses only old words, [224,448) needs new
+// words < 221, [448,624) needs new words < 397 and new[0]. One load round-trip per batch.
 __device__ __noinline__ void mt_twist(Ctx &c) {
   uint32_t *mt = c.mt;
-  for (int cb = 0; cb < 624; cb += 32) {
-    const int i = cb + c.lane;
-    uint32_t v = 0;
-    if (i < 624) {
-      const uint32_t a = mt[i], b = mt[i + 1 == 624 ? 0 : i + 1];
-      const uint32_t m = mt[i + 397 >= 624 ? i + 397 - 624 : i + 397];
-      const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-      v = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+#pragma unroll 1
+  for (int b0 = 0; b0 < 624; b0 += 224) {
+    const int b1 = b0 + 224 < 624 ? b0 + 224 : 624;
+    uint32_t v[7];
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int i = b0 + c.lane + 32 * u;
+      v[u] = 0;
+      if (i < b1) {
+        const uint32_t a = mt[i], b = mt[i + 1 == 624 ? 0 : i + 1];
+        const uint32_t m = mt[i + 397 >= 624 ? i + 397 - 624 : i + 397];
+        const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        v[u] = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
     }
     __syncwarp();
-    if (i < 624) mt[i] = v;
+#pragma unroll
+    for (int u = 0; u < 7; ++u) {
+      const int i = b0 + c.lane + 32 * u;
+      if (i < b1) mt[i] = v[u];
+    }
     __syncwarp();
   }
   c.mt_idx = 0;
@@ -334,12 +381,13 @@ __device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
   c.base = dst;
   c.used = alloc;
   c.searches_done = 0;
+  c.n_copy += alloc;
 }
 
 // ---- TrainMC::receiveEval (trainmc.cpp:269-296) ---------------------------------------------
 // probs element (answer row k, move m) = probs[k * prs + m * pcs]: row-major [n][96] from the
 // host API (prs 96, pcs 1), move-major [96][ld] from the tensor-core network (prs 1, pcs ld)
-__device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &sm,
+__device__ __noinline__ void receive_eval_serial(Ctx &c, const TreeParams &P, WarpSm &sm,
                                           const float *eval, const float *probs, long prs,
                                           long pcs) {
   const int np = c.n_pending;
@@ -350,54 +398,63 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
     uint32_t *r = c.base + leaf_off;
     const int n = (int)(r[4] & 0xffu);
     const float *pk = probs + (long)k * prs;
-    // getFilteredProbs (trainmc.cpp:212-234): gather legal priors, float sum in edge order
-    uint32_t w3[3];
-    float fv[3];
+    // getFilteredProbs (trainmc.cpp:212-234): gather legal priors, float sum in edge order.
+    // Pass j handles edges 32j..32j+31; passes beyond n are skipped warp-uniformly.
+    const int np4 = (n + 3) & ~3;
+    uint32_t w3[3] = {0, 0, 0};
+    float fv[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int e = c.lane + 32 * j;
-      w3[j] = 0, fv[j] = 0.0f;
-      if (e < n) {
-        w3[j] = r[8 + 4 * e + 3];
-        fv[j] = pk[(long)s3_move(w3[j]) * pcs];
-        sm.f[e] = fv[j];
+      if (32 * j < np4) {
+        const int e = c.lane + 32 * j;
+        if (e < n) {
+          w3[j] = r[8 + 4 * e + 3];
+          fv[j] = pk[(long)s3_move(w3[j]) * pcs];
+        }
+        if (e < np4) sm.f[e] = fv[j];  // zero padding up to a multiple of 4 (x + 0 is exact)
       }
     }
     __syncwarp();
     float sum = 0.0f;
-    for (int j = 0; j < n; ++j) sum = __fadd_rn(sum, sm.f[j]);
-    float scalar = __double2float_rn(
-        __dmul_rn(__ddiv_rn(1.0, (double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
+    for (int j = 0; j < np4; j += 4) {
+      const float4 v = *reinterpret_cast<const float4 *>(sm.f + j);
+      sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
+    }
+    const float scalar = __double2float_rn(
+        __dmul_rn(__drcp_rn((double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
     __syncwarp();
     // generateDirichlet (trainmc.cpp:236-246): one MT draw per legal move, in edge order
     uint32_t rnd[3];
     rng_block(c, n, rnd);
-    float dv[3];
+    float dv[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int e = c.lane + 32 * j;
-      dv[j] = 0.0f;
-      if (e < n) {
-        dv[j] = d_gamma[rnd[j] & 1023u];
-        sm.f[e] = dv[j];
+      if (32 * j < np4) {
+        const int e = c.lane + 32 * j;
+        if (e < n) dv[j] = d_gamma[rnd[j] & 1023u];
+        if (e < np4) sm.f[e] = dv[j];
       }
     }
     __syncwarp();
     float dsum = 0.0f;
-    for (int j = 0; j < n; ++j) dsum = __fadd_rn(dsum, sm.f[j]);
+    for (int j = 0; j < np4; j += 4) {
+      const float4 v = *reinterpret_cast<const float4 *>(sm.f + j);
+      dsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(dsum, v.x), v.y), v.z), v.w);
+    }
     const float dscalar =
-        __double2float_rn(__dmul_rn(__ddiv_rn(1.0, (double)dsum), (double)P.epsilon));
+        __double2float_rn(__dmul_rn(__drcp_rn((double)dsum), (double)P.epsilon));
     __syncwarp();
     // setProbs (trainmc.cpp:248-267)
-    float wv[3];
+    float wv[3] = {0.0f, 0.0f, 0.0f};
     float mx = 0.0f;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int e = c.lane + 32 * j;
-      wv[j] = 0.0f;
-      if (e < n) {
-        wv[j] = __fadd_rn(__fmul_rn(fv[j], scalar), __fmul_rn(dv[j], dscalar));
-        mx = fmaxf(mx, wv[j]);
+      if (32 * j < n) {
+        const int e = c.lane + 32 * j;
+        if (e < n) {
+          wv[j] = __fadd_rn(__fmul_rn(fv[j], scalar), __fmul_rn(dv[j], dscalar));
+          mx = fmaxf(mx, wv[j]);
+        }
       }
     }
 #pragma unroll
@@ -406,19 +463,20 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
     int qsum = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int e = c.lane + 32 * j;
-      if (e < n) {
-        // lround(): round half away from zero; exact in double for |x| < 2^51
-        const double x = (double)__fmul_rn(wv[j], denom);
-        const long long q = (long long)floor(x + 0.5);
-        const int prob = q < 1 ? 1 : (int)q;
-        r[8 + 4 * e + 3] = (w3[j] & ~(0x1ffu << 7)) | (((uint32_t)prob & 0x1ffu) << 7);
-        qsum += prob;
+      if (32 * j < n) {
+        const int e = c.lane + 32 * j;
+        if (e < n) {
+          // lround(): round half away from zero; x >= 0 here, exact in double
+          const double x = (double)__fmul_rn(wv[j], denom);
+          const long long q = (long long)floor(x + 0.5);
+          const int prob = q < 1 ? 1 : (int)q;
+          r[8 + 4 * e + 3] = (w3[j] & ~(0x1ffu << 7)) | (((uint32_t)prob & 0x1ffu) << 7);
+          qsum += prob;
+        }
       }
     }
     qsum = __reduce_add_sync(kFull, qsum);
-    if (c.lane == 0)
-      r[5] = __float_as_uint(__double2float_rn(__ddiv_rn(1.0, (double)(float)qsum)));
+    if (c.lane == 0) r[5] = __float_as_uint(__double2float_rn(__drcp_rn((double)(float)qsum)));
     // backup (trainmc.cpp:281-292): the leaf takes e-1, its parent -e-1, ... up to the root
     const float ev = eval[k];
     for (int l0 = 0; l0 < path_len; l0 += 32) {
@@ -438,6 +496,204 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
     }
     __syncwarp();
   }
+  c.root_allv = 0;
+  c.d_evals += np;
+  c.n_pending = 0;
+}
+
+// largest k in [k0, k1) with pre[k] <= i
+__device__ __forceinline__ int find_leaf(const int *pre, int k0, int k1, int i) {
+  int lo = k0, hi = k1 - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (pre[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ---- TrainMC::receiveEval (trainmc.cpp:269-296), latency-oriented restatement ----------------
+// Same arithmetic, in the same order per leaf, as receive_eval_serial (which mirrors the
+// reference loop literally), but organised so that the loads of ALL pending leaves are in
+// flight together:
+//   "flat" phases  : one lane per legal-move slot over the concatenation of all leaves
+//                    (the MT19937 draw of flat element i is simply draw number i);
+//   "leaf" phases  : one lane per leaf for the order-dependent float sums / max / integer sum;
+//   backup         : per tree level, the lanes whose paths meet in the same slot are grouped with
+//                    __match_any_sync and the lowest lane applies the adds in leaf order.
+__device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &sm,
+                                          const float *eval, const float *probs, long prs,
+                                          long pcs) {
+  const int np = c.n_pending;
+  if (np > 32) {
+    receive_eval_serial(c, P, sm, eval, probs, prs, pcs);
+    return;
+  }
+  const int lane = c.lane;
+  // ---- leaf phase 0: pending records and leaf headers
+  uint32_t my_off = 0;
+  int my_n = 0, my_plen = 0;
+  float my_ev = 0.0f;
+  const uint32_t *my_pd = c.pending + lane * kPendWords;
+  if (lane < np) {
+    my_off = my_pd[0];
+    my_plen = (int)my_pd[1];
+    my_ev = eval[lane];
+    my_n = (int)(c.base[my_off + 4] & 0xffu);
+  }
+  const int incl = (int)warp_incl_scan((uint32_t)my_n, lane);
+  sm.l_pre[lane] = incl - my_n;
+  if (lane == 31) sm.l_pre[32] = incl;
+  sm.l_off[lane] = my_off;
+  sm.l_n[lane] = my_n;
+  __syncwarp();
+  for (int k0 = 0; k0 < np;) {
+    // chunk [k0, k1): as many leaves as fit in the scratch arrays
+    int k1 = k0 + 1;
+    const int base_i = sm.l_pre[k0];
+    while (k1 < np && sm.l_pre[k1 + 1] - base_i <= kFlatCap) ++k1;
+    const int T = sm.l_pre[k1] - base_i;
+    if (T > kFlatCap) {  // a single leaf with more than kFlatCap moves cannot exist (<= 96)
+      c.error = CB200_ERR_STATE;
+      return;
+    }
+    const bool mine = lane >= k0 && lane < k1;
+    const int my_i0 = sm.l_pre[lane] - base_i;
+    int nmax = mine ? my_n : 0;
+    nmax = __reduce_max_sync(kFull, nmax);
+    // ---- flat phase 1: move ids and network priors of every legal move (getFilteredProbs).
+    // Four elements per lane per trip, loads grouped so that they overlap.
+    for (int i0 = 0; i0 < T; i0 += 128) {
+      int kk[4];
+      uint32_t w3[4];
+      float pv4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        kk[u] = 0, w3[u] = 0;
+        if (i < T) {
+          kk[u] = find_leaf(sm.l_pre, k0, k1, i + base_i);
+          w3[u] = c.base[sm.l_off[kk[u]] + 8 + 4 * (i + base_i - sm.l_pre[kk[u]]) + 3];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        pv4[u] = 0.0f;
+        if (i < T) pv4[u] = probs[(long)kk[u] * prs + (long)s3_move(w3[u]) * pcs];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + lane + 32 * u;
+        if (i < T) sm.mv[i] = (uint8_t)s3_move(w3[u]), sm.fval[i] = pv4[u];
+      }
+    }
+    __syncwarp();
+    // ---- leaf phase 2: float sum in edge order, scalar = 1/sum * (1 - eps)
+    {
+      float sum = 0.0f;
+      for (int j = 0; j < nmax; ++j)
+        if (mine && j < my_n) sum = __fadd_rn(sum, sm.fval[my_i0 + j]);
+      if (mine)
+        sm.l_a[lane] = __double2float_rn(
+            __dmul_rn(__drcp_rn((double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
+    }
+    // ---- flat phase 3: one MT19937 draw per slot, in order (generateDirichlet)
+    for (int done = 0; done < T;) {
+      if (c.mt_idx >= 624) mt_twist(c);
+      const int seg = min(624 - c.mt_idx, T - done);
+      for (int i0 = 0; i0 < seg; i0 += 128) {
+        uint32_t y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + lane + 32 * u;
+          y[u] = i < seg ? c.mt[c.mt_idx + i] : 0u;
+        }
+        float g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = d_gamma[mt_temper(y[u]) & 1023u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + lane + 32 * u;
+          if (i < seg) sm.dval[done + i] = g[u];
+        }
+      }
+      c.mt_idx += seg;
+      done += seg;
+      __syncwarp();
+    }
+    // ---- leaf phase 4: noise sum, dscalar = 1/sum * eps
+    {
+      float dsum = 0.0f;
+      for (int j = 0; j < nmax; ++j)
+        if (mine && j < my_n) dsum = __fadd_rn(dsum, sm.dval[my_i0 + j]);
+      if (mine)
+        sm.l_b[lane] =
+            __double2float_rn(__dmul_rn(__drcp_rn((double)dsum), (double)P.epsilon));
+    }
+    __syncwarp();
+    // ---- flat phase 5: weighted = filtered*scalar + dirichlet*dscalar (setProbs)
+    for (int i = lane; i < T; i += 32) {
+      const int k = find_leaf(sm.l_pre, k0, k1, i + base_i);
+      sm.fval[i] = __fadd_rn(__fmul_rn(sm.fval[i], sm.l_a[k]), __fmul_rn(sm.dval[i], sm.l_b[k]));
+    }
+    __syncwarp();
+    // ---- leaf phase 6: max (from 0.0f), denom = 511 / max
+    {
+      float mx = 0.0f;
+      for (int j = 0; j < nmax; ++j)
+        if (mine && j < my_n) mx = fmaxf(mx, sm.fval[my_i0 + j]);
+      if (mine) sm.l_a[lane] = __fdiv_rn(511.0f, mx);
+    }
+    __syncwarp();
+    // ---- flat phase 7: 9-bit integer priors. A leaf is evaluated before it can get children,
+    // so its slot words are still {0, 0, 0, move}: the new word is move | prior << 7.
+    for (int i = lane; i < T; i += 32) {
+      const int k = find_leaf(sm.l_pre, k0, k1, i + base_i);
+      const int j = i + base_i - sm.l_pre[k];
+      const double x = (double)__fmul_rn(sm.fval[i], sm.l_a[k]);
+      const long long q = (long long)floor(x + 0.5);  // lround for x >= 0
+      const int prob = q < 1 ? 1 : (int)q;
+      c.base[sm.l_off[k] + 8 + 4 * j + 3] = (uint32_t)sm.mv[i] | (((uint32_t)prob & 0x1ffu) << 7);
+      sm.dval[i] = __int_as_float(prob);
+    }
+    __syncwarp();
+    // ---- leaf phase 8: denominator = 1 / float(sum of integer priors)
+    {
+      int qsum = 0;
+      for (int j = 0; j < nmax; ++j)
+        if (mine && j < my_n) qsum += __float_as_int(sm.dval[my_i0 + j]);
+      if (mine) c.base[my_off + 5] = __float_as_uint(__double2float_rn(__drcp_rn((double)(float)qsum)));
+    }
+    __syncwarp();
+    k0 = k1;
+  }
+  // ---- backup (trainmc.cpp:281-292). Level L slot of leaf k = path[L-1]; the leaf itself
+  // (L == plen) takes e-1, its parent -e-1, ... Adds to one slot are applied in leaf order.
+  const int maxlen = __reduce_max_sync(kFull, my_plen);
+  for (int L = 1; L <= maxlen; ++L) {
+    const bool act = lane < np && my_plen >= L;
+    const uint32_t addr = act ? my_pd[2 + L - 1] : 0xFFFFFF00u + (uint32_t)lane;
+    const unsigned grp = __match_any_sync(kFull, addr);
+    const bool owner = act && (__ffs((int)grp) - 1 == lane);
+    const float ce = ((my_plen - L) & 1) ? -my_ev : my_ev;
+    const float d = __double2float_rn(__dsub_rn((double)ce, 1.0));
+    uint32_t *sp = c.base + (act ? addr : 0u);
+    float v = 0.0f;
+    uint32_t w3 = 0;
+    if (owner) v = __uint_as_float(sp[0]), w3 = sp[3];
+    for (int m = 0; m < np; ++m) {
+      const float dm = __shfl_sync(kFull, d, m);
+      if (owner && ((grp >> m) & 1u)) v = __fadd_rn(v, dm);
+    }
+    if (owner) sp[0] = __float_as_uint(v), sp[3] = w3 & ~kS3Allv;
+  }
+  for (int m = 0; m < np; ++m) {
+    const float e = __shfl_sync(kFull, my_ev, m);
+    const int pl = __shfl_sync(kFull, my_plen, m);
+    const float ce = (pl & 1) ? -e : e;
+    c.root_eval = __fadd_rn(c.root_eval, __double2float_rn(__dsub_rn((double)ce, 1.0)));
+  }
+  __syncwarp();
   c.root_allv = 0;
   c.d_evals += np;
   c.n_pending = 0;
@@ -477,10 +733,31 @@ __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
           if (r_drawn(cr)) {
             u = __fmul_rn(prob, v_sqrt);
           } else {
-            const double cv = (double)(float)(int)s.y;
-            const double a = __ddiv_rn(-(double)__uint_as_float(s.x), cv);
-            const double b = __ddiv_rn((double)__fmul_rn(prob, v_sqrt), __dadd_rn(cv, 1.0));
-            u = __double2float_rn(__dadd_rn(a, b));
+            // reference: u = float(-E/N + (P*v)/(N+1)) with both quotients and the sum
+            // rounded in double. Fast path: multiply by approximate reciprocals (each product
+            // is within 2^-49 of the reference quotient) and accept the result only if every
+            // double within 2^-46*(|a|+|b|) rounds to the same float; otherwise do it exactly.
+            const int cvi = (int)s.y;
+            const double ne = -(double)__uint_as_float(s.x);
+            const double pv = (double)__fmul_rn(prob, v_sqrt);
+            // reciprocals of the small integers N, N+1: 20-bit hardware seed + 2 Newton steps
+            // (relative error < 2^-50), so each product is within 2^-49 of the true quotient
+            const double dn = (double)cvi, dn1 = (double)(cvi + 1);
+            const double ra = fast_rcp(dn), rb = fast_rcp(dn1);
+            const double a = __dmul_rn(ne, ra);
+            const double b = __dmul_rn(pv, rb);
+            const double sf = __dadd_rn(a, b);
+            const double tol = __dmul_rn(__dadd_rn(fabs(a), fabs(b)), 0x1p-46);
+            const float ulo = __double2float_rn(__dsub_rn(sf, tol));
+            const float uhi = __double2float_rn(__dadd_rn(sf, tol));
+            u = ulo;
+            const bool exact = !(ulo == uhi);
+            if (exact) {
+              const double cv = (double)(float)cvi;
+              const double a = __ddiv_rn(ne, cv);
+              const double b = __ddiv_rn(pv, __dadd_rn(cv, 1.0));
+              u = __double2float_rn(__dadd_rn(a, b));
+            }
           }
         }
       } else {
@@ -517,6 +794,7 @@ __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
       c.root_visits -= 1;
       c.root_eval = __fsub_rn(c.root_eval, 1.0f);
       --c.searches_done;
+      c.n_none += 1;
       __syncwarp();
       return;
     }
@@ -642,11 +920,15 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
     request_root(c);
     return false;
   }
+  long long t0 = clock64();
   if (c.n_pending > 0) receive_eval(c, P, sm, eval, probs, prs, pcs);
+  long long t1 = clock64();
+  c.t_ingest += t1 - t0;
   while (c.n_pending < P.spe && c.searches_done < P.max_searches && !r_known(c.root_result) &&
          !c.root_allv && !c.error) {
     search(c, P, sm);
   }
+  c.t_search += clock64() - t1;
   return (c.searches_done == P.max_searches || r_known(c.root_result)) && c.n_pending == 0;
 }
 
@@ -799,7 +1081,13 @@ __device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &
 }
 
 // ---- SelfPlayer::chooseMoveAndContinue (selfplayer.cpp:246-291) -----------------------------
-__device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &P, WarpSm &sm) {
+// defer_search (fused mode only): after handing the move to the opponent, do not run the
+// opponent's searches inside this call; the next game step finds no pending answers and
+// performs exactly the same TrainMC::doIteration then. The order of operations within the game
+// is unchanged (so are its results); only the launch in which they happen moves, which keeps
+// the mover's warp from doing two search phases in one launch.
+__device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &P, WarpSm &sm,
+                                                      bool defer_search) {
   bool need_eval = false;
   while (!need_eval) {
     if (r_known(c.root_result) && c.mate_turn == 0) c.mate_turn = c.n_samples + 1;
@@ -855,6 +1143,7 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
     }
     need_eval = receive_opponent_move(c, P, choice, st, depth);
     if (c.error) return true;
+    if (!need_eval && defer_search) return false;
     if (!need_eval) need_eval = !tree_do_iteration(c, P, sm, nullptr, nullptr);
     if (c.error) return true;
   }
@@ -870,19 +1159,25 @@ __device__ __forceinline__ bool game_selected(const int32_t *ctl, int to_play) {
 
 // One SelfPlayer::doIteration per warp. offs[g] = index of game g's first answer row in
 // eval/probs (exclusive prefix sum of the request counts the answers were produced for).
-__global__ void __launch_bounds__(kTreeWarps * 32)
+// kFused: answers are read at the row the game was handed last time (ctl[CW_REQ_BASE]) and the
+// new leaf states are appended to the group's packed request list (parity `iteration & 1`).
+template <bool kFused>
+__global__ void __launch_bounds__(kTreeWarps * 32, 8)
     k_iterate(TreeParams P, const float *__restrict__ eval, const float *__restrict__ probs,
               long prs, long pcs, const int32_t *__restrict__ offs, int to_play, int iteration,
               int stagger_div) {
   __shared__ WarpSm sm_all[kTreeWarps];
   const int warp = threadIdx.x >> 5;
-  const int g = blockIdx.x * kTreeWarps + warp;
-  if (g >= P.num_games) return;
+  const int g = (kFused ? P.game_begin : 0) + blockIdx.x * kTreeWarps + warp;
+  if (g >= (kFused ? P.game_end : P.num_games)) return;
   int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
   if (!game_selected(ctl, to_play)) return;
   const bool training = (to_play != 0 && to_play != 1);
   // staggered start (trainer.cpp:184-186), on the global game index
-  if (training && stagger_div > 0 && (P.first_game + g) / stagger_div > iteration) return;
+  if (training && stagger_div > 0 && (P.first_game + g) / stagger_div > iteration) {
+    if (kFused && (threadIdx.x & 31) == 0) atomicAdd(P.group_ctr + 2 + ((iteration + 1) & 1), 1);
+    return;  // not started yet, but alive
+  }
   WarpSm &sm = sm_all[warp];
   Ctx c;
   c.lane = threadIdx.x & 31;
@@ -891,6 +1186,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32)
   c.n_pending = ctl[CW_N_PENDING], c.error = ctl[CW_ERROR], c.spare = ctl[CW_SPARE];
   c.mt_idx = ctl[CW_MT_IDX];
   c.d_sims = 0, c.d_evals = 0, c.d_moves = 0;
+  c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
   c.arenas = P.arenas + (size_t)g * 3 * P.arena_words;
   c.mt = P.mt + (size_t)g * 624;
   c.pending = P.pending + (size_t)g * P.spe * kPendWords;
@@ -899,12 +1195,29 @@ __global__ void __launch_bounds__(kTreeWarps * 32)
   c.sample_state = P.sample_state + (size_t)g * kMaxSamples;
   c.sample_probs = P.sample_probs + (size_t)g * kMaxSamples * CB200_NUM_MOVES;
   load_tree(c, P, c.to_play);
-  const int off = offs[g];
+  const int off = kFused ? ctl[CW_REQ_BASE] : offs[g];
   // SelfPlayer::doIteration (selfplayer.cpp:115-122)
   bool done = tree_do_iteration(c, P, sm, eval + off, probs + (long)off * prs, prs, pcs);
-  if (!c.error && done) done = choose_move_and_continue(c, P, sm);
+  if (!c.error && done) {
+    const long long tm = clock64();
+    const long long ts = c.t_search, ti = c.t_ingest;
+    done = choose_move_and_continue(c, P, sm, kFused);
+    c.t_move += (clock64() - tm) - (c.t_search - ts) - (c.t_ingest - ti);
+  }
   if (c.error) done = true;
   store_tree(c);
+  if (kFused) {
+    const int par = (iteration + 1) & 1;
+    int base = 0;
+    if (c.lane == 0) {
+      if (c.n_pending > 0) base = atomicAdd(P.group_ctr + par, c.n_pending);
+      if (!done) atomicAdd(P.group_ctr + 2 + par, 1);
+      if (c.error) atomicMin(P.group_ctr + 4, c.error);
+      ctl[CW_REQ_BASE] = P.group_row0 + base;
+    }
+    base = __shfl_sync(kFull, base, 0);
+    for (int k = c.lane; k < c.n_pending; k += 32) P.packed[P.group_row0 + base + k] = c.leaf_state[k];
+  }
   if (c.lane == 0) {
     ctl[CW_TO_PLAY] = c.to_play, ctl[CW_RESULT] = c.result, ctl[CW_MATE_TURN] = c.mate_turn;
     ctl[CW_N_SAMPLES] = c.n_samples, ctl[CW_N_PENDING] = c.n_pending, ctl[CW_ERROR] = c.error;
@@ -912,6 +1225,16 @@ __global__ void __launch_bounds__(kTreeWarps * 32)
     if (done) ctl[CW_DONE] = 1;
     long long *cnt = P.counters + (size_t)g * 4;
     cnt[0] += c.d_sims, cnt[1] += c.d_moves, cnt[2] += c.d_evals;
+    if (P.phase_prof) {
+      atomicMax(P.phase_prof + 0, (unsigned long long)c.t_ingest);
+      atomicMax(P.phase_prof + 1, (unsigned long long)c.t_search);
+      atomicMax(P.phase_prof + 2, (unsigned long long)c.t_move);
+      atomicAdd(P.phase_prof + 3, (unsigned long long)c.t_ingest);
+      atomicAdd(P.phase_prof + 4, (unsigned long long)c.t_search);
+      atomicAdd(P.phase_prof + 5, (unsigned long long)c.t_move);
+      atomicAdd(P.phase_prof + 6, (unsigned long long)c.n_none);
+      atomicAdd(P.phase_prof + 7, (unsigned long long)c.n_copy);
+    }
   }
 }
 

@@ -156,6 +156,11 @@ int cb200_trainer_reset(cb200_trainer *t, int seed);
 int cb200_trainer_set_profiling(cb200_trainer *t, int enable);
 int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[4], int64_t out_launches[4]);
 
+/* Debug: per-warp phase cycle maxima/sums of the game-step kernel since the last call:
+ * out = {max ingest, max search, max move, sum ingest, sum search, sum move, rolled-back
+ * searches, words copied by re-rooting}. enable != 0 switches the instrumentation on. */
+int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[8]);
+
 /* White-box dump of one search tree for engine-vs-oracle debugging (same layout as
  * oracle/corintho_oracle.h orc_trainer_dump_tree). */
 int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[8],

@@ -1,0 +1,1 @@
+CB200_GROUPS=1 timeout 120 python tools/prof_timeline.py 4096 800 bf16 2>&1 | head -8
