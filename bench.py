@@ -257,6 +257,7 @@ def run_engine_arm(args, rank, world, local_rank):
     import corintho_ai_b200 as cb
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout = the one JSON line
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -334,18 +335,11 @@ def run_engine_arm(args, rank, world, local_rank):
         tr.reset(3000 + k)
         tr.run_selfplay(0, stagger=False)
         gs, ev, pr = tr.write_samples()
-        if dist is not None:  # all-gather the finished (un-augmented) samples + stats over NCCL
+        if dist is not None:  # all-gather the finished (un-augmented) samples over NCCL
+            from corintho_ai_b200.dist import all_gather_rows, pack_raw_samples
             g0 = time.perf_counter()
             st, prb, lb, go = tr.raw_samples()
-            n_loc = torch.tensor([st.shape[0]], device=dev, dtype=torch.int64)
-            counts = [torch.zeros_like(n_loc) for _ in range(world)]
-            dist.all_gather(counts, n_loc)
-            n_max = int(max(int(c.item()) for c in counts))
-            pad = torch.zeros((n_max, 2 * 2 + 96 + 1), device=dev, dtype=torch.float32)
-            row = np.concatenate([st.view(np.float32).reshape(-1, 4), prb, lb[:, None]], 1)
-            pad[:row.shape[0]] = torch.from_numpy(row).to(dev)
-            out = torch.empty((world * n_max, pad.shape[1]), device=dev, dtype=torch.float32)
-            dist.all_gather_into_tensor(out, pad)
+            allrows, _ = all_gather_rows(dist, pack_raw_samples(st, prb, lb, go, first_game=rank * G), dev)
             torch.cuda.synchronize()
             gather_s += time.perf_counter() - g0
         torch.cuda.synchronize()
