@@ -374,10 +374,23 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
   // arena budget: kept subtree + max_searches new nodes per move with head-room; a game that
   // still overflows fails loudly (CB200_ERR_OVERFLOW). ~28 slots/node on average.
   long long nodes = (long long)max_searches * 5 / 2 + 96;
-  if (const char *env = getenv("CB200_ARENA_NODES")) nodes = atoll(env);
   long long words = nodes * (8 + 4 * 28);
+  if (const char *env = getenv("CB200_ARENA_NODES")) {
+    words = atoll(env) * (8 + 4 * 28);
+  } else {
+    // Larger arenas make in-place re-rooting the common case (compaction only when room runs
+    // out): spend up to half of the free HBM, capped at 16 moves' worth of nodes per arena.
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      long long budget = (long long)(free_b / 2) / ((long long)num_games * 3 * 4);
+      long long cap = (long long)max_searches * 16 * (8 + 4 * 28);
+      if (budget > cap) budget = cap;
+      if (budget > words) words = budget;
+    }
+  }
   words = (words + 3) & ~3ll;
   if (words < 1024) words = 1024;
+  if (words > 0x7fffff00ll) words = 0x7fffff00ll;
   P.arena_words = (uint32_t)words;
   t->stagger_div = total_games / max_searches;
   if (t->stagger_div < 1) t->stagger_div = 1;
@@ -919,7 +932,8 @@ int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[
   CB_CUDA(cudaMemcpy(cw, t->P.ctl + (size_t)game * kCtlWords, sizeof(cw), cudaMemcpyDeviceToHost));
   out[0] = tw[TW_HAS_ROOT], out[1] = (uint32_t)tw[TW_USED], out[2] = tw[TW_ROOT_VISITS];
   out[3] = tw[TW_ROOT_RESULT], out[4] = tw[TW_ROOT_ALLV], out[5] = tw[TW_SEARCHES_DONE];
-  out[6] = (uint32_t)tw[TW_ROOT_EVAL], out[7] = cw[CW_TO_PLAY];
+  out[6] = (uint32_t)tw[TW_ROOT_EVAL];
+  out[7] = (int64_t)cw[CW_TO_PLAY] | ((int64_t)(uint32_t)tw[TW_ROOT_OFF] << 8);
   const int used = tw[TW_USED];
   if (tw[TW_HAS_ROOT] && words && cap > 0) {
     const int n = used < cap ? used : cap;

@@ -30,7 +30,7 @@ constexpr int kPendWords = 2 + kMaxPath;  // leaf_off, path_len, path[kMaxPath]
 constexpr int kMaxSamples = 64;
 constexpr int kTreeWarps = 4;  // games per CTA
 constexpr int kCtlWords = 16;
-constexpr int kTreeCtlWords = 8;
+constexpr int kTreeCtlWords = 12;
 constexpr int kTabSize = 4096;  // visit counts served by the sqrt / reciprocal tables
 
 // RN(1.0 / i) as doubles, i in [0, kTabSize]; uploaded by ensure_tree_tables()
@@ -42,7 +42,7 @@ enum CtlWord {
 };
 enum TreeWord {
   TW_ARENA = 0, TW_HAS_ROOT, TW_USED, TW_ROOT_EVAL, TW_ROOT_VISITS, TW_ROOT_RESULT, TW_ROOT_ALLV,
-  TW_SEARCHES_DONE
+  TW_SEARCHES_DONE, TW_ROOT_OFF
 };
 
 struct TreeParams {
@@ -143,6 +143,7 @@ struct Ctx {
   // current tree (trainmc.h:160-188)
   int cur_p, arena, has_root;
   uint32_t used;
+  uint32_t root_off;  // word offset of the root record in its arena (re-rooting is in place)
   float root_eval;
   int root_visits, root_result, root_allv, searches_done;
   uint32_t *base;
@@ -160,6 +161,7 @@ __device__ __forceinline__ void load_tree(Ctx &c, const TreeParams &P, int p) {
   c.cur_p = p;
   c.arena = a.x, c.has_root = a.y, c.used = (uint32_t)a.z, c.root_eval = __int_as_float(a.w);
   c.root_visits = b.x, c.root_result = b.y, c.root_allv = b.z, c.searches_done = b.w;
+  c.root_off = (uint32_t)t[TW_ROOT_OFF];
   c.base = c.arenas + (size_t)c.arena * P.arena_words;
 }
 __device__ __forceinline__ void store_tree(Ctx &c) {
@@ -169,6 +171,7 @@ __device__ __forceinline__ void store_tree(Ctx &c) {
         make_int4(c.arena, c.has_root, (int)c.used, __float_as_int(c.root_eval));
     *reinterpret_cast<int4 *>(t + 4) =
         make_int4(c.root_visits, c.root_result, c.root_allv, c.searches_done);
+    t[TW_ROOT_OFF] = (int)c.root_off;
   }
   __syncwarp();
 }
@@ -292,6 +295,7 @@ __device__ __forceinline__ CState rec_state(const uint32_t *r) {
 __device__ __forceinline__ void fresh_tree(Ctx &c, const TreeParams &P, const CState &st,
                                            int depth) {
   c.used = 0;
+  c.root_off = 0;
   int result;
   make_record(c, P, st, depth, result);
   c.has_root = 1;
@@ -305,8 +309,8 @@ __device__ __forceinline__ void fresh_tree(Ctx &c, const TreeParams &P, const CS
 __device__ __forceinline__ void request_root(Ctx &c) {
   if (c.lane == 0) {
     uint32_t *pd = c.pending + c.n_pending * kPendWords;
-    pd[0] = 0, pd[1] = 0;
-    const uint4 h = ld4(c.base);
+    pd[0] = c.root_off, pd[1] = 0;
+    const uint4 h = ld4(c.base + c.root_off);
     c.leaf_state[c.n_pending] = make_ulonglong2((uint64_t)h.x | ((uint64_t)h.y << 32),
                                                 (uint64_t)h.z | ((uint64_t)h.w << 32));
   }
@@ -320,11 +324,20 @@ __device__ __forceinline__ void request_root(Ctx &c) {
 __device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
   const uint32_t *src = c.base;
   uint32_t *dst = c.arenas + (size_t)c.spare * P.arena_words;
-  const uint4 s = ld4(src + 8 + 4 * e);
+  const uint4 s = ld4(src + c.root_off + 8 + 4 * e);
   c.root_eval = __uint_as_float(s.x);
   c.root_visits = (int)s.y;
   c.root_result = s3_result(s.w);
   c.root_allv = s3_allv(s.w) ? 1 : 0;
+  // Re-root in place while the arena still has room for a full move's worth of new nodes
+  // (max_searches nodes of up to 48 slots); the discarded siblings stay behind as garbage.
+  // Only when the room runs out is the kept subtree compacted into the spare arena.
+  const uint32_t reserve = (uint32_t)(P.max_searches + 64) * (8u + 4u * 48u);
+  if (c.used + reserve <= P.arena_words) {
+    c.root_off = s.z;
+    c.searches_done = 0;
+    return;
+  }
   const uint32_t sz = 8u + 4u * (uint32_t)s3_cnl(s.w);
   copy_words(dst, src + s.z, sz, c.lane);
   uint32_t alloc = sz;
@@ -380,6 +393,7 @@ __device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
   c.spare = old;
   c.base = dst;
   c.used = alloc;
+  c.root_off = 0;
   c.searches_done = 0;
   c.n_copy += alloc;
 }
@@ -703,12 +717,12 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
 __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
   ++c.searches_done;
   int level = 0;
-  uint32_t node = 0;
+  uint32_t node = c.root_off;
   int cur_result = c.root_result;
   int cur_visits = c.root_visits;
   float cur_eval = c.root_eval;
   uint32_t cur_w3 = 0;
-  if (c.lane == 0) sm.node[0] = 0;
+  if (c.lane == 0) sm.node[0] = c.root_off;
   CState leaf_state{0, 0};
   while (!r_terminal(cur_result)) {
     const uint32_t *r = c.base + node;
@@ -934,7 +948,7 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
 
 // TrainMC::chooseHighProbMove (trainmc.cpp:298-308) incl. the int32 max_prob quirk (Q3)
 __device__ __forceinline__ int choose_high_prob(Ctx &c, WarpSm &sm) {
-  const uint32_t *r = c.base;
+  const uint32_t *r = c.base + c.root_off;
   const int n = (int)(r[4] & 0xffu);
   const float denominator = __uint_as_float(r[5]);
   for (int e = c.lane; e < n; e += 32)
@@ -951,8 +965,8 @@ __device__ __forceinline__ int choose_high_prob(Ctx &c, WarpSm &sm) {
 
 // "Reset tree" (trainmc.cpp:397-404, 461-468): single node reached by `move` from the root
 __device__ __forceinline__ void reset_tree_after(Ctx &c, const TreeParams &P, int move) {
-  const CState st = do_move(rec_state(c.base), move);
-  const int depth = (int)((c.base[4] >> 8) & 0xffu) + 1;
+  const CState st = do_move(rec_state(c.base + c.root_off), move);
+  const int depth = (int)((c.base[c.root_off + 4] >> 8) & 0xffu) + 1;
   __syncwarp();
   fresh_tree(c, P, st, depth);
   c.searches_done = 0;
@@ -965,7 +979,7 @@ __device__ __forceinline__ void reset_tree_after(Ctx &c, const TreeParams &P, in
 // ---- TrainMC::chooseMove (trainmc.cpp:110-137, 310-473) -------------------------------------
 __device__ __noinline__ int choose_move(Ctx &c, const TreeParams &P, WarpSm &sm,
                                         float *prob_sample) {
-  const uint32_t *r = c.base;
+  const uint32_t *r = c.base + c.root_off;
   const int n = (int)(r[4] & 0xffu);
   const int depth = (int)((r[4] >> 8) & 0xffu);
   uint4 sl[3];
@@ -1062,7 +1076,7 @@ __device__ __noinline__ int choose_move(Ctx &c, const TreeParams &P, WarpSm &sm,
 // ---- TrainMC::receiveOpponentMove (trainmc.cpp:180-204) -------------------------------------
 __device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &P, int move,
                                                       const CState &st, int depth) {
-  const uint32_t *r = c.base;
+  const uint32_t *r = c.base + c.root_off;
   const int n = (int)(r[4] & 0xffu);
   int found = 0x7fffffff;
   for (int e = c.lane; e < n; e += 32) {
@@ -1106,7 +1120,7 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
       float *ps = c.sample_probs + (size_t)c.n_samples * CB200_NUM_MOVES;
       for (int j = c.lane; j < CB200_NUM_MOVES; j += 32) ps[j] = 0.0f;
       if (c.lane == 0) {
-        const uint4 h = ld4(c.base);
+        const uint4 h = ld4(c.base + c.root_off);
         c.sample_state[c.n_samples] = make_ulonglong2((uint64_t)h.x | ((uint64_t)h.y << 32),
                                                       (uint64_t)h.z | ((uint64_t)h.w << 32));
       }
@@ -1131,8 +1145,8 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
       c.has_root = 0;
       return true;
     }
-    const CState st = rec_state(c.base);
-    const int depth = (int)((c.base[4] >> 8) & 0xffu);
+    const CState st = rec_state(c.base + c.root_off);
+    const int depth = (int)((c.base[c.root_off + 4] >> 8) & 0xffu);
     c.to_play = 1 - c.to_play;
     store_tree(c);
     load_tree(c, P, c.to_play);

@@ -12,9 +12,15 @@ def _records(words):
     return out
 
 
+def _rec(words, off):
+    n = int(words[off + 4] & 0xFF)
+    return words[off:off + 8], words[off + 8:off + 8 + 4 * n].reshape(n, 4)
+
+
 def compare_trees(eng, orc_lib, orc_tr, game, player):
-    """Compare one tree of the engine with the oracle's (same arena layout). Returns '' if equal
-    else a description of the first difference."""
+    """Logical comparison of one tree of the engine with the oracle's: same statistics, priors
+    and shape from the root down (record offsets may differ: the engine re-roots in place).
+    Returns '' if equal else a description of the first difference."""
     import ctypes as C
     eo, ew = eng.dump_tree(game, player)
     oo = np.zeros(8, np.int64)
@@ -24,24 +30,34 @@ def compare_trees(eng, orc_lib, orc_tr, game, player):
     f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     used = f(orc_tr.h, game, player, oo.ctypes.data_as(C.c_void_p), ow.ctypes.data_as(C.c_void_p), len(ow))
     ow = ow[:used]
+    e_root = int(eo[7]) >> 8
+    eo = eo.copy()
+    eo[7] &= 0xFF
     names = ["has_root", "used", "root_visits", "root_result", "root_allv", "searches_done", "root_eval_bits", "to_play"]
     if not eo[0] and not oo[0]:
         return ""
     for i, nm in enumerate(names):
-        if eo[i] != oo[i]:
+        if nm != "used" and eo[i] != oo[i]:
             return f"game {game} player {player}: ctl {nm}: engine {eo[i]} oracle {oo[i]} (all: {eo} vs {oo})"
-    er, orr = _records(ew), _records(ow)
-    for (o1, h1, s1), (o2, h2, s2) in zip(er, orr):
-        if o1 != o2 or h1[4] != h2[4] or h1[5] != h2[5]:
-            return f"game {game} player {player}: record @{o1}/{o2} header {h1} vs {h2}"
+    stack = [(e_root, 0, "root")]
+    keep = np.uint32(0xFFFFFFFF & ~(1 << 28))  # engine-only child_has_children bit
+    while stack:
+        eoff, ooff, path = stack.pop()
+        h1, s1 = _rec(ew, eoff)
+        h2, s2 = _rec(ow, ooff)
+        if h1[4] != h2[4] or h1[5] != h2[5]:
+            return f"game {game} player {player}: node {path}: header {h1} vs {h2}"
         a, b = s1.copy(), s2.copy()
-        a[:, 3] &= np.uint32(~(1 << 28) & 0xFFFFFFFF)  # engine-only child_has_children bit
+        a[:, 3] &= keep
+        a[:, 2] = 0
+        b[:, 2] = 0
         if not (a == b).all():
             k = int(np.argwhere((a != b).any(1))[0][0])
-            return (f"game {game} player {player}: record @{o1} depth {(h1[4] >> 8) & 255} slot {k}: engine {a[k]} "
+            return (f"game {game} player {player}: node {path} depth {(h1[4] >> 8) & 255} slot {k}: engine {a[k]} "
                     f"(eval {a[k][0:1].view(np.float32)[0]}) oracle {b[k]} (eval {b[k][0:1].view(np.float32)[0]})")
-    if len(er) != len(orr):
-        return f"game {game} player {player}: {len(er)} records vs {len(orr)}"
+        for k in range(len(s1)):
+            if (s1[k][3] >> 20) & 1:
+                stack.append((int(s1[k][2]), int(s2[k][2]), path + "/" + str(int(s1[k][3] & 0x7F))))
     return ""
 
 
