@@ -300,7 +300,7 @@ class Trainer:
         return bool(_check(lib().cb200_trainer_run_selfplay(self._h, max_iterations, int(stagger))))
 
     def phase_profile(self, enable=True):
-        out = np.zeros(8, np.uint64)
+        out = np.zeros(16, np.uint64)
         _check(lib().cb200_trainer_phase_profile(self._h, int(enable), _ptr(out)))
         return out
 

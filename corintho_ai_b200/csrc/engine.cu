@@ -475,17 +475,17 @@ cb200_trainer *cb200_trainer_create(int num_games, const char *log_folder, int s
 }
 
 // debug: straggler instrumentation of the game-step kernel (see TreeParams::phase_prof)
-int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[8]) {
+int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[16]) {
   int rc = guard(t);
   if (rc) return rc;
   CB_CUDA(cudaStreamSynchronize(G().stream));
   if (t->P.phase_prof && out) {
-    CB_CUDA(cudaMemcpy(out, t->P.phase_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    CB_CUDA(cudaMemset(t->P.phase_prof, 0, 8 * sizeof(uint64_t)));
+    CB_CUDA(cudaMemcpy(out, t->P.phase_prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemset(t->P.phase_prof, 0, 16 * sizeof(uint64_t)));
   }
   if (enable && !t->P.phase_prof) {
-    CB_CUDA(cudaMalloc((void **)&t->P.phase_prof, 8 * sizeof(uint64_t)));
-    CB_CUDA(cudaMemset(t->P.phase_prof, 0, 8 * sizeof(uint64_t)));
+    CB_CUDA(cudaMalloc((void **)&t->P.phase_prof, 16 * sizeof(uint64_t)));
+    CB_CUDA(cudaMemset(t->P.phase_prof, 0, 16 * sizeof(uint64_t)));
   } else if (!enable && t->P.phase_prof) {
     cudaFree(t->P.phase_prof);
     t->P.phase_prof = nullptr;

@@ -140,6 +140,7 @@ struct Ctx {
   long long d_sims, d_evals;
   int d_moves;
   long long t_ingest, t_search, t_move, n_none, n_copy;
+  long long t_sel, t_exp, n_lvl, n_exp;
   // current tree (trainmc.h:160-188)
   int cur_p, arena, has_root;
   uint32_t used;
@@ -725,6 +726,8 @@ __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
   if (c.lane == 0) sm.node[0] = c.root_off;
   CState leaf_state{0, 0};
   while (!r_terminal(cur_result)) {
+    const long long tl0 = clock64();
+    c.n_lvl += 1;
     const uint32_t *r = c.base + node;
     const uint4 h0 = ld4(r);
     const uint4 h1 = ld4(r + 4);
@@ -816,7 +819,10 @@ __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
     const int owner = emin & 31;
     const uint32_t so = node + 8u + 4u * (uint32_t)emin;
     const uint32_t ch_w3 = __shfl_sync(kFull, best_s.w, owner);
+    c.t_sel += clock64() - tl0;
     if (!s3_has(ch_w3)) {  // kNew: expand (trainmc.cpp:645-660)
+      const long long te0 = clock64();
+      c.n_exp += 1;
       if (level + 1 >= kMaxPath) {
         c.error = CB200_ERR_OVERFLOW;
         return;
@@ -842,6 +848,7 @@ __device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
       node = coff;
       cur_result = result;
       __syncwarp();
+      c.t_exp += clock64() - te0;
       break;
     }
     // existing child: descend
@@ -1201,6 +1208,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 8)
   c.mt_idx = ctl[CW_MT_IDX];
   c.d_sims = 0, c.d_evals = 0, c.d_moves = 0;
   c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
+  c.t_sel = c.t_exp = c.n_lvl = c.n_exp = 0;
   c.arenas = P.arenas + (size_t)g * 3 * P.arena_words;
   c.mt = P.mt + (size_t)g * 624;
   c.pending = P.pending + (size_t)g * P.spe * kPendWords;
@@ -1248,6 +1256,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 8)
       atomicAdd(P.phase_prof + 5, (unsigned long long)c.t_move);
       atomicAdd(P.phase_prof + 6, (unsigned long long)c.n_none);
       atomicAdd(P.phase_prof + 7, (unsigned long long)c.n_copy);
+      atomicAdd(P.phase_prof + 8, (unsigned long long)c.t_sel);
+      atomicAdd(P.phase_prof + 9, (unsigned long long)c.t_exp);
+      atomicAdd(P.phase_prof + 10, (unsigned long long)c.n_lvl);
+      atomicAdd(P.phase_prof + 11, (unsigned long long)c.n_exp);
     }
   }
 }

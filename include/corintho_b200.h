@@ -158,8 +158,9 @@ int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[4], int64_t out_l
 
 /* Debug: per-warp phase cycle maxima/sums of the game-step kernel since the last call:
  * out = {max ingest, max search, max move, sum ingest, sum search, sum move, rolled-back
- * searches, words copied by re-rooting}. enable != 0 switches the instrumentation on. */
-int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[8]);
+ * searches, words copied by re-rooting, sum select cycles, sum expand cycles, tree levels
+ * visited, expansions}. enable != 0 switches the instrumentation on. */
+int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[16]);
 
 /* White-box dump of one search tree for engine-vs-oracle debugging (same layout as
  * oracle/corintho_oracle.h orc_trainer_dump_tree). */

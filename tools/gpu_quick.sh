@@ -1,0 +1,3 @@
+timeout 600 python -m pytest tests/test_gpu_net.py tests/test_gpu_trainer.py -q -m gpu --timeout 200 -x 2>&1 | tail -2
+for g in 1 2; do echo "== groups $g"; CB200_GROUPS=$g timeout 120 python tools/prof_selfplay.py 4096 800 0 bf16 noprof 2>&1 | grep done; done
+echo "== dense"; CB200_GROUPS=1 timeout 120 python tools/prof_selfplay.py 4096 800 300 bf16 2>&1 | tail -2
