@@ -46,7 +46,7 @@ inline Globals &G() {
 
 // ---- device-resident rule data (uploaded once per device by ensure_tables) ------------------
 // line-breaker masks padded to 4 words so one 128-bit load fetches a mask
-__device__ uint32_t d_line_breakers[102 * 4];
+__device__ uint32_t d_line_breakers[103 * 4];  // entry 102 = all ones (no line)
 __device__ float d_gamma[1024];
 
 struct DeviceLB {
@@ -59,7 +59,8 @@ inline int ensure_tables() {
   int dev = 0;
   CB_CUDA(cudaGetDevice(&dev));
   if (dev < 16 && G().tables_ready[dev]) return CB200_OK;
-  static uint32_t lb[102 * 4];
+  static uint32_t lb[103 * 4];
+  lb[408] = lb[409] = lb[410] = 0xFFFFFFFFu, lb[411] = 0;
   for (int i = 0; i < 102; ++i) {
     lb[4 * i] = kCLineBreakers[i][0], lb[4 * i + 1] = kCLineBreakers[i][1];
     lb[4 * i + 2] = kCLineBreakers[i][2], lb[4 * i + 3] = 0;

@@ -417,7 +417,9 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     return nullptr;
   }
   // stream groups for the fused loop
-  int ng = 8;
+  // With in-place re-rooting the per-launch stragglers are gone and one lock-step group is
+  // fastest; CB200_GROUPS > 1 splits the games over independent streams.
+  int ng = 1;
   if (const char *env = getenv("CB200_GROUPS")) ng = atoi(env);
   if (ng < 1) ng = 1;
   while (ng > 1 && num_games / ng < 64) ng /= 2;

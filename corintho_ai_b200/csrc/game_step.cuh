@@ -27,15 +27,15 @@ __global__ void __launch_bounds__(kStepThreads)
       const ulonglong2 v = __ldg(states + i);
       s.w0 = v.x, s.w1 = v.y;
       uint32_t m[3];
-      const bool lines = legal_moves(s, m, DeviceLB());
+      const bool lines = legal_moves_t<true>(s, m, DeviceLB());
       const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
       const int result = terminal_result(nl, lines);
-      int chosen = 0x7f;
-      CState o = s;
-      if (nl > 0) {
-        chosen = nth_move(m, (int)(step_rnd(seed, (uint64_t)i) % (uint32_t)nl));
-        o = do_move(s, chosen);
-      }
+      // select-only: compute the move for every state, keep it only where one exists
+      const int pick = nth_move(m, (int)(step_rnd(seed, (uint64_t)i) % (uint32_t)max(nl, 1)));
+      const CState moved = do_move(s, pick & 127);
+      const int chosen = nl > 0 ? pick : 0x7f;
+      CState o;
+      o.w0 = nl > 0 ? moved.w0 : s.w0, o.w1 = nl > 0 ? moved.w1 : s.w1;
       mask_flags[i] = make_uint4(m[0], m[1], m[2],
                                  (uint32_t)result | (lines ? 4u : 0u) | ((uint32_t)nl << 8) |
                                      ((uint32_t)chosen << 16));

@@ -9,14 +9,18 @@
 //     no-swizzle layout: 16-byte k-chunks (8 bf16) of all 128 rows are contiguous
 //     (chunk stride 2048 B = LBO, 8-row core-matrix stride 128 B = SBO);
 //   * B operand (weights of one layer, bf16, [N=112][K=112] K-major, same canonical layout
-//     with chunk stride 1792 B) plus the fp32 bias is ONE 25.5 KB image per layer, fetched by
+//     with chunk stride 1792 B, bias rows included) is ONE 24.5 KB image per layer, fetched by
 //     a single cp.async.bulk (UBLKCP) per layer into a double buffer, mbarrier-tracked;
 //   * D (fp32) lives in TMEM: 112 columns per tile, 7 x tcgen05.mma (M128 N112 K16) per layer,
 //     issued by one thread per warpgroup and committed to an mbarrier;
-//   * epilogue: tcgen05.ld (32 lanes x 16 columns) -> +bias, ReLU, bf16 -> written straight
+//   * epilogue: batched tcgen05.ld (32 lanes x 32 columns) -> ReLU + bf16 pack -> written straight
 //     back as the next layer's A operand. Input encoding (game.cpp:45-58) is expanded from
 //     the packed cstate inside the kernel; tanh / softmax are done from TMEM in the last layer.
 // All dimensions are padded with zeros: K 70/100 -> 112, N 100/97 -> 112.
+// The bias rides in the GEMM: activation columns 100 and 101 are constant 1 (kept alive through
+// the layers by unit weights), and weight rows 100/101 hold the bias split into bf16 hi + lo
+// parts (~16 significant bits), so the hidden epilogue is just ReLU + bf16 packing
+// (cvt.rn.relu.bf16x2.f32) on batched TMEM loads.
 #ifndef CORINTHO_B200_MLP_TC_CUH
 #define CORINTHO_B200_MLP_TC_CUH
 
@@ -33,7 +37,8 @@ constexpr int kTcAChunkBytes = 128 * 16;                 // 2048: one k-chunk of
 constexpr int kTcWChunkBytes = kTcN * 16;                // 1792: one k-chunk of 112 rows
 constexpr int kTcABytes = kTcChunks * kTcAChunkBytes;    // 28672
 constexpr int kTcWBytes = kTcChunks * kTcWChunkBytes;    // 25088
-constexpr int kTcLayerBytes = kTcWBytes + kTcN * 4;      // 25536 (weights + fp32 bias)
+constexpr int kTcLayerBytes = kTcWBytes;                 // 25088 (bias folded into rows 100/101)
+constexpr int kTcOnes = 100;                             // activation columns 100,101 == 1
 constexpr int kTcThreads = 256;
 constexpr int kTcTmemCols = 256;                         // 2 tiles x 128 columns
 constexpr size_t kTcSmemBytes = 2 * kTcABytes + 2 * kTcLayerBytes + 64;
@@ -120,6 +125,36 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// two fp32 -> packed bf16x2 with ReLU, `lo` in bits 0-15
+__device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t *>(&h);
@@ -186,8 +221,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const int j = 8 * c + 2 * h;
-          const float a = j < CB200_STATE_SIZE ? encode_elem(st, j) : 0.0f;
-          const float b = j + 1 < CB200_STATE_SIZE ? encode_elem(st, j + 1) : 0.0f;
+          const float a = j < CB200_STATE_SIZE ? encode_elem(st, j) : (j == kTcOnes ? 1.0f : 0.0f);
+          const float b = j + 1 < CB200_STATE_SIZE ? encode_elem(st, j + 1)
+                                                   : (j + 1 == kTcOnes + 1 ? 1.0f : 0.0f);
           q[h] = pack_bf16(a, b);
         }
         *reinterpret_cast<uint4 *>(myA + c * kTcAChunkBytes + row * 16) =
@@ -217,23 +253,34 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       mbar_wait(mbar0 + 8 * wg, mcount & 1);
       mcount += 1;
       tc_fence_after();
-      const float *bias = reinterpret_cast<const float *>(wbuf + kTcWBytes);
       if (layer < kTcLayers - 1) {
-        // ---- hidden-layer epilogue: +bias, ReLU, bf16, becomes the next A operand
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTcN; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_row + c0, v);
-          uint32_t q[8];
+        // ---- hidden-layer epilogue: ReLU + bf16 (bias already in the accumulator), the result
+        // becomes the next A operand. TMEM loads are batched: 64 columns, then 48.
+        {
+          uint32_t v[64];
+          tmem_ld32_nowait(tmem_row, v);
+          tmem_ld32_nowait(tmem_row + 32, v + 32);
+          tmem_wait_ld();
 #pragma unroll
-          for (int h = 0; h < 8; ++h) {
-            const float x0 = fmaxf(__uint_as_float(v[2 * h]) + bias[c0 + 2 * h], 0.0f);
-            const float x1 = fmaxf(__uint_as_float(v[2 * h + 1]) + bias[c0 + 2 * h + 1], 0.0f);
-            q[h] = pack_bf16(x0, x1);
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint32_t *x = v + 8 * c8;
+            *reinterpret_cast<uint4 *>(myA + c8 * kTcAChunkBytes + row * 16) =
+                make_uint4(relu_pack_bf16(x[0], x[1]), relu_pack_bf16(x[2], x[3]),
+                           relu_pack_bf16(x[4], x[5]), relu_pack_bf16(x[6], x[7]));
           }
-          uint8_t *dst = myA + (c0 >> 3) * kTcAChunkBytes + row * 16;
-          *reinterpret_cast<uint4 *>(dst) = make_uint4(q[0], q[1], q[2], q[3]);
-          *reinterpret_cast<uint4 *>(dst + kTcAChunkBytes) = make_uint4(q[4], q[5], q[6], q[7]);
+        }
+        {
+          uint32_t v[48];
+          tmem_ld32_nowait(tmem_row + 64, v);
+          tmem_ld16_nowait(tmem_row + 96, v + 32);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c8 = 0; c8 < 6; ++c8) {
+            const uint32_t *x = v + 8 * c8;
+            *reinterpret_cast<uint4 *>(myA + (8 + c8) * kTcAChunkBytes + row * 16) =
+                make_uint4(relu_pack_bf16(x[0], x[1]), relu_pack_bf16(x[2], x[3]),
+                           relu_pack_bf16(x[4], x[5]), relu_pack_bf16(x[6], x[7]));
+          }
         }
       } else {
         // ---- heads: column 0 = value (tanh), columns 1..96 = policy logits (softmax)
@@ -245,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 #pragma unroll
           for (int h = 0; h < 16; ++h) {
             const int col = c0 + h;
-            const float x = __uint_as_float(v[h]) + bias[col];
+            const float x = __uint_as_float(v[h]);
             if (col == 0) v0 = x;
             if (col >= 1 && col <= CB200_NUM_MOVES) mx = fmaxf(mx, x);
           }
@@ -259,7 +306,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           for (int h = 0; h < 16; ++h) {
             const int col = c0 + h;
             if (col >= 1 && col <= CB200_NUM_MOVES)
-              sum += __expf(__uint_as_float(v[h]) + bias[col] - mx);
+              sum += __expf(__uint_as_float(v[h]) - mx);
           }
         }
         const float inv = 1.0f / sum;
@@ -274,7 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
             const int col = c0 + h;
             if (col >= 1 && col <= CB200_NUM_MOVES && p < n)
               probs[(size_t)(col - 1) * probs_ld + p] =
-                  __expf(__uint_as_float(v[h]) + bias[col] - mx) * inv;
+                  __expf(__uint_as_float(v[h]) - mx) * inv;
           }
         }
       }
@@ -315,7 +362,20 @@ inline int net_tc_upload(NetTC &net, const float *weights) {
         memcpy(img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2, &h, 2);
       }
     src += (size_t)K * N;
-    memcpy(img + kTcWBytes, src, (size_t)N * sizeof(float));
+    auto put = [&](int k, int o, float v) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      memcpy(img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2, &h, 2);
+    };
+    for (int o = 0; o < N; ++o) {  // bias = hi + lo, multiplied by the two ones columns
+      const float b = src[o];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      put(kTcOnes, o, hi);
+      put(kTcOnes + 1, o, b - hi);
+    }
+    if (l < kTcLayers - 1) {  // keep the ones columns alive: out[:,100] = out[:,101] = 1
+      put(kTcOnes, kTcOnes, 1.0f);
+      put(kTcOnes, kTcOnes + 1, 1.0f);
+    }
     src += N;
   }
   if (!net.w) CB_CUDA(cudaMalloc(&net.w, host.size()));

@@ -69,9 +69,12 @@ CB_HD uint32_t compress3(uint32_t v) {
 }
 
 // Legal-move mask (96 bits in m[0..2], bit id&31 of word id>>5) and the "lines present" flag.
-// LB(idx) must return a pointer to the 3 words of line-breaker mask idx (util.h:85-290 data).
-template <class LBFn>
-CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
+// LB(idx) must return a pointer to the 3 words of line-breaker mask idx (util.h:85-290 data);
+// idx 102 must return an all-ones mask ("no line in this category").
+// kBranchless: thread-per-state callers (K1) get select-only code (every category ANDs a table
+// entry, 102 when there is no line); warp-uniform callers keep early-outs that skip work.
+template <bool kBranchless, class LBFn>
+CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
   const uint32_t lo = (uint32_t)st.w0, hi = (uint32_t)(st.w0 >> 32);
   const uint32_t B = lo & 0xFFFFu, C = lo >> 16, A = hi & 0xFFFFu, F = hi >> 16;
   const uint32_t O = B | C | A;
@@ -106,15 +109,16 @@ CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
     const uint32_t Wa = W0 | W1 | W2;
     const uint32_t left = Wa & 0x1111u, right = (Wa >> 1) & 0x1111u;
     const uint32_t any = left | right;
-    if (any) {
-      lines = true;
-      const int i4 = cb_ffs(any) - 1, i = i4 >> 2;
+    if (kBranchless || any) {
+      const bool has = any != 0;
+      lines |= has;
+      const int i4 = has ? cb_ffs(any) - 1 : 0, i = i4 >> 2;
       const int t = (int)((any1 >> i4) & 1u) + 2 * (int)((any2 >> i4) & 1u);
       const bool l = (left >> i4) & 1u, r = (right >> i4) & 1u;
       const int cat = (l && r) ? 2 : (l ? 0 : 1);  // RB, RL, RR (util.h:67-69)
-      const uint32_t *lb = LB(cat * 12 + i * 3 + t);
+      const uint32_t *lb = LB(has ? cat * 12 + i * 3 + t : 102);
       m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
-      if (t == 2 && cat != 2) {  // capital fix-ups (game.cpp:280-309), column `e`
+      if (has && t == 2 && cat != 2) {  // capital fix-ups (game.cpp:280-309), column `e`
         const int e = l ? 3 : 0;
         const uint32_t colm = 0x111u << e;
         m0 &= ~(colm << 12) | ((A & colm) << 12);        // down moves from (k,e), k=0..2
@@ -130,15 +134,16 @@ CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
     const uint32_t Wa = W0 | W1 | W2;
     const uint32_t upper = Wa & 0xFu, lower = (Wa >> 4) & 0xFu;
     const uint32_t any = upper | lower;
-    if (any) {
-      lines = true;
-      const int i = cb_ffs(any) - 1;
+    if (kBranchless || any) {
+      const bool has = any != 0;
+      lines |= has;
+      const int i = has ? cb_ffs(any) - 1 : 0;
       const int t = (int)((any1 >> i) & 1u) + 2 * (int)((any2 >> i) & 1u);
       const bool u = (upper >> i) & 1u, d = (lower >> i) & 1u;
       const int cat = (u && d) ? 5 : (u ? 3 : 4);  // CB, CU, CD (util.h:70-72)
-      const uint32_t *lb = LB(cat * 12 + i * 3 + t);
+      const uint32_t *lb = LB(has ? cat * 12 + i * 3 + t : 102);
       m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
-      if (t == 2 && cat != 5) {  // capital fix-ups along row `e`
+      if (has && t == 2 && cat != 5) {  // capital fix-ups along row `e`
         const int e = u ? 3 : 0;
         const uint32_t Arow = (A >> (4 * e)) & 0xFu;
         const uint32_t rowm = 7u << (3 * e);
@@ -157,73 +162,63 @@ CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
     const uint32_t A3 = T0 & (T0 >> 3) & (T0 >> 6), B3 = T1 & (T1 >> 3) & (T1 >> 6),
                    C3 = T2 & (T2 >> 3) & (T2 >> 6);
     const uint32_t D5 = (A5 | B5 | C5) & 0x33u, D3 = (A3 | B3 | C3) & 0xCCu;
-    if (D5 | D3) {
+    if (kBranchless || (D5 | D3)) {
       // long diagonals (game.cpp:317-360): main then anti; long > upper > lower
-      int D = -1, base = 0, step5 = 1;
-      if (D5 & 0x21u) {
-        const bool up = D5 & 0x01u, lo = D5 & 0x20u;
-        D = (up && lo) ? 2 : (up ? 0 : 1);  // D0B, D0U, D0D
-        base = up ? 0 : 5;
-      } else if (D3 & 0x48u) {
-        const bool up = D3 & 0x08u, lo = D3 & 0x40u;
-        D = (up && lo) ? 5 : (up ? 3 : 4);  // D1B, D1U, D1D
-        base = up ? 3 : 6, step5 = 0;
-      }
-      if (D >= 0) {
-        const uint32_t b1 = step5 ? B5 : B3, b2 = step5 ? C5 : C3;
-        const int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
-        lines = true;
-        const uint32_t *lb = LB(72 + D * 3 + t);
-        m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
-      }
+      const bool mu5 = D5 & 0x01u, ml5 = D5 & 0x20u, au3 = D3 & 0x08u, al3 = D3 & 0x40u;
+      const bool mainl = mu5 || ml5, antil = au3 || al3;
+      int D = mainl ? ((mu5 && ml5) ? 2 : (mu5 ? 0 : 1))    // D0B, D0U, D0D
+                    : ((au3 && al3) ? 5 : (au3 ? 3 : 4));   // D1B, D1U, D1D
+      int base = mainl ? (mu5 ? 0 : 5) : (au3 ? 3 : 6);
+      uint32_t b1 = mainl ? B5 : B3, b2 = mainl ? C5 : C3;
+      int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
+      bool has = mainl || antil;
+      lines |= has;
+      const uint32_t *lb = LB(has ? 72 + D * 3 + t : 102);
+      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
       // short diagonals (game.cpp:362-391): S0..S3, first found
-      D = -1;
-      if (D3 & 0x04u) D = 6, base = 2, step5 = 0;
-      else if (D5 & 0x02u) D = 7, base = 1, step5 = 1;
-      else if (D3 & 0x80u) D = 8, base = 7, step5 = 0;
-      else if (D5 & 0x10u) D = 9, base = 4, step5 = 1;
-      if (D >= 0) {
-        const uint32_t b1 = step5 ? B5 : B3, b2 = step5 ? C5 : C3;
-        const int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
-        lines = true;
-        const uint32_t *lb = LB(72 + D * 3 + t);
-        m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
-      }
+      const bool s0 = D3 & 0x04u, s1 = D5 & 0x02u, s2 = D3 & 0x80u, s3 = D5 & 0x10u;
+      D = s0 ? 6 : (s1 ? 7 : (s2 ? 8 : 9));
+      base = s0 ? 2 : (s1 ? 1 : (s2 ? 7 : 4));
+      const bool st5 = !s0 && (s1 || (!s2 && s3));
+      b1 = st5 ? B5 : B3, b2 = st5 ? C5 : C3;
+      t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
+      has = s0 || s1 || s2 || s3;
+      lines |= has;
+      lb = LB(has ? 72 + D * 3 + t : 102);
+      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
     }
   }
   m[0] = m0, m[1] = m1, m[2] = m2;
   return lines;
 }
+template <class LBFn>
+CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
+  return legal_moves_t<false>(st, m, LB);
+}
 
-// game.cpp:60-96 (no legality check, like the reference)
+// game.cpp:60-96 (no legality check, like the reference); select-only code
 CB_HD CState do_move(const CState &st, int move) {
   CState o;
   uint64_t w0 = st.w0 & 0x0000FFFFFFFFFFFFull;  // clear every frozen bit
   uint64_t w1 = st.w1;
   const uint32_t tp = (uint32_t)(w1 >> 48) & 1u;
-  int to;
-  if (move >= 48) {
-    const int piece = (move - 48) >> 4;
-    to = move & 15;
-    w0 |= 1ull << (16 * piece + to);
-    w1 -= 1ull << (8 * (tp * 3 + piece));
-  } else {
-    const int dir = move / 12, r = move - dir * 12;
-    int from;
-    if (dir == 0) {
-      from = (r / 3) * 4 + r % 3, to = from + 1;
-    } else if (dir == 1) {
-      from = r, to = r + 4;
-    } else if (dir == 2) {
-      to = (r / 3) * 4 + r % 3, from = to + 1;
-    } else {
-      to = r, from = r + 4;
-    }
-    const uint64_t stack = (w0 >> from) & 0x0000000100010001ull;
-    w0 &= ~(0x0000000100010001ull << from);
-    w0 |= stack << to;
-  }
+  const bool is_place = move >= 48;
+  // place: 48 + piece*16 + square
+  const int piece = (move - 48) >> 4;
+  // move: dir = id/12 (0 right, 1 down, 2 left, 3 up), r = id%12 (move.cpp:11-42)
+  const int dir = move / 12, r = move - dir * 12;
+  const int r3 = (r / 3) * 4 + r % 3;  // (row, col<3) of a horizontal move
+  const int from = dir == 0 ? r3 : (dir == 1 ? r : (dir == 2 ? r3 + 1 : r + 4));
+  const int to_m = dir == 0 ? r3 + 1 : (dir == 1 ? r + 4 : (dir == 2 ? r3 : r));
+  const int to = is_place ? (move & 15) : to_m;
+  const int fsh = is_place ? 0 : from;
+  const uint64_t planes = is_place ? 0ull : 0x0000000100010001ull;
+  const uint64_t stack = (w0 >> fsh) & planes;
+  w0 &= ~(planes << fsh);
+  w0 |= stack << to;
+  w0 |= is_place ? (1ull << (16 * (piece & 3) + to)) : 0ull;
   w0 |= 1ull << (48 + to);
+  w1 -= is_place ? (1ull << (8 * (tp * 3 + (uint32_t)(piece & 3)))) : 0ull;
   w1 ^= 1ull << 48;
   o.w0 = w0, o.w1 = w1;
   return o;
@@ -243,18 +238,22 @@ CB_HD int terminal_result(int n_legal, bool lines) {
   return n_legal == 0 ? (lines ? kResultLoss : kResultDraw) : kResultNone;
 }
 
-// id of the k-th (0-based) set bit of the 96-bit mask
+// id of the k-th (0-based) set bit of the 96-bit mask (popcount binary search, no loops)
 CB_HD int nth_move(const uint32_t m[3], int k) {
-  int base = 0;
-  uint32_t w = m[0];
-  int c = cb_popc(w);
-  if (k >= c) {
-    k -= c, base = 32, w = m[1];
-    c = cb_popc(w);
-    if (k >= c) k -= c, base = 64, w = m[2];
+  const int c0 = cb_popc(m[0]), c1 = cb_popc(m[1]);
+  const bool in0 = k < c0, in1 = k < c0 + c1;
+  uint32_t w = in0 ? m[0] : (in1 ? m[1] : m[2]);
+  int base = in0 ? 0 : (in1 ? 32 : 64);
+  k -= in0 ? 0 : (in1 ? c0 : c0 + c1);
+#pragma unroll
+  for (int sh = 16; sh >= 1; sh >>= 1) {
+    const int c = cb_popc(w & ((1u << sh) - 1u));
+    const bool up = k >= c;
+    k -= up ? c : 0;
+    w = up ? (w >> sh) : w;
+    base += up ? sh : 0;
   }
-  for (int i = 0; i < k; ++i) w &= w - 1;
-  return base + cb_ffs(w) - 1;
+  return base;
 }
 
 // deterministic per-state random word of the game-logic workload (splitmix64 finaliser)

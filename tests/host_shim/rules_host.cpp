@@ -8,11 +8,12 @@
 extern "C" void shim_step_batch(int64_t n, const uint64_t *states, uint64_t seed, uint32_t *maskflags,
                                 uint64_t *next, float *enc) {
   using namespace cb200;
-  auto LB = [](int idx) { return kCLineBreakers[idx]; };
+  static const uint32_t ones[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  auto LB = [](int idx) { return idx < 102 ? kCLineBreakers[idx] : ones; };
   for (int64_t i = 0; i < n; ++i) {
     CState s{states[2 * i], states[2 * i + 1]};
     uint32_t m[3];
-    bool lines = legal_moves(s, m, LB);
+    bool lines = (i & 1) ? legal_moves_t<true>(s, m, LB) : legal_moves_t<false>(s, m, LB);
     int nl = cb_popc(m[0]) + cb_popc(m[1]) + cb_popc(m[2]);
     int result = terminal_result(nl, lines);
     int chosen = 0x7f;

@@ -153,3 +153,41 @@ def test_fused_selfplay_bf16_equals_oracle_driven_by_the_same_network(oracle):
     assert pr.tobytes() == r["samples"][2].tobytes()
     oc, ec = oracle.counters(o), fused.counters()
     assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
+
+
+def _trained_like_params(seed):
+    """Random weights with non-trivial biases and BatchNorm statistics, so that the folded
+    biases are non-zero (random init has b = 0, beta = 0)."""
+    rng = np.random.default_rng(seed)
+    p = cb.random_weights(seed)
+    for L in p["layers"]:
+        n = L["gamma"].size
+        L["gamma"] = rng.uniform(0.5, 1.5, n).astype(np.float32)
+        L["beta"] = rng.uniform(-0.3, 0.3, n).astype(np.float32)
+        L["mean"] = rng.uniform(-0.1, 0.3, n).astype(np.float32)
+        L["var"] = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        L["b"] = rng.uniform(-0.2, 0.2, n).astype(np.float32)
+    p["head"]["bv"] = rng.uniform(-0.2, 0.2, 1).astype(np.float32)
+    p["head"]["bp"] = rng.uniform(-0.5, 0.5, 96).astype(np.float32)
+    return p
+
+
+def test_networks_with_nonzero_biases(oracle):
+    """Bias handling: fp32 kernel adds fp32 biases; the tensor-core kernel carries them through
+    the GEMM as a bf16 hi + lo pair on two constant-one activation columns."""
+    x = sample_positions(oracle, 700, seed=11)
+    flat = cb.fold_batchnorm(_trained_like_params(4))
+    v64, p64 = forward_folded(flat, x, np.float64)
+    t = cb.Trainer(64, "", 1, 32, 16)
+    t.set_weights(flat, 0, "fp32")
+    ev, pr = t.evaluate(x)
+    assert np.max(np.abs(ev - v64) / np.maximum(np.abs(v64), 1e-3)) < 1e-5
+    assert np.max(np.abs(pr - p64) / p64) < 1e-5
+    t.set_weights(flat, 0, "bf16")
+    ev, pr = t.evaluate(x)
+    vb, pb = forward_folded(flat, x, np.float64, round_bf16=True)
+    e_emul = np.max(np.abs(pr - pb) / pb), np.max(np.abs(ev - vb))
+    e_fp = np.max(np.abs(pr - p64) / p64), np.max(np.abs(ev - v64))
+    print("nonzero-bias bf16: vs emulation probs rel %.3e value abs %.3e; vs fp64 probs rel %.3e value abs %.3e" % (e_emul + e_fp))
+    assert e_emul[0] < 5e-3 and e_emul[1] < 5e-3
+    assert e_fp[0] < 2e-2 and e_fp[1] < 2e-2
