@@ -68,6 +68,8 @@ struct cb200_trainer {
   ulonglong2 *d_packed = nullptr;
   int32_t *d_offs = nullptr, *d_summary = nullptr, *d_soff = nullptr;
   float *d_vsqrt = nullptr;
+  float *d_samp = nullptr;  // cached output buffer of write_samples
+  size_t samp_rows = 0;
   int32_t *h_summary = nullptr;  // pinned
   NetF32 net32[2];
   NetTC nettc[2];
@@ -531,6 +533,7 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(t->d_eval), cudaFree(t->d_probs), cudaFree(t->d_rows), cudaFree(t->d_packed);
   cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
   cudaFree(t->d_vsqrt);
+  cudaFree(t->d_samp);
   if (t->h_summary) cudaFreeHost(t->h_summary);
   if (t->h_gctr) cudaFreeHost(t->h_gctr);
   cudaFree(t->d_gctr);
@@ -617,12 +620,17 @@ int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eva
     ns += t->h_ctl[(size_t)g * kCtlWords + CW_N_SAMPLES];
   }
   if (ns == 0) return CB200_OK;
-  float *d_gs = nullptr, *d_ev = nullptr, *d_pr = nullptr;
   const size_t rows = (size_t)ns * 8;
-  rc = dmalloc(&d_gs, rows * CB200_STATE_SIZE);
-  if (rc == CB200_OK) rc = dmalloc(&d_ev, rows);
-  if (rc == CB200_OK) rc = dmalloc(&d_pr, rows * CB200_NUM_MOVES);
-  if (rc == CB200_OK) {
+  if (rows > t->samp_rows) {  // one cached device buffer: [rows][70] + [rows] + [rows][96]
+    cudaFree(t->d_samp);
+    t->d_samp = nullptr, t->samp_rows = 0;
+    const size_t want = rows + rows / 4 + 1024;
+    rc = dmalloc(&t->d_samp, want * (CB200_STATE_SIZE + 1 + CB200_NUM_MOVES));
+    if (rc != CB200_OK) return rc;
+    t->samp_rows = want;
+  }
+  float *d_gs = t->d_samp, *d_ev = d_gs + t->samp_rows * CB200_STATE_SIZE, *d_pr = d_ev + t->samp_rows;
+  {
     cudaStream_t s = G().stream;
     cudaError_t e = cudaMemcpyAsync(t->d_soff, soff.data(), Gn * sizeof(int32_t),
                                     cudaMemcpyHostToDevice, s);
@@ -640,7 +648,6 @@ int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eva
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) rc = set_error(CB200_ERR_CUDA, cudaGetErrorString(e));
   }
-  cudaFree(d_gs), cudaFree(d_ev), cudaFree(d_pr);
   return rc;
 }
 
