@@ -211,7 +211,7 @@ int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_
   const long prs = probs_move_major ? 1 : CB200_NUM_MOVES;
   const long pcs = probs_move_major ? (long)t->cap : 1;
   ProfScope ps(t, 3);
-  k_iterate<false><<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
+  k_iterate<false, 8><<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
                                                        to_play, t->iterations_done,
                                                        t->stagger_div);
   CB_LAUNCHED();
@@ -823,7 +823,17 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   // work queued on the default stream (weights, reset) must be visible to the group streams
   CB_CUDA(cudaStreamSynchronize(G().stream));
   int done_iters = 0, result = 0;
+  long long live_games = t->P.num_games;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
   while (max_iterations <= 0 || done_iters < max_iterations) {
+    int variant = 8;
+    if (ng == 1 && !getenv("CB200_FIXED_VARIANT")) {
+      const long long per_sm = (live_games + sms - 1) / sms;  // warps (= games) per SM
+      if (per_sm <= 3 * kTreeWarps) variant = 3;
+      else if (per_sm <= 4 * kTreeWarps) variant = 4;
+      else if (per_sm <= 5 * kTreeWarps) variant = 5;
+    }
     int batch = 32;
     if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
     for (int i = 0; i < batch; ++i) {
@@ -849,8 +859,16 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
         P.game_begin = gb, P.game_end = ge, P.group_row0 = row0, P.group_ctr = ctr;
         {
           ProfScope ps(t, 3, st);
-          k_iterate<true><<<(ge - gb + kTreeWarps - 1) / kTreeWarps, kTreeWarps * 32, 0, st>>>(
-              P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, t->stagger_div);
+          const dim3 grid((ge - gb + kTreeWarps - 1) / kTreeWarps), block(kTreeWarps * 32);
+#define CB_ITER(MB) \
+  k_iterate<true, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, \
+                                              t->stagger_div)
+          // register-budget variant by live games: one wave must hold every live game
+          if (variant == 3) CB_ITER(3);
+          else if (variant == 4) CB_ITER(4);
+          else if (variant == 5) CB_ITER(5);
+          else CB_ITER(8);
+#undef CB_ITER
           CB_LAUNCHED();
         }
         CB_CUDA(cudaGetLastError());
@@ -879,6 +897,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       if (c[2 + par] == 0 && c[par] == 0) active[g] = 0;
       live += c[2 + par];
     }
+    live_games = live;
     if (live == 0) {
       result = 1;
       break;

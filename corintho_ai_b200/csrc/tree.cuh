@@ -29,6 +29,9 @@ constexpr int kMaxPath = 64;
 constexpr int kPendWords = 2 + kMaxPath;  // leaf_off, path_len, path[kMaxPath]
 constexpr int kMaxSamples = 64;
 constexpr int kTreeWarps = 4;  // games per CTA
+// The game-step kernel is compiled for several register budgets (resident CTAs per SM):
+// 8 -> 64 regs (32 warps/SM, spills; best while every SM is full), 5 -> 96, 4 -> 128,
+// 3 -> ~156 regs (no spills, shortest serial chain; best once few games are live).
 constexpr int kCtlWords = 16;
 constexpr int kTreeCtlWords = 12;
 constexpr int kTabSize = 4096;  // visit counts served by the sqrt / reciprocal tables
@@ -188,15 +191,14 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // In-place regeneration of the 624-word state in three batches (new[i] depends on old[i],
 // old[i+1] and, for i >= 227, on new[i-227]): [0,224) uses only old words, [224,448) needs new
 // words < 221, [448,624) needs new words < 397 and new[0]. One load round-trip per batch.
-__device__ __noinline__ void mt_twist(Ctx &c) {
-  uint32_t *mt = c.mt;
+__device__ __noinline__ void mt_twist_state(uint32_t *mt, int lane) {
 #pragma unroll 1
   for (int b0 = 0; b0 < 624; b0 += 224) {
     const int b1 = b0 + 224 < 624 ? b0 + 224 : 624;
     uint32_t v[7];
 #pragma unroll
     for (int u = 0; u < 7; ++u) {
-      const int i = b0 + c.lane + 32 * u;
+      const int i = b0 + lane + 32 * u;
       v[u] = 0;
       if (i < b1) {
         const uint32_t a = mt[i], b = mt[i + 1 == 624 ? 0 : i + 1];
@@ -208,11 +210,14 @@ __device__ __noinline__ void mt_twist(Ctx &c) {
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < 7; ++u) {
-      const int i = b0 + c.lane + 32 * u;
+      const int i = b0 + lane + 32 * u;
       if (i < b1) mt[i] = v[u];
     }
     __syncwarp();
   }
+}
+__device__ __forceinline__ void mt_twist(Ctx &c) {
+  mt_twist_state(c.mt, c.lane);
   c.mt_idx = 0;
 }
 // n (<=96) consecutive outputs; output e = lane + 32 j lands in out[j] of that lane
@@ -322,7 +327,7 @@ __device__ __forceinline__ void request_root(Ctx &c) {
 // ---- TrainMC::moveDown (trainmc.cpp:475-495): child behind root slot e becomes the root -----
 // Breadth-first copy of the kept subtree into the spare arena; only records that have
 // children are queued for scanning (queue grows down from the top of the target arena).
-__device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
+__device__ __forceinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
   const uint32_t *src = c.base;
   uint32_t *dst = c.arenas + (size_t)c.spare * P.arena_words;
   const uint4 s = ld4(src + c.root_off + 8 + 4 * e);
@@ -402,120 +407,6 @@ __device__ __noinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
 // ---- TrainMC::receiveEval (trainmc.cpp:269-296) ---------------------------------------------
 // probs element (answer row k, move m) = probs[k * prs + m * pcs]: row-major [n][96] from the
 // host API (prs 96, pcs 1), move-major [96][ld] from the tensor-core network (prs 1, pcs ld)
-__device__ __noinline__ void receive_eval_serial(Ctx &c, const TreeParams &P, WarpSm &sm,
-                                          const float *eval, const float *probs, long prs,
-                                          long pcs) {
-  const int np = c.n_pending;
-  for (int k = 0; k < np; ++k) {
-    const uint32_t *pd = c.pending + k * kPendWords;
-    const uint32_t leaf_off = pd[0];
-    const int path_len = (int)pd[1];
-    uint32_t *r = c.base + leaf_off;
-    const int n = (int)(r[4] & 0xffu);
-    const float *pk = probs + (long)k * prs;
-    // getFilteredProbs (trainmc.cpp:212-234): gather legal priors, float sum in edge order.
-    // Pass j handles edges 32j..32j+31; passes beyond n are skipped warp-uniformly.
-    const int np4 = (n + 3) & ~3;
-    uint32_t w3[3] = {0, 0, 0};
-    float fv[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (32 * j < np4) {
-        const int e = c.lane + 32 * j;
-        if (e < n) {
-          w3[j] = r[8 + 4 * e + 3];
-          fv[j] = pk[(long)s3_move(w3[j]) * pcs];
-        }
-        if (e < np4) sm.f[e] = fv[j];  // zero padding up to a multiple of 4 (x + 0 is exact)
-      }
-    }
-    __syncwarp();
-    float sum = 0.0f;
-    for (int j = 0; j < np4; j += 4) {
-      const float4 v = *reinterpret_cast<const float4 *>(sm.f + j);
-      sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, v.x), v.y), v.z), v.w);
-    }
-    const float scalar = __double2float_rn(
-        __dmul_rn(__drcp_rn((double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
-    __syncwarp();
-    // generateDirichlet (trainmc.cpp:236-246): one MT draw per legal move, in edge order
-    uint32_t rnd[3];
-    rng_block(c, n, rnd);
-    float dv[3] = {0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (32 * j < np4) {
-        const int e = c.lane + 32 * j;
-        if (e < n) dv[j] = d_gamma[rnd[j] & 1023u];
-        if (e < np4) sm.f[e] = dv[j];
-      }
-    }
-    __syncwarp();
-    float dsum = 0.0f;
-    for (int j = 0; j < np4; j += 4) {
-      const float4 v = *reinterpret_cast<const float4 *>(sm.f + j);
-      dsum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(dsum, v.x), v.y), v.z), v.w);
-    }
-    const float dscalar =
-        __double2float_rn(__dmul_rn(__drcp_rn((double)dsum), (double)P.epsilon));
-    __syncwarp();
-    // setProbs (trainmc.cpp:248-267)
-    float wv[3] = {0.0f, 0.0f, 0.0f};
-    float mx = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (32 * j < n) {
-        const int e = c.lane + 32 * j;
-        if (e < n) {
-          wv[j] = __fadd_rn(__fmul_rn(fv[j], scalar), __fmul_rn(dv[j], dscalar));
-          mx = fmaxf(mx, wv[j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, d));
-    const float denom = __fdiv_rn(511.0f, mx);
-    int qsum = 0;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (32 * j < n) {
-        const int e = c.lane + 32 * j;
-        if (e < n) {
-          // lround(): round half away from zero; x >= 0 here, exact in double
-          const double x = (double)__fmul_rn(wv[j], denom);
-          const long long q = (long long)floor(x + 0.5);
-          const int prob = q < 1 ? 1 : (int)q;
-          r[8 + 4 * e + 3] = (w3[j] & ~(0x1ffu << 7)) | (((uint32_t)prob & 0x1ffu) << 7);
-          qsum += prob;
-        }
-      }
-    }
-    qsum = __reduce_add_sync(kFull, qsum);
-    if (c.lane == 0) r[5] = __float_as_uint(__double2float_rn(__drcp_rn((double)(float)qsum)));
-    // backup (trainmc.cpp:281-292): the leaf takes e-1, its parent -e-1, ... up to the root
-    const float ev = eval[k];
-    for (int l0 = 0; l0 < path_len; l0 += 32) {
-      const int lvl = l0 + c.lane;  // index into path: 0 = child of root .. path_len-1 = leaf
-      if (lvl < path_len) {
-        const int dist = path_len - 1 - lvl;
-        const float ce = (dist & 1) ? -ev : ev;
-        const float d = __double2float_rn(__dsub_rn((double)ce, 1.0));
-        uint32_t *s = c.base + pd[2 + lvl];
-        s[0] = __float_as_uint(__fadd_rn(__uint_as_float(s[0]), d));
-        s[3] = s[3] & ~kS3Allv;
-      }
-    }
-    {
-      const float ce = (path_len & 1) ? -ev : ev;
-      c.root_eval = __fadd_rn(c.root_eval, __double2float_rn(__dsub_rn((double)ce, 1.0)));
-    }
-    __syncwarp();
-  }
-  c.root_allv = 0;
-  c.d_evals += np;
-  c.n_pending = 0;
-}
-
 // largest k in [k0, k1) with pre[k] <= i
 __device__ __forceinline__ int find_leaf(const int *pre, int k0, int k1, int i) {
   int lo = k0, hi = k1 - 1;
@@ -527,32 +418,31 @@ __device__ __forceinline__ int find_leaf(const int *pre, int k0, int k1, int i) 
 }
 
 // ---- TrainMC::receiveEval (trainmc.cpp:269-296), latency-oriented restatement ----------------
-// Same arithmetic, in the same order per leaf, as receive_eval_serial (which mirrors the
-// reference loop literally), but organised so that the loads of ALL pending leaves are in
-// flight together:
+// Same arithmetic, in the same order per leaf, as the reference loop, but organised so that the
+// loads of all pending leaves (processed 32 at a time) are in flight together:
 //   "flat" phases  : one lane per legal-move slot over the concatenation of all leaves
 //                    (the MT19937 draw of flat element i is simply draw number i);
 //   "leaf" phases  : one lane per leaf for the order-dependent float sums / max / integer sum;
 //   backup         : per tree level, the lanes whose paths meet in the same slot are grouped with
 //                    __match_any_sync and the lowest lane applies the adds in leaf order.
-__device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &sm,
+__device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &sm,
                                           const float *eval, const float *probs, long prs,
                                           long pcs) {
-  const int np = c.n_pending;
-  if (np > 32) {
-    receive_eval_serial(c, P, sm, eval, probs, prs, pcs);
-    return;
-  }
+  const int np_all = c.n_pending;
   const int lane = c.lane;
+  for (int b0 = 0; b0 < np_all; b0 += 32) {
+  const int np = min(32, np_all - b0);
+  const float *eval_b = eval + b0;
+  const float *probs_b = probs + (long)b0 * prs;
   // ---- leaf phase 0: pending records and leaf headers
   uint32_t my_off = 0;
   int my_n = 0, my_plen = 0;
   float my_ev = 0.0f;
-  const uint32_t *my_pd = c.pending + lane * kPendWords;
+  const uint32_t *my_pd = c.pending + (b0 + lane) * kPendWords;
   if (lane < np) {
     my_off = my_pd[0];
     my_plen = (int)my_pd[1];
-    my_ev = eval[lane];
+    my_ev = eval_b[lane];
     my_n = (int)(c.base[my_off + 4] & 0xffu);
   }
   const int incl = (int)warp_incl_scan((uint32_t)my_n, lane);
@@ -594,7 +484,7 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + lane + 32 * u;
         pv4[u] = 0.0f;
-        if (i < T) pv4[u] = probs[(long)kk[u] * prs + (long)s3_move(w3[u]) * pcs];
+        if (i < T) pv4[u] = probs_b[(long)kk[u] * prs + (long)s3_move(w3[u]) * pcs];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -709,13 +599,14 @@ __device__ __noinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm &s
     c.root_eval = __fadd_rn(c.root_eval, __double2float_rn(__dsub_rn((double)ce, 1.0)));
   }
   __syncwarp();
+  }  // batch of <= 32 leaves
   c.root_allv = 0;
-  c.d_evals += np;
+  c.d_evals += np_all;
   c.n_pending = 0;
 }
 
 // ---- TrainMC::search (trainmc.cpp:602-696) --------------------------------------------------
-__device__ __noinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
+__device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
   ++c.searches_done;
   int level = 0;
   uint32_t node = c.root_off;
@@ -984,7 +875,7 @@ __device__ __forceinline__ void reset_tree_after(Ctx &c, const TreeParams &P, in
   for (int j = 0, e = c.lane; j < 3 && 32 * j < (n); ++j, e += 32)
 
 // ---- TrainMC::chooseMove (trainmc.cpp:110-137, 310-473) -------------------------------------
-__device__ __noinline__ int choose_move(Ctx &c, const TreeParams &P, WarpSm &sm,
+__device__ __forceinline__ int choose_move(Ctx &c, const TreeParams &P, WarpSm &sm,
                                         float *prob_sample) {
   const uint32_t *r = c.base + c.root_off;
   const int n = (int)(r[4] & 0xffu);
@@ -1107,22 +998,25 @@ __device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &
 // performs exactly the same TrainMC::doIteration then. The order of operations within the game
 // is unchanged (so are its results); only the launch in which they happen moves, which keeps
 // the mover's warp from doing two search phases in one launch.
-__device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &P, WarpSm &sm,
-                                                      bool defer_search) {
-  bool need_eval = false;
-  while (!need_eval) {
+// Returns kTurnWait (an evaluation is pending, or the next search was deferred), kTurnOver (game
+// finished) or kTurnIterate (the caller must run TrainMC::doIteration for the side now to move,
+// without answers, and come back here if that completes the turn as well).
+enum : int { kTurnWait = 0, kTurnOver = 1, kTurnIterate = 2 };
+__device__ __forceinline__ int choose_move_and_continue(Ctx &c, const TreeParams &P, WarpSm &sm,
+                                                        bool defer_search) {
+  {
     if (r_known(c.root_result) && c.mate_turn == 0) c.mate_turn = c.n_samples + 1;
     c.d_sims += c.searches_done;
     c.d_moves += 1;
     if (c.d_moves > 128) {  // no Corintho game has this many plies: refuse to spin
       c.error = CB200_ERR_STATE;
-      return true;
+      return kTurnOver;
     }
     int choice;
     if (!P.testing) {  // SelfPlayer::chooseMove (selfplayer.cpp:234-244)
       if (c.n_samples >= kMaxSamples) {
         c.error = CB200_ERR_OVERFLOW;
-        return true;
+        return kTurnOver;
       }
       float *ps = c.sample_probs + (size_t)c.n_samples * CB200_NUM_MOVES;
       for (int j = c.lane; j < CB200_NUM_MOVES; j += 32) ps[j] = 0.0f;
@@ -1137,7 +1031,7 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
     } else {
       choice = choose_move(c, P, sm, nullptr);
     }
-    if (c.error) return true;
+    if (c.error) return kTurnOver;
     __syncwarp();
     if (r_terminal(c.root_result)) {  // endGame (selfplayer.cpp:206-232)
       if (c.root_result == kResultDraw)
@@ -1150,7 +1044,7 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
       store_tree(c);
       load_tree(c, P, 1 - c.cur_p);
       c.has_root = 0;
-      return true;
+      return kTurnOver;
     }
     const CState st = rec_state(c.base + c.root_off);
     const int depth = (int)((c.base[c.root_off + 4] >> 8) & 0xffu);
@@ -1160,15 +1054,13 @@ __device__ __noinline__ bool choose_move_and_continue(Ctx &c, const TreeParams &
     if (!c.has_root) {
       fresh_tree(c, P, st, depth);
       c.searches_done = 0;
-      return tree_do_iteration(c, P, sm, nullptr, nullptr);  // false: the root needs an eval
+      return kTurnIterate;  // doIteration will just queue the fresh root for evaluation
     }
-    need_eval = receive_opponent_move(c, P, choice, st, depth);
-    if (c.error) return true;
-    if (!need_eval && defer_search) return false;
-    if (!need_eval) need_eval = !tree_do_iteration(c, P, sm, nullptr, nullptr);
-    if (c.error) return true;
+    const bool need_eval = receive_opponent_move(c, P, choice, st, depth);
+    if (c.error) return kTurnOver;
+    if (need_eval || defer_search) return kTurnWait;
+    return kTurnIterate;
   }
-  return false;
 }
 
 // Which games take part in this call (trainer.cpp:39-49, 79-101, 164-236)
@@ -1182,8 +1074,8 @@ __device__ __forceinline__ bool game_selected(const int32_t *ctl, int to_play) {
 // eval/probs (exclusive prefix sum of the request counts the answers were produced for).
 // kFused: answers are read at the row the game was handed last time (ctl[CW_REQ_BASE]) and the
 // new leaf states are appended to the group's packed request list (parity `iteration & 1`).
-template <bool kFused>
-__global__ void __launch_bounds__(kTreeWarps * 32, 8)
+template <bool kFused, int kMinBlocks>
+__global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
     k_iterate(TreeParams P, const float *__restrict__ eval, const float *__restrict__ probs,
               long prs, long pcs, const int32_t *__restrict__ offs, int to_play, int iteration,
               int stagger_div) {
@@ -1218,13 +1110,21 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 8)
   c.sample_probs = P.sample_probs + (size_t)g * kMaxSamples * CB200_NUM_MOVES;
   load_tree(c, P, c.to_play);
   const int off = kFused ? ctl[CW_REQ_BASE] : offs[g];
-  // SelfPlayer::doIteration (selfplayer.cpp:115-122)
-  bool done = tree_do_iteration(c, P, sm, eval + off, probs + (long)off * prs, prs, pcs);
-  if (!c.error && done) {
+  // SelfPlayer::doIteration (selfplayer.cpp:115-122) with chooseMoveAndContinue's loop
+  // (selfplayer.cpp:246-291) unrolled here so that doIteration has a single call site
+  bool done = false;
+  const float *ev_p = eval + off, *pr_p = probs + (long)off * prs;
+  for (;;) {
+    const bool turn_done = tree_do_iteration(c, P, sm, ev_p, pr_p, prs, pcs);
+    if (c.error || !turn_done) break;
     const long long tm = clock64();
-    const long long ts = c.t_search, ti = c.t_ingest;
-    done = choose_move_and_continue(c, P, sm, kFused);
-    c.t_move += (clock64() - tm) - (c.t_search - ts) - (c.t_ingest - ti);
+    const int r = choose_move_and_continue(c, P, sm, kFused);
+    c.t_move += clock64() - tm;
+    if (r == kTurnOver) {
+      done = true;
+      break;
+    }
+    if (r == kTurnWait) break;
   }
   if (c.error) done = true;
   store_tree(c);

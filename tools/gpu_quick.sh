@@ -1,3 +1,5 @@
-timeout 600 python -m pytest tests/test_gpu_net.py -q -m gpu --timeout 200 -x -s 2>&1 | grep -E "passed|failed|bf16|Error|error" | head
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_n1.json')); print({k:d[k] for k in ['value','ms_per_step','ms_per_step_profiled','moves_per_sec','gpu_launches']}); print(d['e2e']); print(d['roofline']); print(d['cpu_baseline']); print(d['clocks']); print(d['game_logic'])"
+timeout 600 python -m pytest tests/test_gpu_net.py tests/test_gpu_trainer.py -q -m gpu --timeout 200 -x 2>&1 | tail -2
+echo "== whole run (variants by live games)"; CB200_GROUPS=1 timeout 120 python tools/prof_selfplay.py 4096 800 0 bf16 noprof 2>&1 | grep done
+echo "== whole run (fixed 64-reg variant)"; CB200_FIXED_VARIANT=1 CB200_GROUPS=1 timeout 120 python tools/prof_selfplay.py 4096 800 0 bf16 noprof 2>&1 | grep done
+echo "== 1 game"; CB200_GROUPS=1 timeout 120 python tools/prof_selfplay.py 1 800 300 bf16 2>&1 | tail -1
+echo "== 32768 games"; CB200_GROUPS=1 timeout 300 python tools/prof_selfplay.py 32768 800 0 bf16 noprof 2>&1 | grep done
