@@ -833,6 +833,8 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       if (per_sm <= 3 * kTreeWarps) variant = 3;
       else if (per_sm <= 4 * kTreeWarps) variant = 4;
       else if (per_sm <= 5 * kTreeWarps) variant = 5;
+      else if (per_sm <= 6 * kTreeWarps) variant = 6;
+      else if (per_sm <= 7 * kTreeWarps) variant = 7;
     }
     int batch = 32;
     if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
@@ -867,6 +869,8 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
           if (variant == 3) CB_ITER(3);
           else if (variant == 4) CB_ITER(4);
           else if (variant == 5) CB_ITER(5);
+          else if (variant == 6) CB_ITER(6);
+          else if (variant == 7) CB_ITER(7);
           else CB_ITER(8);
 #undef CB_ITER
           CB_LAUNCHED();
