@@ -345,10 +345,10 @@ def run_engine_arm(args, rank, world, local_rank):
         gs, ev, pr = pin_gs.numpy()[:n_s * 8], pin_ev.numpy()[:n_s * 8], pin_pr.numpy()[:n_s * 8]
         tr.writeSamples(gs, ev, pr)
         if dist is not None:  # all-gather the finished (un-augmented) samples over NCCL
-            from corintho_ai_b200.dist import all_gather_rows, pack_raw_samples
+            from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
             g0 = time.perf_counter()
-            st, prb, lb, go = tr.raw_samples()
-            allrows, _ = all_gather_rows(dist, pack_raw_samples(st, prb, lb, go, first_game=rank * G), dev)
+            ptr, n_rows = tr.raw_samples_device()
+            allrows, _ = all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
             torch.cuda.synchronize()
             gather_s += time.perf_counter() - g0
         torch.cuda.synchronize()

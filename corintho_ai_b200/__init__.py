@@ -78,6 +78,7 @@ def lib():
         "cb200_trainer_counters": (i32, [vp, vp]),
         "cb200_trainer_write_raw_samples": (i32, [vp, vp, vp, vp, vp]),
         "cb200_trainer_game_results": (i32, [vp, vp]),
+        "cb200_trainer_raw_samples_device": (i32, [vp, vp, vp]),
         "cb200_trainer_set_weights": (i32, [vp, i32, vp, C.c_size_t, i32]),
         "cb200_trainer_evaluate": (i32, [vp, i32, i32, vp, vp, vp]),
         "cb200_trainer_run_selfplay": (i32, [vp, i32, i32]),
@@ -325,6 +326,13 @@ class Trainer:
         go = np.zeros(max(n, 1), np.int32)
         _check(lib().cb200_trainer_write_raw_samples(self._h, _ptr(st), _ptr(pr), _ptr(lb), _ptr(go)))
         return st[:n], pr[:n], lb[:n], go[:n]
+
+    def raw_samples_device(self):
+        """(device pointer, n_rows) of the [n_rows][102] float row block (see the C header)."""
+        ptr = C.c_void_p()
+        n = C.c_int()
+        _check(lib().cb200_trainer_raw_samples_device(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value or 0, n.value
 
     def game_results(self):
         out = np.zeros(self.num_games, np.int32)

@@ -54,6 +54,31 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Un-augmented samples as 102-float rows for the NCCL gather: 4 words of cstate (bit-cast),
+// 96 move probabilities, the value label, the global game index (bit-cast).
+__global__ void __launch_bounds__(256)
+    k_pack_raw_samples(TreeParams P, const int32_t *__restrict__ soff, float *__restrict__ rows) {
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int g = w / kMaxSamples, i = w - g * kMaxSamples;
+  if (g >= P.num_games) return;
+  const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+  const int ns = ctl[CW_N_SAMPLES];
+  if (i >= ns) return;
+  float *out = rows + ((size_t)soff[g] + i) * 102;
+  const float *pr = P.sample_probs + ((size_t)g * kMaxSamples + i) * CB200_NUM_MOVES;
+  for (int j = lane; j < CB200_NUM_MOVES; j += 32) out[4 + j] = pr[j];
+  if (lane == 0) {
+    const ulonglong2 sv = P.sample_state[(size_t)g * kMaxSamples + i];
+    out[0] = __uint_as_float((uint32_t)sv.x), out[1] = __uint_as_float((uint32_t)(sv.x >> 32));
+    out[2] = __uint_as_float((uint32_t)sv.y), out[3] = __uint_as_float((uint32_t)(sv.y >> 32));
+    float ev = ctl[CW_RESULT] == kResultDraw ? 0.0f : 1.0f;
+    if ((ns - 1 - i) & 1) ev = -ev;
+    out[100] = ev;
+    out[101] = __int_as_float(P.first_game + g);
+  }
+}
+
 }  // namespace cb200
 
 // ==============================================================================================
@@ -70,6 +95,8 @@ struct cb200_trainer {
   float *d_vsqrt = nullptr;
   float *d_samp = nullptr;  // cached output buffer of write_samples
   size_t samp_rows = 0;
+  float *d_raw = nullptr;   // cached [rows][102] buffer of raw_samples_device
+  size_t raw_rows = 0;
   int32_t *h_summary = nullptr;  // pinned
   NetF32 net32[2];
   NetTC nettc[2];
@@ -534,6 +561,7 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
   cudaFree(t->d_vsqrt);
   cudaFree(t->d_samp);
+  cudaFree(t->d_raw);
   if (t->h_summary) cudaFreeHost(t->h_summary);
   if (t->h_gctr) cudaFreeHost(t->h_gctr);
   cudaFree(t->d_gctr);
@@ -623,6 +651,7 @@ int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eva
   const size_t rows = (size_t)ns * 8;
   if (rows > t->samp_rows) {  // one cached device buffer: [rows][70] + [rows] + [rows][96]
     cudaFree(t->d_samp);
+  cudaFree(t->d_raw);
     t->d_samp = nullptr, t->samp_rows = 0;
     const size_t want = rows + rows / 4 + 1024;
     rc = dmalloc(&t->d_samp, want * (CB200_STATE_SIZE + 1 + CB200_NUM_MOVES));
@@ -760,6 +789,39 @@ int cb200_trainer_write_raw_samples(cb200_trainer *t, uint64_t *states, float *p
       if (game_of) game_of[row] = g;
     }
   }
+  return CB200_OK;
+}
+
+int cb200_trainer_raw_samples_device(cb200_trainer *t, void **rows_device, int *n_rows) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (!rows_device || !n_rows) return set_error(CB200_ERR_ARG, "null output");
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  const int Gn = t->P.num_games;
+  std::vector<int32_t> soff(Gn);
+  long long ns = 0;
+  for (int g = 0; g < Gn; ++g) {
+    soff[g] = (int32_t)ns;
+    ns += t->h_ctl[(size_t)g * kCtlWords + CW_N_SAMPLES];
+  }
+  if ((size_t)ns > t->raw_rows) {
+    cudaFree(t->d_raw);
+    t->d_raw = nullptr, t->raw_rows = 0;
+    const size_t want = (size_t)ns + (size_t)ns / 4 + 1024;
+    if ((rc = dmalloc(&t->d_raw, want * 102)) != CB200_OK) return rc;
+    t->raw_rows = want;
+  }
+  cudaStream_t s = G().stream;
+  CB_CUDA(cudaMemcpyAsync(t->d_soff, soff.data(), Gn * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  if (ns > 0) {
+    const long long warps = (long long)Gn * kMaxSamples;
+    k_pack_raw_samples<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(t->P, t->d_soff, t->d_raw);
+    CB_LAUNCHED();
+    CB_CUDA(cudaGetLastError());
+  }
+  CB_CUDA(cudaStreamSynchronize(s));
+  *rows_device = t->d_raw;
+  *n_rows = (int)ns;
   return CB200_OK;
 }
 

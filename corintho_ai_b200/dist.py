@@ -50,3 +50,35 @@ def all_gather_rows(dist, rows, device):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad)
     return np.concatenate([o[:c].cpu().numpy() for o, c in zip(out, counts)], 0), counts
+
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can view engine-owned device memory."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def device_rows_as_tensor(ptr, n_rows, width, device):
+    import torch
+    if n_rows == 0 or not ptr:
+        return torch.empty((0, width), dtype=torch.float32, device=device)
+    return torch.as_tensor(_DeviceArray(ptr, (n_rows, width)), device=device)
+
+
+def all_gather_rows_device(dist, rows, device):
+    """Variable-length all-gather of a device tensor [n_r, w] over NCCL; returns (tensor
+    [sum n_r, w] in rank order on the device, counts)."""
+    import torch
+    world = dist.get_world_size()
+    n_loc = torch.tensor([rows.shape[0]], device=device, dtype=torch.int64)
+    counts = torch.zeros(world, device=device, dtype=torch.int64)
+    dist.all_gather_into_tensor(counts, n_loc)
+    counts = [int(c) for c in counts.tolist()]
+    n_max = max(max(counts), 1)
+    pad = torch.zeros((n_max, rows.shape[1]), device=device, dtype=torch.float32)
+    pad[:rows.shape[0]] = rows
+    out = torch.empty((world * n_max, rows.shape[1]), device=device, dtype=torch.float32)
+    dist.all_gather_into_tensor(out, pad)
+    return torch.cat([out[r * n_max:r * n_max + c] for r, c in enumerate(counts)], 0), counts

@@ -127,6 +127,10 @@ int cb200_trainer_counters(cb200_trainer *t, int64_t out[4]);
  * labels[num_samples], game_of[num_samples] (local game index). Any pointer may be NULL. */
 int cb200_trainer_write_raw_samples(cb200_trainer *t, uint64_t *states, float *probs,
                                     float *labels, int32_t *game_of);
+/* Same rows on the device for the NCCL gather: *rows_device -> float [n_rows][102] =
+ * {cstate as 4 bit-cast words, probs[96], label, global game index bit-cast}; the buffer is owned
+ * by the trainer and valid until the next call. */
+int cb200_trainer_raw_samples_device(cb200_trainer *t, void **rows_device, int *n_rows);
 /* per game: result (util.h:58-61: 1 first player lost, 2 draw, 3 first player won) */
 int cb200_trainer_game_results(cb200_trainer *t, int32_t *results /* [num_games] */);
 

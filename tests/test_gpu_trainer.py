@@ -103,3 +103,15 @@ def test_arena_overflow_fails_loudly(monkeypatch):
     t = make_engine((2, 3, 200, 16, 1.0, 0.25, False))
     with pytest.raises(cb.Corintho200Error):
         run_trainer(t, synth_eval)
+
+
+def test_raw_samples_device_rows_match_host_rows():
+    import torch
+    from corintho_ai_b200.dist import device_rows_as_tensor, pack_raw_samples
+    t = make_engine((6, 3, 24, 8, 1.0, 0.25, False))
+    run_trainer(t, synth_eval)
+    st, pr, lb, go = t.raw_samples()
+    ptr, n = t.raw_samples_device()
+    rows = device_rows_as_tensor(ptr, n, 102, torch.device("cuda", 0)).cpu().numpy()
+    assert n == st.shape[0]
+    assert rows.tobytes() == pack_raw_samples(st, pr, lb, go, first_game=0).tobytes()
