@@ -92,7 +92,6 @@ struct cb200_trainer {
   float *d_eval = nullptr, *d_probs = nullptr, *d_rows = nullptr;
   ulonglong2 *d_packed = nullptr;
   int32_t *d_offs = nullptr, *d_summary = nullptr, *d_soff = nullptr;
-  float *d_vsqrt = nullptr;
   float *d_samp = nullptr;  // cached output buffer of write_samples
   size_t samp_rows = 0;
   float *d_raw = nullptr;   // cached [rows][102] buffer of raw_samples_device
@@ -156,12 +155,7 @@ int upload_tables_once() {
   if (dev < 16 && sym_ready[dev]) return CB200_OK;
   CB_CUDA(cudaMemcpyToSymbol(d_space_sym, kCSpaceSym, sizeof(kCSpaceSym)));
   CB_CUDA(cudaMemcpyToSymbol(d_move_sym, kCMoveSym, sizeof(kCMoveSym)));
-  {
-    static double rcp[kTabSize + 1];
-    rcp[0] = 0.0;
-    for (int i = 1; i <= kTabSize; ++i) rcp[i] = 1.0 / (double)i;
-    CB_CUDA(cudaMemcpyToSymbol(d_rcp_tab, rcp, sizeof(rcp)));
-  }
+
   if (dev < 16) sym_ready[dev] = true;
   return CB200_OK;
 }
@@ -438,7 +432,6 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
             dmalloc(&t->d_rows, t->cap * CB200_STATE_SIZE) == CB200_OK &&
             dmalloc(&t->d_packed, t->cap) == CB200_OK && dmalloc(&t->d_offs, Gn) == CB200_OK &&
             dmalloc(&t->d_soff, Gn) == CB200_OK && dmalloc(&t->d_summary, 4) == CB200_OK &&
-            dmalloc(&t->d_vsqrt, kTabSize) == CB200_OK &&
             cudaMallocHost((void **)&t->h_summary, 4 * sizeof(int32_t)) == cudaSuccess;
   if (!ok) {
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
@@ -473,18 +466,6 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
     cb200_trainer_destroy(t);
     return nullptr;
-  }
-  {
-    // v_sqrt = c_puct * sqrt(float(visits)) exactly as the reference evaluates it
-    // (trainmc.cpp:549: float * double sqrt(double) -> float), tabulated on the host
-    std::vector<float> tab(kTabSize);
-    for (int v = 0; v < kTabSize; ++v) tab[v] = (float)((double)c_puct * sqrt((double)(float)v));
-    if (cudaMemcpy(t->d_vsqrt, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_error(CB200_ERR_CUDA, "vsqrt table upload failed");
-      cb200_trainer_destroy(t);
-      return nullptr;
-    }
-    P.vsqrt_tab = t->d_vsqrt;
   }
   P.game_begin = 0, P.game_end = num_games, P.group_row0 = 0, P.group_ctr = nullptr;
   P.packed = t->d_packed;
@@ -559,7 +540,6 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);
   cudaFree(t->d_eval), cudaFree(t->d_probs), cudaFree(t->d_rows), cudaFree(t->d_packed);
   cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
-  cudaFree(t->d_vsqrt);
   cudaFree(t->d_samp);
   cudaFree(t->d_raw);
   if (t->h_summary) cudaFreeHost(t->h_summary);

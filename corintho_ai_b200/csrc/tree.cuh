@@ -15,7 +15,10 @@
 //                 child_n_legal<<21 | child_has_children<<28}
 // A node's statistics live in its parent's slot, so PUCT selection at a node is ONE coalesced
 // read of header+slots (lane e loads slot e as a uint4) and virtual loss is a plain store.
-// The root record is at word 0; root statistics are in the per-tree control block.
+// The root record is at word root_off (re-rooting is in place; the kept subtree is compacted
+// into the spare arena only when room runs out); root statistics are in the per-tree control
+// block. The per-game context (Ctx) lives in registers: every device function below is
+// force-inlined into k_iterate, which has a single TrainMC::doIteration call site.
 // Float expression types follow the reference literally (double intermediates, no FMA
 // contraction): explicit __f*_rn / __d*_rn intrinsics are used for every rounded operation.
 #ifndef CORINTHO_B200_TREE_CUH
@@ -24,6 +27,17 @@
 #include "common.cuh"
 
 namespace cb200 {
+
+// Straggler instrumentation (tools/prof_timeline.py): build with -DCB200_PHASE_PROF=1 to record
+// per-phase cycles; off by default so that the hot loops carry no clock reads.
+#ifndef CB200_PHASE_PROF
+#define CB200_PHASE_PROF 0
+#endif
+#if CB200_PHASE_PROF
+#define CB_CLOCK() clock64()
+#else
+#define CB_CLOCK() 0ll
+#endif
 
 constexpr int kMaxPath = 64;
 constexpr int kPendWords = 2 + kMaxPath;  // leaf_off, path_len, path[kMaxPath]
@@ -34,10 +48,6 @@ constexpr int kTreeWarps = 4;  // games per CTA
 // 3 -> ~156 regs (no spills, shortest serial chain; best once few games are live).
 constexpr int kCtlWords = 16;
 constexpr int kTreeCtlWords = 12;
-constexpr int kTabSize = 4096;  // visit counts served by the sqrt / reciprocal tables
-
-// RN(1.0 / i) as doubles, i in [0, kTabSize]; uploaded by ensure_tree_tables()
-__device__ double d_rcp_tab[kTabSize + 1];
 
 enum CtlWord {
   CW_TO_PLAY = 0, CW_PARITY, CW_RESULT, CW_MATE_TURN, CW_N_SAMPLES, CW_N_PENDING, CW_ERROR,
@@ -63,7 +73,6 @@ struct TreeParams {
   ulonglong2 *sample_state;  // [G][kMaxSamples]
   float *sample_probs;       // [G][kMaxSamples][96]
   long long *counters;       // [G][4] simulations, moves, leaf evals, (unused)
-  const float *vsqrt_tab;    // [kTabSize] (float)(c_puct * sqrt((double)(float)v)), host-computed
   // fused (device-resident) mode: the kernel instance covers games [game_begin, game_end) of one
   // stream group; request rows are handed out with one atomicAdd per game
   int game_begin, game_end;
@@ -219,29 +228,6 @@ __device__ __noinline__ void mt_twist_state(uint32_t *mt, int lane) {
 __device__ __forceinline__ void mt_twist(Ctx &c) {
   mt_twist_state(c.mt, c.lane);
   c.mt_idx = 0;
-}
-// n (<=96) consecutive outputs; output e = lane + 32 j lands in out[j] of that lane
-__device__ __forceinline__ void rng_block(Ctx &c, int n, uint32_t out[3]) {
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    out[j] = 0;
-    const int e0 = 32 * j;
-    if (e0 < n) {
-      const int cnt = min(32, n - e0);
-      const int avail = 624 - c.mt_idx;
-      uint32_t y = 0;
-      if (cnt <= avail) {
-        if (c.lane < cnt) y = c.mt[c.mt_idx + c.lane];
-        c.mt_idx += cnt;
-      } else {
-        if (c.lane < avail) y = c.mt[c.mt_idx + c.lane];
-        mt_twist(c);
-        if (c.lane >= avail && c.lane < cnt) y = c.mt[c.lane - avail];
-        c.mt_idx = cnt - avail;
-      }
-      out[j] = mt_temper(y);
-    }
-  }
 }
 __device__ __forceinline__ uint32_t rng_one(Ctx &c) {
   if (c.mt_idx >= 624) mt_twist(c);
@@ -617,7 +603,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
   if (c.lane == 0) sm.node[0] = c.root_off;
   CState leaf_state{0, 0};
   while (!r_terminal(cur_result)) {
-    const long long tl0 = clock64();
+    const long long tl0 = CB_CLOCK();
     c.n_lvl += 1;
     const uint32_t *r = c.base + node;
     const uint4 h0 = ld4(r);
@@ -710,9 +696,9 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     const int owner = emin & 31;
     const uint32_t so = node + 8u + 4u * (uint32_t)emin;
     const uint32_t ch_w3 = __shfl_sync(kFull, best_s.w, owner);
-    c.t_sel += clock64() - tl0;
+    c.t_sel += CB_CLOCK() - tl0;
     if (!s3_has(ch_w3)) {  // kNew: expand (trainmc.cpp:645-660)
-      const long long te0 = clock64();
+      const long long te0 = CB_CLOCK();
       c.n_exp += 1;
       if (level + 1 >= kMaxPath) {
         c.error = CB200_ERR_OVERFLOW;
@@ -739,7 +725,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
       node = coff;
       cur_result = result;
       __syncwarp();
-      c.t_exp += clock64() - te0;
+      c.t_exp += CB_CLOCK() - te0;
       break;
     }
     // existing child: descend
@@ -832,15 +818,15 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
     request_root(c);
     return false;
   }
-  long long t0 = clock64();
+  long long t0 = CB_CLOCK();
   if (c.n_pending > 0) receive_eval(c, P, sm, eval, probs, prs, pcs);
-  long long t1 = clock64();
+  long long t1 = CB_CLOCK();
   c.t_ingest += t1 - t0;
   while (c.n_pending < P.spe && c.searches_done < P.max_searches && !r_known(c.root_result) &&
          !c.root_allv && !c.error) {
     search(c, P, sm);
   }
-  c.t_search += clock64() - t1;
+  c.t_search += CB_CLOCK() - t1;
   return (c.searches_done == P.max_searches || r_known(c.root_result)) && c.n_pending == 0;
 }
 
@@ -1117,9 +1103,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
   for (;;) {
     const bool turn_done = tree_do_iteration(c, P, sm, ev_p, pr_p, prs, pcs);
     if (c.error || !turn_done) break;
-    const long long tm = clock64();
+    const long long tm = CB_CLOCK();
     const int r = choose_move_and_continue(c, P, sm, kFused);
-    c.t_move += clock64() - tm;
+    c.t_move += CB_CLOCK() - tm;
     if (r == kTurnOver) {
       done = true;
       break;
