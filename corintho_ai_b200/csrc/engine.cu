@@ -810,10 +810,12 @@ int cb200_trainer_set_weights(cb200_trainer *t, int model, const float *weights,
   int rc = guard(t);
   if (rc) return rc;
   if (model < 0 || model > 1 || !weights || n_floats != kNetWeightFloats ||
-      (precision != 0 && precision != 1))
-    return set_error(CB200_ERR_ARG, "cb200_trainer_set_weights: bad arguments (127997 floats, precision 0|1)");
-  rc = precision == 0 ? net_f32_upload(t->net32[model], weights) : net_tc_upload(t->nettc[model], weights);
-  if (rc == CB200_OK) t->precision[model] = precision;
+      (precision < 0 || precision > 2))
+    return set_error(CB200_ERR_ARG, "cb200_trainer_set_weights: bad arguments (127997 floats, precision 0|1|2)");
+  rc = precision == 0 ? net_f32_upload(t->net32[model], weights)
+                      : net_tc_upload(t->nettc[model], weights, precision == 2);
+  // precisions 1 (bf16) and 2 (fp16) share the tensor-core kernel and the move-major output
+  if (rc == CB200_OK) t->precision[model] = precision == 0 ? 0 : 1;
   return rc;
 }
 

@@ -25,6 +25,7 @@
 #define CORINTHO_B200_MLP_TC_CUH
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -46,10 +47,14 @@ constexpr size_t kTcSmemBytes = 2 * kTcABytes + 2 * kTcLayerBytes + 64;
 // A=B=BF16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
                               ((uint32_t)(128 >> 4) << 24);
+// same with A = B = F16 (format code 0): 8x finer mantissa than bf16, range +-65504 -- needed for
+// trained checkpoints whose folded BatchNorm scales make the network sensitive to operand rounding
+constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct NetTC {
   void *w = nullptr;  // device: kTcLayers images of kTcLayerBytes
   bool ready = false;
+  bool fp16 = false;  // operand format of the images: false = bf16, true = fp16
 };
 
 // ---- raw PTX helpers -------------------------------------------------------------------------
@@ -149,17 +154,27 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t v[16])
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// two fp32 -> packed bf16x2 with ReLU, `lo` in bits 0-15
-__device__ __forceinline__ uint32_t relu_pack_bf16(uint32_t lo, uint32_t hi) {
+// two fp32 -> packed 16-bit pair (bf16 or fp16) with ReLU, `lo` in bits 0-15
+template <bool kFp16>
+__device__ __forceinline__ uint32_t relu_pack16(uint32_t lo, uint32_t hi) {
   uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  if (kFp16)
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
   return d;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+template <bool kFp16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if (kFp16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+  }
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+template <bool kFp16>
 __global__ void __launch_bounds__(kTcThreads, 2)
     k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
              const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           const float a = j < CB200_STATE_SIZE ? encode_elem(st, j) : (j == kTcOnes ? 1.0f : 0.0f);
           const float b = j + 1 < CB200_STATE_SIZE ? encode_elem(st, j + 1)
                                                    : (j + 1 == kTcOnes + 1 ? 1.0f : 0.0f);
-          q[h] = pack_bf16(a, b);
+          q[h] = pack16<kFp16>(a, b);
         }
         *reinterpret_cast<uint4 *>(myA + c * kTcAChunkBytes + row * 16) =
             make_uint4(q[0], q[1], q[2], q[3]);
@@ -246,7 +261,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         for (int kk = 0; kk < kTcChunks / 2; ++kk) {
           const uint64_t ad = umma_desc(aaddr + kk * 2 * kTcAChunkBytes, kTcAChunkBytes, 128);
           const uint64_t bd = umma_desc(waddr + kk * 2 * kTcWChunkBytes, kTcWChunkBytes, 128);
-          umma_bf16(tmem_tile, ad, bd, kTcIdesc, kk > 0 ? 1u : 0u);
+          umma_bf16(tmem_tile, ad, bd, kFp16 ? kTcIdescF16 : kTcIdesc, kk > 0 ? 1u : 0u);
         }
         umma_commit(mbar0 + 8 * wg);
       }
@@ -265,8 +280,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           for (int c8 = 0; c8 < 8; ++c8) {
             const uint32_t *x = v + 8 * c8;
             *reinterpret_cast<uint4 *>(myA + c8 * kTcAChunkBytes + row * 16) =
-                make_uint4(relu_pack_bf16(x[0], x[1]), relu_pack_bf16(x[2], x[3]),
-                           relu_pack_bf16(x[4], x[5]), relu_pack_bf16(x[6], x[7]));
+                make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
+                           relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
           }
         }
         {
@@ -278,8 +293,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           for (int c8 = 0; c8 < 6; ++c8) {
             const uint32_t *x = v + 8 * c8;
             *reinterpret_cast<uint4 *>(myA + (8 + c8) * kTcAChunkBytes + row * 16) =
-                make_uint4(relu_pack_bf16(x[0], x[1]), relu_pack_bf16(x[2], x[3]),
-                           relu_pack_bf16(x[4], x[5]), relu_pack_bf16(x[6], x[7]));
+                make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
+                           relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
           }
         }
       } else {
@@ -348,7 +363,8 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 }
 
 // Re-layout the C-ABI weight vector into per-layer UMMA images (bf16, zero padded) and upload.
-inline int net_tc_upload(NetTC &net, const float *weights) {
+inline int net_tc_upload(NetTC &net, const float *weights, bool fp16 = false) {
+  net.fp16 = fp16;
   std::vector<uint8_t> host((size_t)kTcLayers * kTcLayerBytes, 0);
   const float *src = weights;
   for (int l = 0; l < kTcLayers; ++l) {
@@ -357,18 +373,30 @@ inline int net_tc_upload(NetTC &net, const float *weights) {
     uint8_t *img = host.data() + (size_t)l * kTcLayerBytes;
     for (int k = 0; k < K; ++k)
       for (int o = 0; o < N; ++o) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(src[(size_t)k * N + o]);
         // B operand is [N][K] K-major: chunk k/8, row o, element k%8
-        memcpy(img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2, &h, 2);
+        uint8_t *dst = img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2;
+        if (fp16) {
+          const __half h = __float2half_rn(src[(size_t)k * N + o]);
+          memcpy(dst, &h, 2);
+        } else {
+          const __nv_bfloat16 h = __float2bfloat16_rn(src[(size_t)k * N + o]);
+          memcpy(dst, &h, 2);
+        }
       }
     src += (size_t)K * N;
     auto put = [&](int k, int o, float v) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      memcpy(img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2, &h, 2);
+      uint8_t *dst = img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2;
+      if (fp16) {
+        const __half h = __float2half_rn(v);
+        memcpy(dst, &h, 2);
+      } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        memcpy(dst, &h, 2);
+      }
     };
     for (int o = 0; o < N; ++o) {  // bias = hi + lo, multiplied by the two ones columns
       const float b = src[o];
-      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      const float hi = fp16 ? __half2float(__float2half_rn(b)) : __bfloat162float(__float2bfloat16_rn(b));
       put(kTcOnes, o, hi);
       put(kTcOnes + 1, o, b - hi);
     }
@@ -398,15 +426,21 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 16 && !attr_set[dev]) {
-    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kTcSmemBytes));
+    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTcSmemBytes));
     attr_set[dev] = true;
   }
   if (n_max <= 0) return CB200_OK;
   const int pairs = (n_max + 255) / 256;
   const int grid = pairs < 2 * sms ? pairs : 2 * sms;
-  k_mlp_tc<<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : G().stream>>>(
-      (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
+  if (net.fp16)
+    k_mlp_tc<true><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+        (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
+  else
+    k_mlp_tc<false><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+        (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;

@@ -140,7 +140,9 @@ int cb200_trainer_game_results(cb200_trainer *t, int32_t *results /* [num_games]
  *   weights = W1[70][100], b1[100], (W_l[100][100], b_l[100]) l=2..12, Wh[100][97], bh[97]
  * row-major [in][out] like Keras Dense kernels; head column 0 = value (tanh), 1..96 = policy
  * logits (softmax). n_floats must be 127997. precision: 0 = fp32 SIMT kernel (parity mode,
- * 1e-5), 1 = bf16 tcgen05 tensor-core kernel with fp32 accumulation (2e-2). */
+ * 1e-5), 1 = bf16 tcgen05 tensor-core kernel with fp32 accumulation (2e-2 on random-init
+ * networks), 2 = the same kernel with fp16 operands (for trained checkpoints, whose folded
+ * BatchNorm scales make bf16 operand rounding too coarse; activations must stay below 65504). */
 int cb200_trainer_set_weights(cb200_trainer *t, int model, const float *weights, size_t n_floats,
                               int precision);
 /* Evaluate positions with the resident network (the engine's replacement for the Keras
