@@ -23,7 +23,8 @@ NUM_SYMMETRIES = 8  # util.h:47
 WEIGHT_FLOATS = 127997
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcorintho_b200.so")
+# CB200_LIB selects another build of the same library (the instrumented `make prof` variant)
+LIB_PATH = os.environ.get("CB200_LIB") or os.path.join(_HERE, "libcorintho_b200.so")
 
 
 class Corintho200Error(RuntimeError):

@@ -93,8 +93,8 @@ struct WarpSm {
   float fval[kFlatCap];
   float dval[kFlatCap];
   uint8_t mv[kFlatCap];
+  uint8_t own[kFlatCap];  // leaf (lane) owning each flat element
   uint32_t l_off[32];
-  int l_n[32];
   int l_pre[33];
   float l_a[32];
   float l_b[32];
@@ -301,8 +301,8 @@ __device__ __forceinline__ void fresh_tree(Ctx &c, const TreeParams &P, const CS
 __device__ __forceinline__ void request_root(Ctx &c) {
   if (c.lane == 0) {
     uint32_t *pd = c.pending + c.n_pending * kPendWords;
-    pd[0] = c.root_off, pd[1] = 0;
     const uint4 h = ld4(c.base + c.root_off);
+    pd[0] = c.root_off, pd[1] = (c.base[c.root_off + 4] & 0xffu) << 8;  // path length 0 | n_legal << 8
     c.leaf_state[c.n_pending] = make_ulonglong2((uint64_t)h.x | ((uint64_t)h.y << 32),
                                                 (uint64_t)h.z | ((uint64_t)h.w << 32));
   }
@@ -393,21 +393,13 @@ __device__ __forceinline__ void move_down(Ctx &c, const TreeParams &P, int e) {
 // ---- TrainMC::receiveEval (trainmc.cpp:269-296) ---------------------------------------------
 // probs element (answer row k, move m) = probs[k * prs + m * pcs]: row-major [n][96] from the
 // host API (prs 96, pcs 1), move-major [96][ld] from the tensor-core network (prs 1, pcs ld)
-// largest k in [k0, k1) with pre[k] <= i
-__device__ __forceinline__ int find_leaf(const int *pre, int k0, int k1, int i) {
-  int lo = k0, hi = k1 - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (pre[mid] <= i) lo = mid; else hi = mid - 1;
-  }
-  return lo;
-}
 
 // ---- TrainMC::receiveEval (trainmc.cpp:269-296), latency-oriented restatement ----------------
 // Same arithmetic, in the same order per leaf, as the reference loop, but organised so that the
 // loads of all pending leaves (processed 32 at a time) are in flight together:
 //   "flat" phases  : one lane per legal-move slot over the concatenation of all leaves
-//                    (the MT19937 draw of flat element i is simply draw number i);
+//                    (the MT19937 draw of flat element i is simply draw number i); the leaf an
+//                    element belongs to comes from a byte array filled once per chunk;
 //   "leaf" phases  : one lane per leaf for the order-dependent float sums / max / integer sum;
 //   backup         : per tree level, the lanes whose paths meet in the same slot are grouped with
 //                    __match_any_sync and the lowest lane applies the adds in leaf order.
@@ -420,22 +412,26 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
   const int np = min(32, np_all - b0);
   const float *eval_b = eval + b0;
   const float *probs_b = probs + (long)b0 * prs;
-  // ---- leaf phase 0: pending records and leaf headers
+  // ---- leaf phase 0: pending records (leaf offset, path length | n_legal << 8)
   uint32_t my_off = 0;
   int my_n = 0, my_plen = 0;
   float my_ev = 0.0f;
   const uint32_t *my_pd = c.pending + (b0 + lane) * kPendWords;
   if (lane < np) {
-    my_off = my_pd[0];
-    my_plen = (int)my_pd[1];
+    const uint2 h = *reinterpret_cast<const uint2 *>(my_pd);
+    my_off = h.x;
+    my_plen = (int)(h.y & 0xffu);
+    my_n = (int)(h.y >> 8);
     my_ev = eval_b[lane];
-    my_n = (int)(c.base[my_off + 4] & 0xffu);
   }
+  // path slots of the first four levels: in flight while the priors are processed
+  uint32_t path4[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) path4[u] = (lane < np && my_plen > u) ? my_pd[2 + u] : 0u;
   const int incl = (int)warp_incl_scan((uint32_t)my_n, lane);
   sm.l_pre[lane] = incl - my_n;
   if (lane == 31) sm.l_pre[32] = incl;
   sm.l_off[lane] = my_off;
-  sm.l_n[lane] = my_n;
   __syncwarp();
   for (int k0 = 0; k0 < np;) {
     // chunk [k0, k1): as many leaves as fit in the scratch arrays
@@ -449,28 +445,44 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
     }
     const bool mine = lane >= k0 && lane < k1;
     const int my_i0 = sm.l_pre[lane] - base_i;
-    int nmax = mine ? my_n : 0;
-    nmax = __reduce_max_sync(kFull, nmax);
+    const int my_cnt = mine ? my_n : 0;
+    const int nmax = __reduce_max_sync(kFull, my_cnt);
+    for (int j = 0; j < nmax; ++j)
+      if (j < my_cnt) sm.own[my_i0 + j] = (uint8_t)lane;
+    __syncwarp();
     // ---- flat phase 1: move ids and network priors of every legal move (getFilteredProbs).
-    // Four elements per lane per trip, loads grouped so that they overlap.
+    // Four elements per lane per trip; the slot words of the next trip are requested before the
+    // priors of this one are consumed.
+    uint32_t w3n[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = lane + 32 * u;
+      w3n[u] = 0;
+      if (i < T) {
+        const int k = sm.own[i];
+        w3n[u] = c.base[sm.l_off[k] + 8 + 4 * (i + base_i - sm.l_pre[k]) + 3];
+      }
+    }
     for (int i0 = 0; i0 < T; i0 += 128) {
-      int kk[4];
       uint32_t w3[4];
       float pv4[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + lane + 32 * u;
-        kk[u] = 0, w3[u] = 0;
-        if (i < T) {
-          kk[u] = find_leaf(sm.l_pre, k0, k1, i + base_i);
-          w3[u] = c.base[sm.l_off[kk[u]] + 8 + 4 * (i + base_i - sm.l_pre[kk[u]]) + 3];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + lane + 32 * u;
+        w3[u] = w3n[u];
         pv4[u] = 0.0f;
-        if (i < T) pv4[u] = probs_b[(long)kk[u] * prs + (long)s3_move(w3[u]) * pcs];
+        if (i < T) pv4[u] = probs_b[(long)sm.own[i] * prs + (long)s3_move(w3[u]) * pcs];
+      }
+      if (i0 + 128 < T) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + 128 + lane + 32 * u;
+          w3n[u] = 0;
+          if (i < T) {
+            const int k = sm.own[i];
+            w3n[u] = c.base[sm.l_off[k] + 8 + 4 * (i + base_i - sm.l_pre[k]) + 3];
+          }
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -478,17 +490,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
         if (i < T) sm.mv[i] = (uint8_t)s3_move(w3[u]), sm.fval[i] = pv4[u];
       }
     }
-    __syncwarp();
-    // ---- leaf phase 2: float sum in edge order, scalar = 1/sum * (1 - eps)
-    {
-      float sum = 0.0f;
-      for (int j = 0; j < nmax; ++j)
-        if (mine && j < my_n) sum = __fadd_rn(sum, sm.fval[my_i0 + j]);
-      if (mine)
-        sm.l_a[lane] = __double2float_rn(
-            __dmul_rn(__drcp_rn((double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
-    }
-    // ---- flat phase 3: one MT19937 draw per slot, in order (generateDirichlet)
+    // ---- flat phase 2: one MT19937 draw per slot, in order (generateDirichlet)
     for (int done = 0; done < T;) {
       if (c.mt_idx >= 624) mt_twist(c);
       const int seg = min(624 - c.mt_idx, T - done);
@@ -510,36 +512,45 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
       }
       c.mt_idx += seg;
       done += seg;
-      __syncwarp();
-    }
-    // ---- leaf phase 4: noise sum, dscalar = 1/sum * eps
-    {
-      float dsum = 0.0f;
-      for (int j = 0; j < nmax; ++j)
-        if (mine && j < my_n) dsum = __fadd_rn(dsum, sm.dval[my_i0 + j]);
-      if (mine)
-        sm.l_b[lane] =
-            __double2float_rn(__dmul_rn(__drcp_rn((double)dsum), (double)P.epsilon));
     }
     __syncwarp();
-    // ---- flat phase 5: weighted = filtered*scalar + dirichlet*dscalar (setProbs)
+    // ---- leaf phase 3: both float sums in edge order;
+    // scalar = 1/sum * (1 - eps), dscalar = 1/noise sum * eps
+    {
+      float sum = 0.0f, dsum = 0.0f;
+      for (int j = 0; j < nmax; ++j)
+        if (j < my_cnt) {
+          sum = __fadd_rn(sum, sm.fval[my_i0 + j]);
+          dsum = __fadd_rn(dsum, sm.dval[my_i0 + j]);
+        }
+      if (mine) {
+        sm.l_a[lane] = __double2float_rn(
+            __dmul_rn(__drcp_rn((double)sum), (double)__fsub_rn(1.0f, P.epsilon)));
+        sm.l_b[lane] =
+            __double2float_rn(__dmul_rn(__drcp_rn((double)dsum), (double)P.epsilon));
+      }
+    }
+    __syncwarp();
+    // ---- flat phase 4: weighted = filtered*scalar + dirichlet*dscalar (setProbs)
+#pragma unroll 2
     for (int i = lane; i < T; i += 32) {
-      const int k = find_leaf(sm.l_pre, k0, k1, i + base_i);
+      const int k = sm.own[i];
       sm.fval[i] = __fadd_rn(__fmul_rn(sm.fval[i], sm.l_a[k]), __fmul_rn(sm.dval[i], sm.l_b[k]));
     }
     __syncwarp();
-    // ---- leaf phase 6: max (from 0.0f), denom = 511 / max
+    // ---- leaf phase 5: max (from 0.0f), denom = 511 / max
     {
       float mx = 0.0f;
       for (int j = 0; j < nmax; ++j)
-        if (mine && j < my_n) mx = fmaxf(mx, sm.fval[my_i0 + j]);
+        if (j < my_cnt) mx = fmaxf(mx, sm.fval[my_i0 + j]);
       if (mine) sm.l_a[lane] = __fdiv_rn(511.0f, mx);
     }
     __syncwarp();
-    // ---- flat phase 7: 9-bit integer priors. A leaf is evaluated before it can get children,
+    // ---- flat phase 6: 9-bit integer priors. A leaf is evaluated before it can get children,
     // so its slot words are still {0, 0, 0, move}: the new word is move | prior << 7.
+#pragma unroll 2
     for (int i = lane; i < T; i += 32) {
-      const int k = find_leaf(sm.l_pre, k0, k1, i + base_i);
+      const int k = sm.own[i];
       const int j = i + base_i - sm.l_pre[k];
       const double x = (double)__fmul_rn(sm.fval[i], sm.l_a[k]);
       const long long q = (long long)floor(x + 0.5);  // lround for x >= 0
@@ -548,11 +559,11 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
       sm.dval[i] = __int_as_float(prob);
     }
     __syncwarp();
-    // ---- leaf phase 8: denominator = 1 / float(sum of integer priors)
+    // ---- leaf phase 7: denominator = 1 / float(sum of integer priors)
     {
       int qsum = 0;
       for (int j = 0; j < nmax; ++j)
-        if (mine && j < my_n) qsum += __float_as_int(sm.dval[my_i0 + j]);
+        if (j < my_cnt) qsum += __float_as_int(sm.dval[my_i0 + j]);
       if (mine) c.base[my_off + 5] = __float_as_uint(__double2float_rn(__drcp_rn((double)(float)qsum)));
     }
     __syncwarp();
@@ -560,35 +571,101 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
   }
   // ---- backup (trainmc.cpp:281-292). Level L slot of leaf k = path[L-1]; the leaf itself
   // (L == plen) takes e-1, its parent -e-1, ... Adds to one slot are applied in leaf order.
+  // Four levels per trip so that their slot reads overlap.
   const int maxlen = __reduce_max_sync(kFull, my_plen);
-  for (int L = 1; L <= maxlen; ++L) {
-    const bool act = lane < np && my_plen >= L;
-    const uint32_t addr = act ? my_pd[2 + L - 1] : 0xFFFFFF00u + (uint32_t)lane;
-    const unsigned grp = __match_any_sync(kFull, addr);
-    const bool owner = act && (__ffs((int)grp) - 1 == lane);
-    const float ce = ((my_plen - L) & 1) ? -my_ev : my_ev;
-    const float d = __double2float_rn(__dsub_rn((double)ce, 1.0));
-    uint32_t *sp = c.base + (act ? addr : 0u);
-    float v = 0.0f;
-    uint32_t w3 = 0;
-    if (owner) v = __uint_as_float(sp[0]), w3 = sp[3];
-    for (int m = 0; m < np; ++m) {
-      const float dm = __shfl_sync(kFull, d, m);
-      if (owner && ((grp >> m) & 1u)) v = __fadd_rn(v, dm);
+  const float d_even = __double2float_rn(__dsub_rn((double)my_ev, 1.0));
+  const float d_odd = __double2float_rn(__dsub_rn((double)-my_ev, 1.0));
+  for (int L0 = 1; L0 <= maxlen; L0 += 4) {
+    uint32_t addr[4];
+    bool owner[4];
+    unsigned grp[4];
+    float v[4];
+    uint32_t w3[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int L = L0 + u;
+      const bool act = lane < np && my_plen >= L;
+      uint32_t a = 0xFFFFFF00u + (uint32_t)lane;
+      if (act) a = L0 == 1 ? path4[u] : my_pd[2 + L - 1];
+      addr[u] = a;
     }
-    if (owner) sp[0] = __float_as_uint(v), sp[3] = w3 & ~kS3Allv;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      owner[u] = false, grp[u] = 0, v[u] = 0.0f, w3[u] = 0;
+      if (L0 + u <= maxlen) {
+        const bool act = lane < np && my_plen >= L0 + u;
+        grp[u] = __match_any_sync(kFull, addr[u]);
+        owner[u] = act && (__ffs((int)grp[u]) - 1 == lane);
+        if (owner[u]) {
+          const uint32_t *sp = c.base + addr[u];
+          v[u] = __uint_as_float(sp[0]), w3[u] = sp[3];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (L0 + u <= maxlen) {
+        const float d = ((my_plen - (L0 + u)) & 1) ? d_odd : d_even;
+        for (int m = 0; m < np; ++m) {
+          const float dm = __shfl_sync(kFull, d, m);
+          if (owner[u] && ((grp[u] >> m) & 1u)) v[u] = __fadd_rn(v[u], dm);
+        }
+        if (owner[u]) {
+          uint32_t *sp = c.base + addr[u];
+          sp[0] = __float_as_uint(v[u]), sp[3] = w3[u] & ~kS3Allv;
+        }
+      }
+    }
   }
   for (int m = 0; m < np; ++m) {
-    const float e = __shfl_sync(kFull, my_ev, m);
+    const float de = __shfl_sync(kFull, d_even, m);
+    const float dd = __shfl_sync(kFull, d_odd, m);
     const int pl = __shfl_sync(kFull, my_plen, m);
-    const float ce = (pl & 1) ? -e : e;
-    c.root_eval = __fadd_rn(c.root_eval, __double2float_rn(__dsub_rn((double)ce, 1.0)));
+    c.root_eval = __fadd_rn(c.root_eval, (pl & 1) ? dd : de);
   }
   __syncwarp();
   }  // batch of <= 32 leaves
   c.root_allv = 0;
   c.d_evals += np_all;
   c.n_pending = 0;
+}
+
+// PUCT value of one slot (chooseNext, trainmc.cpp:540-600); -inf = not selectable
+__device__ __forceinline__ float puct_u(const uint4 s, float denominator, float v_sqrt) {
+  const float prob = __fmul_rn((float)s3_prior(s.w), denominator);
+  const float pvf = __fmul_rn(prob, v_sqrt);
+  float u = pvf;  // no child yet, or a drawn child
+  if (s3_has(s.w)) {
+    const int cr = s3_result(s.w);
+    if ((r_known(cr) && !r_drawn(cr)) || s3_allv(s.w)) {
+      u = -INFINITY;
+    } else if (!r_drawn(cr)) {
+      // reference: u = float(-E/N + (P*v)/(N+1)) with both quotients and the sum rounded in
+      // double. Fast path: multiply by approximate reciprocals (20-bit hardware seed + 2 Newton
+      // steps, relative error < 2^-50, so each product is within 2^-49 of the true quotient) and
+      // accept the result only if every double within 2^-46*(|a|+|b|) rounds to the same float;
+      // otherwise do it exactly.
+      const int cvi = (int)s.y;
+      const double ne = -(double)__uint_as_float(s.x);
+      const double pv = (double)pvf;
+      const double dn = (double)cvi, dn1 = (double)(cvi + 1);
+      const double ra = fast_rcp(dn), rb = fast_rcp(dn1);
+      const double a = __dmul_rn(ne, ra);
+      const double b = __dmul_rn(pv, rb);
+      const double sf = __dadd_rn(a, b);
+      const double tol = __dmul_rn(__dadd_rn(fabs(a), fabs(b)), 0x1p-46);
+      const float ulo = __double2float_rn(__dsub_rn(sf, tol));
+      const float uhi = __double2float_rn(__dadd_rn(sf, tol));
+      u = ulo;
+      if (!(ulo == uhi)) {
+        const double cv = (double)(float)cvi;
+        const double a = __ddiv_rn(ne, cv);
+        const double b = __ddiv_rn(pv, __dadd_rn(cv, 1.0));
+        u = __double2float_rn(__dadd_rn(a, b));
+      }
+    }
+  }
+  return __fadd_rn(u, 0.0f);  // -0.0 -> +0.0 so the integer key orders like operator>
 }
 
 // ---- TrainMC::search (trainmc.cpp:602-696) --------------------------------------------------
@@ -602,62 +679,36 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
   uint32_t cur_w3 = 0;
   if (c.lane == 0) sm.node[0] = c.root_off;
   CState leaf_state{0, 0};
+  int leaf_n = 0;
+  // number of legal moves of the node we stand on: known from the parent's slot below the
+  // root, so the slot loads do not wait for the header load (one memory round trip per level)
+  int cur_n = (int)(c.base[node + 4] & 0xffu);
   while (!r_terminal(cur_result)) {
     const long long tl0 = CB_CLOCK();
     c.n_lvl += 1;
     const uint32_t *r = c.base + node;
-    const uint4 h0 = ld4(r);
+    const int n = cur_n;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    const uint4 sa = c.lane < n ? ld4(r + 8 + 4 * c.lane) : zero4;
+    const uint4 sb = c.lane + 32 < n ? ld4(r + 8 + 4 * (c.lane + 32)) : zero4;
     const uint4 h1 = ld4(r + 4);
-    const int n = (int)(h1.x & 0xffu);
     const int depth = (int)((h1.x >> 8) & 0xffu);
     const float denominator = __uint_as_float(h1.y);
-    // chooseNext (trainmc.cpp:540-600). sqrt(float) binds to double sqrt(double).
+    // sqrt(float) binds to double sqrt(double)
     const float v_sqrt =
         __double2float_rn(__dmul_rn((double)P.c_puct, sqrt((double)(float)cur_visits)));
     float best_u = -INFINITY;
     int best_e = 0x7fffffff;
-    uint4 best_s = make_uint4(0, 0, 0, 0);
-    for (int e = c.lane; e < n; e += 32) {
+    uint4 best_s = zero4;
+    {
+      const float ua = c.lane < n ? puct_u(sa, denominator, v_sqrt) : -INFINITY;
+      const float ub = c.lane + 32 < n ? puct_u(sb, denominator, v_sqrt) : -INFINITY;
+      if (ua > best_u) best_u = ua, best_e = c.lane, best_s = sa;
+      if (ub > best_u) best_u = ub, best_e = c.lane + 32, best_s = sb;
+    }
+    for (int e = c.lane + 64; e < n; e += 32) {
       const uint4 s = ld4(r + 8 + 4 * e);
-      const float prob = __fmul_rn((float)s3_prior(s.w), denominator);
-      float u = -INFINITY;
-      if (s3_has(s.w)) {
-        const int cr = s3_result(s.w);
-        if ((!r_known(cr) || r_drawn(cr)) && !s3_allv(s.w)) {
-          if (r_drawn(cr)) {
-            u = __fmul_rn(prob, v_sqrt);
-          } else {
-            // reference: u = float(-E/N + (P*v)/(N+1)) with both quotients and the sum
-            // rounded in double. Fast path: multiply by approximate reciprocals (each product
-            // is within 2^-49 of the reference quotient) and accept the result only if every
-            // double within 2^-46*(|a|+|b|) rounds to the same float; otherwise do it exactly.
-            const int cvi = (int)s.y;
-            const double ne = -(double)__uint_as_float(s.x);
-            const double pv = (double)__fmul_rn(prob, v_sqrt);
-            // reciprocals of the small integers N, N+1: 20-bit hardware seed + 2 Newton steps
-            // (relative error < 2^-50), so each product is within 2^-49 of the true quotient
-            const double dn = (double)cvi, dn1 = (double)(cvi + 1);
-            const double ra = fast_rcp(dn), rb = fast_rcp(dn1);
-            const double a = __dmul_rn(ne, ra);
-            const double b = __dmul_rn(pv, rb);
-            const double sf = __dadd_rn(a, b);
-            const double tol = __dmul_rn(__dadd_rn(fabs(a), fabs(b)), 0x1p-46);
-            const float ulo = __double2float_rn(__dsub_rn(sf, tol));
-            const float uhi = __double2float_rn(__dadd_rn(sf, tol));
-            u = ulo;
-            const bool exact = !(ulo == uhi);
-            if (exact) {
-              const double cv = (double)(float)cvi;
-              const double a = __ddiv_rn(ne, cv);
-              const double b = __ddiv_rn(pv, __dadd_rn(cv, 1.0));
-              u = __double2float_rn(__dadd_rn(a, b));
-            }
-          }
-        }
-      } else {
-        u = __fmul_rn(prob, v_sqrt);
-      }
-      u = __fadd_rn(u, 0.0f);  // -0.0 -> +0.0 so the integer key orders like operator>
+      const float u = puct_u(s, denominator, v_sqrt);
       if (u > best_u) best_u = u, best_e = e, best_s = s;
     }
     const uint32_t key = fkey(best_u);
@@ -704,14 +755,13 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
         c.error = CB200_ERR_OVERFLOW;
         return;
       }
-      CState ps;
-      ps.w0 = (uint64_t)h0.x | ((uint64_t)h0.y << 32);
-      ps.w1 = (uint64_t)h0.z | ((uint64_t)h0.w << 32);
+      const CState ps = rec_state(r);  // same sector as the header word loaded above
       leaf_state = do_move(ps, s3_move(ch_w3));
       const uint32_t coff = c.used;
       int result;
       const int cn = make_record(c, P, leaf_state, depth + 1, result);
       if (cn < 0) return;
+      leaf_n = cn;
       if (c.lane == 0) {
         const float e0 = r_terminal(result) ? (result == kResultDraw ? 0.0f : -1.0f) : 1.0f;
         st4(c.base + so, make_uint4(__float_as_uint(e0), 1u, coff,
@@ -734,6 +784,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     cur_visits = (int)__shfl_sync(kFull, best_s.y, owner);
     cur_w3 = ch_w3;
     cur_result = s3_result(ch_w3);
+    cur_n = s3_cnl(ch_w3);
     ++level;
     if (c.lane == 0) {
       sm.node[level] = ch_off;
@@ -794,7 +845,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     // request an evaluation (trainmc.cpp:684-691): remember the leaf and the path to it
     uint32_t *pd = c.pending + c.n_pending * kPendWords;
     if (c.lane == 0) {
-      pd[0] = node, pd[1] = (uint32_t)level;
+      pd[0] = node, pd[1] = (uint32_t)level | ((uint32_t)leaf_n << 8);
       c.leaf_state[c.n_pending] = make_ulonglong2(leaf_state.w0, leaf_state.w1);
     }
     for (int lv = 1 + c.lane; lv <= level; lv += 32) pd[2 + lv - 1] = sm.slot[lv];
