@@ -433,15 +433,27 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
             dmalloc(&t->d_packed, t->cap) == CB200_OK && dmalloc(&t->d_offs, Gn) == CB200_OK &&
             dmalloc(&t->d_soff, Gn) == CB200_OK && dmalloc(&t->d_summary, 4) == CB200_OK &&
             cudaMallocHost((void **)&t->h_summary, 4 * sizeof(int32_t)) == cudaSuccess;
+  if (ok) {
+    // c_puct * sqrt(visits) exactly as trainmc.cpp:568 evaluates it (double sqrt, double product,
+    // one rounding to float); IEEE sqrt is correctly rounded on host and device alike
+    float *d_vsqrt = nullptr;
+    std::vector<float> vs(kVsqrtCap);
+    for (int i = 0; i < kVsqrtCap; ++i)
+      vs[i] = (float)((double)c_puct * sqrt((double)(float)i));
+    ok = dmalloc(&d_vsqrt, (size_t)kVsqrtCap) == CB200_OK &&
+         cudaMemcpy(d_vsqrt, vs.data(), sizeof(float) * kVsqrtCap, cudaMemcpyHostToDevice) ==
+             cudaSuccess;
+    P.vsqrt = d_vsqrt;
+  }
   if (!ok) {
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
     cb200_trainer_destroy(t);
     return nullptr;
   }
   // stream groups for the fused loop
-  // With in-place re-rooting the per-launch stragglers are gone and one lock-step group is
-  // fastest; CB200_GROUPS > 1 splits the games over independent streams.
-  int ng = 1;
+  // A launch ends when its slowest game does, so large batches are split over a few independent
+  // streams (a group only waits for its own stragglers); CB200_GROUPS overrides.
+  int ng = num_games >= 2048 ? 4 : (num_games >= 512 ? 2 : 1);
   if (const char *env = getenv("CB200_GROUPS")) ng = atoi(env);
   if (ng < 1) ng = 1;
   while (ng > 1 && num_games / ng < 64) ng /= 2;
@@ -536,7 +548,7 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaSetDevice(t->device);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   TreeParams &P = t->P;
-  cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
+  cudaFree((void *)P.vsqrt), cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
   cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);
   cudaFree(t->d_eval), cudaFree(t->d_probs), cudaFree(t->d_rows), cudaFree(t->d_packed);
   cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
@@ -870,9 +882,17 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   long long live_games = t->P.num_games;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
+  // parking budget (TreeParams::yield_budget): a typical doIteration is ~16 searches x ~3 levels
+  // = ~60 units; while many games are live, longer ones (end-game searches that keep hitting
+  // terminal nodes) are cut into several launches. Once few games are left nobody gains from
+  // parking, and it would only stretch the last games.
+  int yield_budget = 96, yield_min_live = 128;
+  if (const char *e = getenv("CB200_YIELD")) yield_budget = atoi(e);
+  if (const char *e = getenv("CB200_YIELD_MIN_LIVE")) yield_min_live = atoi(e);
   while (max_iterations <= 0 || done_iters < max_iterations) {
+    const int yb = live_games >= yield_min_live ? yield_budget : 0;
     int variant = 8;
-    if (ng == 1 && !getenv("CB200_FIXED_VARIANT")) {
+    if (!getenv("CB200_FIXED_VARIANT")) {
       const long long per_sm = (live_games + sms - 1) / sms;  // warps (= games) per SM
       if (per_sm <= 3 * kTreeWarps) variant = 3;
       else if (per_sm <= 4 * kTreeWarps) variant = 4;
@@ -903,6 +923,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
         if (rc != CB200_OK) return rc;
         TreeParams P = t->P;
         P.game_begin = gb, P.game_end = ge, P.group_row0 = row0, P.group_ctr = ctr;
+        P.yield_budget = yb;
         {
           ProfScope ps(t, 3, st);
           const dim3 grid((ge - gb + kTreeWarps - 1) / kTreeWarps), block(kTreeWarps * 32);

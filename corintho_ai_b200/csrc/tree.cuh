@@ -42,6 +42,7 @@ namespace cb200 {
 constexpr int kMaxPath = 64;
 constexpr int kPendWords = 2 + kMaxPath;  // leaf_off, path_len, path[kMaxPath]
 constexpr int kMaxSamples = 64;
+constexpr int kVsqrtCap = 2048;  // entries of the c_puct*sqrt(visits) table
 constexpr int kTreeWarps = 4;  // games per CTA
 // The game-step kernel is compiled for several register budgets (resident CTAs per SM):
 // 8 -> 64 regs (32 warps/SM, spills; best while every SM is full), 5 -> 96, 4 -> 128,
@@ -51,7 +52,7 @@ constexpr int kTreeCtlWords = 12;
 
 enum CtlWord {
   CW_TO_PLAY = 0, CW_PARITY, CW_RESULT, CW_MATE_TURN, CW_N_SAMPLES, CW_N_PENDING, CW_ERROR,
-  CW_DONE, CW_SPARE, CW_MT_IDX, CW_REQ_BASE
+  CW_DONE, CW_SPARE, CW_MT_IDX, CW_REQ_BASE, CW_YIELD
 };
 enum TreeWord {
   TW_ARENA = 0, TW_HAS_ROOT, TW_USED, TW_ROOT_EVAL, TW_ROOT_VISITS, TW_ROOT_RESULT, TW_ROOT_ALLV,
@@ -62,6 +63,7 @@ struct TreeParams {
   int num_games, first_game, total_games;
   int max_searches, spe;
   float c_puct, epsilon;
+  const float *vsqrt;        // [kVsqrtCap] float(double(c_puct) * sqrt(double(i)))
   int testing;
   uint32_t arena_words;
   uint32_t *arenas;          // [G][3][arena_words]
@@ -79,6 +81,10 @@ struct TreeParams {
   int group_row0;            // first request row owned by this group
   int32_t *group_ctr;        // [0..1] request count per parity, [2..3] live games per parity, [4] error
   ulonglong2 *packed;        // [num_games*spe] leaf cstates in request-row order
+  // fused mode: a game whose doIteration needs more than this many select levels + searches in
+  // one launch parks (keeps its partial request list, asks for no evaluation) and resumes in the
+  // next launch, so that one long iteration does not hold back every other game; 0 = never
+  int yield_budget;
   // optional straggler instrumentation (null = off): [0..2] max cycles of one warp in ingest /
   // search / move phases, [3..5] summed cycles, [6] rolled-back searches, [7] words re-rooted
   unsigned long long *phase_prof;
@@ -152,7 +158,8 @@ struct Ctx {
   long long d_sims, d_evals;
   int d_moves;
   long long t_ingest, t_search, t_move, n_none, n_copy;
-  long long t_sel, t_exp, n_lvl, n_exp;
+  long long t_sel, t_exp, n_lvl, n_exp, n_exact;
+  int work, yielded;
   // current tree (trainmc.h:160-188)
   int cur_p, arena, has_root;
   uint32_t used;
@@ -668,9 +675,41 @@ __device__ __forceinline__ float puct_u(const uint4 s, float denominator, float 
   return __fadd_rn(u, 0.0f);  // -0.0 -> +0.0 so the integer key orders like operator>
 }
 
+// Cheap screening of the same value: an interval [lo, hi] that provably contains puct_u().
+// Slots without a (non-drawn) child are exact (lo == hi == the reference's float product). For
+// visited children the float expression -E*rcp(N) + pv*rcp(N+1) is within 2^-22*(|a|+|b|) of the
+// real-number value (rcp.approx: 1 ulp; three roundings) and the reference's double-rounded
+// float within 2^-24 of it, so a half-width of 2^-20*(|a|+|b|) leaves a 3x margin. The argmax
+// is decided from the intervals whenever they separate; otherwise search() redoes the level
+// with puct_u().
+__device__ __forceinline__ bool puct_bounds(const uint4 s, float denominator, float v_sqrt,
+                                            float &lo, float &hi) {
+  const float prob = __fmul_rn((float)s3_prior(s.w), denominator);
+  const float pvf = __fadd_rn(__fmul_rn(prob, v_sqrt), 0.0f);
+  lo = pvf, hi = pvf;
+  if (!s3_has(s.w)) return false;
+  const int cr = s3_result(s.w);
+  if ((r_known(cr) && !r_drawn(cr)) || s3_allv(s.w)) {
+    lo = -INFINITY, hi = -INFINITY;
+    return false;
+  }
+  if (r_drawn(cr)) return false;
+  const float fn = (float)(int)s.y;
+  float ra, rb;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(ra) : "f"(fn));
+  asm("rcp.approx.f32 %0, %1;" : "=f"(rb) : "f"(__fadd_rn(fn, 1.0f)));
+  const float a = __fmul_rn(-__uint_as_float(s.x), ra);
+  const float b = __fmul_rn(pvf, rb);
+  const float u = __fadd_rn(a, b);
+  const float d = __fmul_rn(__fadd_rn(fabsf(a), fabsf(b)), 0x1p-20f);
+  lo = __fadd_rn(__fsub_rn(u, d), 0.0f), hi = __fadd_rn(__fadd_rn(u, d), 0.0f);  // no -0.0 keys
+  return true;
+}
+
 // ---- TrainMC::search (trainmc.cpp:602-696) --------------------------------------------------
 __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) {
   ++c.searches_done;
+  c.work += 1;
   int level = 0;
   uint32_t node = c.root_off;
   int cur_result = c.root_result;
@@ -686,6 +725,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
   while (!r_terminal(cur_result)) {
     const long long tl0 = CB_CLOCK();
     c.n_lvl += 1;
+    c.work += 1;
     const uint32_t *r = c.base + node;
     const int n = cur_n;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
@@ -694,26 +734,48 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     const uint4 h1 = ld4(r + 4);
     const int depth = (int)((h1.x >> 8) & 0xffu);
     const float denominator = __uint_as_float(h1.y);
-    // sqrt(float) binds to double sqrt(double)
-    const float v_sqrt =
-        __double2float_rn(__dmul_rn((double)P.c_puct, sqrt((double)(float)cur_visits)));
-    float best_u = -INFINITY;
-    int best_e = 0x7fffffff;
-    uint4 best_s = zero4;
-    {
-      const float ua = c.lane < n ? puct_u(sa, denominator, v_sqrt) : -INFINITY;
-      const float ub = c.lane + 32 < n ? puct_u(sb, denominator, v_sqrt) : -INFINITY;
-      if (ua > best_u) best_u = ua, best_e = c.lane, best_s = sa;
-      if (ub > best_u) best_u = ub, best_e = c.lane + 32, best_s = sb;
+    // sqrt(float) binds to double sqrt(double); small arguments come from a table
+    // filled by the host with the same expression
+    float v_sqrt;
+    if ((unsigned)cur_visits < (unsigned)kVsqrtCap)
+      v_sqrt = __ldg(P.vsqrt + cur_visits);
+    else
+      v_sqrt = __double2float_rn(__dmul_rn((double)P.c_puct, sqrt((double)(float)cur_visits)));
+    int emin = -1;
+    bool none = false;
+    if (n <= 64) {
+      // screening pass: interval per slot, decide when a single slot (or only exact ones) can
+      // hold the maximum
+      float loa = -INFINITY, hia = -INFINITY, lob = -INFINITY, hib = -INFINITY;
+      bool ina = false, inb = false;
+      if (c.lane < n) ina = puct_bounds(sa, denominator, v_sqrt, loa, hia);
+      if (n > 32 && c.lane + 32 < n) inb = puct_bounds(sb, denominator, v_sqrt, lob, hib);
+      const uint32_t lkey = __reduce_max_sync(kFull, fkey(fmaxf(loa, lob)));
+      if (lkey == kKeyNegInf) {
+        none = true;
+      } else {
+        const bool ca = fkey(hia) >= lkey, cb = fkey(hib) >= lkey;
+        const unsigned ma = __ballot_sync(kFull, ca), mb = __ballot_sync(kFull, cb);
+        const unsigned mi = __ballot_sync(kFull, (ca && ina) || (cb && inb));
+        if (mi == 0u || __popc(ma) + __popc(mb) == 1)
+          emin = ma ? __ffs((int)ma) - 1 : 32 + __ffs((int)mb) - 1;
+      }
     }
-    for (int e = c.lane + 64; e < n; e += 32) {
-      const uint4 s = ld4(r + 8 + 4 * e);
-      const float u = puct_u(s, denominator, v_sqrt);
-      if (u > best_u) best_u = u, best_e = e, best_s = s;
+    if (emin < 0 && !none) {
+      // exact pass (rare): the reference's expression for every slot
+      c.n_exact += 1;
+      float best_u = -INFINITY;
+      int best_e = 0x7fffffff;
+      for (int e = c.lane; e < n; e += 32) {
+        const uint4 s = e < 32 ? sa : (e < 64 ? sb : ld4(r + 8 + 4 * e));
+        const float u = puct_u(s, denominator, v_sqrt);
+        if (u > best_u) best_u = u, best_e = e;
+      }
+      const uint32_t key = fkey(best_u);
+      const uint32_t kmax = __reduce_max_sync(kFull, key);
+      none = (kmax == kKeyNegInf);
+      if (!none) emin = __reduce_min_sync(kFull, key == kmax ? best_e : 0x7fffffff);
     }
-    const uint32_t key = fkey(best_u);
-    const uint32_t kmax = __reduce_max_sync(kFull, key);
-    const bool none = (kmax == kKeyNegInf);
     // virtual loss on the node we stand on (trainmc.cpp:611,625)
     if (level == 0) {
       c.root_visits += 1;
@@ -743,9 +805,10 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
       __syncwarp();
       return;
     }
-    const int emin = __reduce_min_sync(kFull, key == kmax ? best_e : 0x7fffffff);
     const int owner = emin & 31;
     const uint32_t so = node + 8u + 4u * (uint32_t)emin;
+    uint4 best_s = emin < 32 ? sa : sb;
+    if (emin >= 64 && c.lane == owner) best_s = ld4(r + 8 + 4 * emin);
     const uint32_t ch_w3 = __shfl_sync(kFull, best_s.w, owner);
     c.t_sel += CB_CLOCK() - tl0;
     if (!s3_has(ch_w3)) {  // kNew: expand (trainmc.cpp:645-660)
@@ -857,7 +920,8 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
 // ---- TrainMC::doIteration (trainmc.cpp:139-178) ---------------------------------------------
 __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, WarpSm &sm,
                                                   const float *eval, const float *probs,
-                                                  long prs = 0, long pcs = 0) {
+                                                  long prs = 0, long pcs = 0,
+                                                  bool resume = false) {
   if (!c.has_root) {
     fresh_tree(c, P, start_state(), 0);
     c.searches_done = 1;
@@ -870,14 +934,19 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
     return false;
   }
   long long t0 = CB_CLOCK();
-  if (c.n_pending > 0) receive_eval(c, P, sm, eval, probs, prs, pcs);
+  if (c.n_pending > 0 && !resume) receive_eval(c, P, sm, eval, probs, prs, pcs);
   long long t1 = CB_CLOCK();
   c.t_ingest += t1 - t0;
   while (c.n_pending < P.spe && c.searches_done < P.max_searches && !r_known(c.root_result) &&
          !c.root_allv && !c.error) {
+    if (P.yield_budget > 0 && c.work >= P.yield_budget) {
+      c.yielded = 1;  // parked: continue this doIteration in the next launch
+      break;
+    }
     search(c, P, sm);
   }
   c.t_search += CB_CLOCK() - t1;
+  if (c.yielded) return false;
   return (c.searches_done == P.max_searches || r_known(c.root_result)) && c.n_pending == 0;
 }
 
@@ -1137,7 +1206,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
   c.mt_idx = ctl[CW_MT_IDX];
   c.d_sims = 0, c.d_evals = 0, c.d_moves = 0;
   c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
-  c.t_sel = c.t_exp = c.n_lvl = c.n_exp = 0;
+  c.t_sel = c.t_exp = c.n_lvl = c.n_exp = c.n_exact = 0;
+  c.work = 0, c.yielded = 0;
+  bool resume = kFused && ctl[CW_YIELD] != 0;
   c.arenas = P.arenas + (size_t)g * 3 * P.arena_words;
   c.mt = P.mt + (size_t)g * 624;
   c.pending = P.pending + (size_t)g * P.spe * kPendWords;
@@ -1152,7 +1223,8 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
   bool done = false;
   const float *ev_p = eval + off, *pr_p = probs + (long)off * prs;
   for (;;) {
-    const bool turn_done = tree_do_iteration(c, P, sm, ev_p, pr_p, prs, pcs);
+    const bool turn_done = tree_do_iteration(c, P, sm, ev_p, pr_p, prs, pcs, resume);
+    resume = false;
     if (c.error || !turn_done) break;
     const long long tm = CB_CLOCK();
     const int r = choose_move_and_continue(c, P, sm, kFused);
@@ -1169,13 +1241,16 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
     const int par = (iteration + 1) & 1;
     int base = 0;
     if (c.lane == 0) {
-      if (c.n_pending > 0) base = atomicAdd(P.group_ctr + par, c.n_pending);
+      if (c.n_pending > 0 && !c.yielded) base = atomicAdd(P.group_ctr + par, c.n_pending);
       if (!done) atomicAdd(P.group_ctr + 2 + par, 1);
       if (c.error) atomicMin(P.group_ctr + 4, c.error);
       ctl[CW_REQ_BASE] = P.group_row0 + base;
     }
     base = __shfl_sync(kFull, base, 0);
-    for (int k = c.lane; k < c.n_pending; k += 32) P.packed[P.group_row0 + base + k] = c.leaf_state[k];
+    if (!c.yielded)
+      for (int k = c.lane; k < c.n_pending; k += 32)
+        P.packed[P.group_row0 + base + k] = c.leaf_state[k];
+    if (c.lane == 0) ctl[CW_YIELD] = c.yielded;
   }
   if (c.lane == 0) {
     ctl[CW_TO_PLAY] = c.to_play, ctl[CW_RESULT] = c.result, ctl[CW_MATE_TURN] = c.mate_turn;
@@ -1197,6 +1272,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
       atomicAdd(P.phase_prof + 9, (unsigned long long)c.t_exp);
       atomicAdd(P.phase_prof + 10, (unsigned long long)c.n_lvl);
       atomicAdd(P.phase_prof + 11, (unsigned long long)c.n_exp);
+      atomicAdd(P.phase_prof + 12, (unsigned long long)c.n_exact);
     }
   }
 }

@@ -26,6 +26,6 @@ while True:
     pp = t.phase_profile(True).astype(np.float64)
     print("      max-warp kcycles (sum over 64 launches of per-launch max is not available; max over window): ingest %.0f search %.0f move %.0f | mean/warp-iter kcycles: ingest %.1f search %.1f move %.1f | rollbacks %d copied words %d" % (pp[0]/1e3, pp[1]/1e3, pp[2]/1e3, pp[3]/1e3/max(1,live*64), pp[4]/1e3/max(1,live*64), pp[5]/1e3/max(1,live*64), pp[6], pp[7]))
     if pp[10] > 0:
-        print("      select %.0f cycles/level (%.2f levels/sim), expand %.0f cycles/expansion (%d expansions), rollback searches %d" % (pp[8]/pp[10], pp[10]/max(1, c["simulations"]-psims0), pp[9]/max(1,pp[11]), pp[11], pp[6]))
+        print("      select %.0f cycles/level (%.2f levels/sim, exact pass %.2f%%), expand %.0f cycles/expansion (%d expansions), rollback searches %d" % (pp[8]/pp[10], pp[10]/max(1, c["simulations"]-psims0), 100*pp[12]/pp[10], pp[9]/max(1,pp[11]), pp[11], pp[6]))
     if done: break
 print("total %.3f s" % (time.time() - t0), t.counters())
