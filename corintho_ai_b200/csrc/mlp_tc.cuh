@@ -151,6 +151,29 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t v[16])
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+      "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+      "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -174,11 +197,20 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+#if CB200_PHASE_PROF
+#define TC_CLK(v) const long long v = clock64()
+#else
+#define TC_CLK(v)
+#endif
 template <bool kFp16>
 __global__ void __launch_bounds__(kTcThreads, 2)
     k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
              const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
              float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
+  TC_CLK(tk0);
+#if CB200_PHASE_PROF
+  long long tk_w = 0, tk_m = 0, tk_e = 0, tk_s = 0, tk_head = 0;
+#endif
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t *sA = smem;                                // 2 x kTcABytes
   uint8_t *sW = smem + 2 * kTcABytes;                // 2 x kTcLayerBytes
@@ -213,6 +245,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   uint32_t wcount[2] = {0, 0};  // completed waits per weight buffer
   uint32_t mcount = 0;          // completed waits on this warpgroup's MMA barrier
 
+  TC_CLK(tk1);
   const int n_pairs = (n + 255) / 256;
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     if (t == 0) {  // both weight buffers are free here: fetch layers 0 and 1
@@ -224,7 +257,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     }
     // ---- input encoding straight from the packed state into the A operand (bf16 exact)
     const int p = pair * 256 + wg * 128 + row;
-    {
+    // a warpgroup whose tile holds no position (small batches) only keeps the barriers company
+    const bool tile_live = pair * 256 + wg * 128 < n;
+    if (tile_live) {
       CState st{0, 0};
       if (p < n) {
         const ulonglong2 v = states[p];
@@ -250,11 +285,18 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    TC_CLK(tk2);
     for (int layer = 0; layer < kTcLayers; ++layer) {
+      TC_CLK(ta);
       const int b = layer & 1;
       uint8_t *wbuf = sW + b * kTcLayerBytes;
       mbar_wait(wbar0 + 8 * b, wcount[b] & 1);
       wcount[b] += 1;
+      TC_CLK(tb);
+#if CB200_PHASE_PROF
+      long long tc_ = tb;
+#endif
+      if (tile_live) {
       if (row == 0) {  // one thread per warpgroup issues the 7 MMAs of its tile
         const uint32_t waddr = smem_u32(wbuf);
 #pragma unroll
@@ -268,6 +310,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       mbar_wait(mbar0 + 8 * wg, mcount & 1);
       mcount += 1;
       tc_fence_after();
+#if CB200_PHASE_PROF
+      tc_ = clock64();
+#endif
       if (layer < kTcLayers - 1) {
         // ---- hidden-layer epilogue: ReLU + bf16 (bias already in the accumulator), the result
         // becomes the next A operand. TMEM loads are batched: 64 columns, then 48.
@@ -298,48 +343,78 @@ __global__ void __launch_bounds__(kTcThreads, 2)
           }
         }
       } else {
-        // ---- heads: column 0 = value (tanh), columns 1..96 = policy logits (softmax)
+        // ---- heads: column 0 = value (tanh), columns 1..96 = policy logits (softmax).
+        // Pass 1 finds the row maximum, pass 2 writes e = exp(x - max) back into TMEM over the
+        // logits while summing, pass 3 normalises and stores: one exponential per logit.
+        // Columns come in batches of 16: batch 0 holds the value in column 0, batches 1-5 are all
+        // logits, batch 6 holds the last logit (column 96) and padding.
         float mx = -INFINITY, v0 = 0.0f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+        {
           uint32_t v[16];
-          tmem_ld16(tmem_row + c0, v);
+          tmem_ld16(tmem_row, v);
+          v0 = __uint_as_float(v[0]);
 #pragma unroll
-          for (int h = 0; h < 16; ++h) {
-            const int col = c0 + h;
-            const float x = __uint_as_float(v[h]);
-            if (col == 0) v0 = x;
-            if (col >= 1 && col <= CB200_NUM_MOVES) mx = fmaxf(mx, x);
+          for (int h = 1; h < 16; ++h) mx = fmaxf(mx, __uint_as_float(v[h]));
+#pragma unroll 1
+          for (int c0 = 16; c0 < 96; c0 += 16) {
+            tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+            for (int h = 0; h < 16; ++h) mx = fmaxf(mx, __uint_as_float(v[h]));
           }
+          tmem_ld16(tmem_row + 96, v);
+          mx = fmaxf(mx, __uint_as_float(v[0]));
         }
         float sum = 0.0f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+        {
           uint32_t v[16];
-          tmem_ld16(tmem_row + c0, v);
+          tmem_ld16(tmem_row, v);
 #pragma unroll
-          for (int h = 0; h < 16; ++h) {
-            const int col = c0 + h;
-            if (col >= 1 && col <= CB200_NUM_MOVES)
-              sum += __expf(__uint_as_float(v[h]) - mx);
+          for (int h = 1; h < 16; ++h) {
+            const float e = __expf(__uint_as_float(v[h]) - mx);
+            sum += e, v[h] = __float_as_uint(e);
           }
+          tmem_st16(tmem_row, v);
+#pragma unroll 1
+          for (int c0 = 16; c0 < 96; c0 += 16) {
+            tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+              const float e = __expf(__uint_as_float(v[h]) - mx);
+              sum += e, v[h] = __float_as_uint(e);
+            }
+            tmem_st16(tmem_row + c0, v);
+          }
+          tmem_ld16(tmem_row + 96, v);
+          const float e = __expf(__uint_as_float(v[0]) - mx);
+          sum += e, v[0] = __float_as_uint(e);
+          tmem_st16(tmem_row + 96, v);
+          tmem_wait_st();
         }
         const float inv = 1.0f / sum;
         if (p < n) eval[p] = tanhf(v0);
-        // probabilities are written move-major ([96][ld]) so that a warp's stores coalesce
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTcN; c0 += 16) {
+        {
+          // probabilities are written move-major ([96][ld]) so that a warp's stores coalesce;
+          // the TMEM loads are warp-collective, only the stores are per-row
+          const bool wr = p < n;
+          float *pp = probs + p;
           uint32_t v[16];
-          tmem_ld16(tmem_row + c0, v);
+          tmem_ld16(tmem_row, v);
 #pragma unroll
-          for (int h = 0; h < 16; ++h) {
-            const int col = c0 + h;
-            if (col >= 1 && col <= CB200_NUM_MOVES && p < n)
-              probs[(size_t)(col - 1) * probs_ld + p] =
-                  __expf(__uint_as_float(v[h]) - mx) * inv;
+          for (int h = 1; h < 16; ++h, pp += probs_ld)
+            if (wr) *pp = __uint_as_float(v[h]) * inv;
+#pragma unroll 1
+          for (int c0 = 16; c0 < 96; c0 += 16) {
+            tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+            for (int h = 0; h < 16; ++h, pp += probs_ld)
+              if (wr) *pp = __uint_as_float(v[h]) * inv;
           }
+          tmem_ld16(tmem_row + 96, v);
+          if (wr) *pp = __uint_as_float(v[0]) * inv;
         }
       }
+      }  // tile_live
+      TC_CLK(td);
       // A (next layer's operand) is written, both tiles are done with this layer's
       // weights/bias: publish, sync, refill the weight buffer two layers ahead
       fence_proxy_async();
@@ -351,7 +426,19 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kTcLayerBytes, kTcLayerBytes,
                  wbar0 + 8 * b);
       }
+#if CB200_PHASE_PROF
+      {
+        const long long te_ = clock64();
+        tk_w += tb - ta, tk_m += tc_ - tb, tk_s += te_ - td;
+        if (layer < kTcLayers - 1) tk_e += td - tc_; else tk_head += td - tc_;
+      }
+#endif
     }
+#if CB200_PHASE_PROF
+    if (blockIdx.x == 0 && (t == 0 || t == 128) && pair == blockIdx.x && n <= 512)
+      printf("mlp_tc wg%d n=%d: setup %lld encode %lld | 13 layers: wait-w %lld mma %lld epilogue(12) %lld head %lld sync %lld | total %lld\n",
+             wg, n, tk1 - tk0, tk2 - tk1, tk_w, tk_m, tk_e, tk_head, tk_s, clock64() - tk0);
+#endif
   }
   tc_fence_before();
   __syncthreads();

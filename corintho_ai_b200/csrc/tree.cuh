@@ -684,16 +684,15 @@ __device__ __forceinline__ float puct_u(const uint4 s, float denominator, float 
 // with puct_u().
 __device__ __forceinline__ bool puct_bounds(const uint4 s, float denominator, float v_sqrt,
                                             float &lo, float &hi) {
-  const float prob = __fmul_rn((float)s3_prior(s.w), denominator);
+  // straight-line (select-only) code: result codes are classified with bit tables
+  const uint32_t w = s.w;
+  const uint32_t cr = (w >> 16) & 7u;
+  const bool has = (w >> 20) & 1u;
+  // not selectable: pending/exhausted child, or a decided (non-drawn) result {1, 3, 4, 6}
+  const bool unsel = has && ((((w >> 19) | (0x5Au >> cr)) & 1u) != 0u);
+  const bool inexact = has && !unsel && ((0x24u >> cr) & 1u) == 0u;  // drawn {2, 5} is exact
+  const float prob = __fmul_rn((float)s3_prior(w), denominator);
   const float pvf = __fadd_rn(__fmul_rn(prob, v_sqrt), 0.0f);
-  lo = pvf, hi = pvf;
-  if (!s3_has(s.w)) return false;
-  const int cr = s3_result(s.w);
-  if ((r_known(cr) && !r_drawn(cr)) || s3_allv(s.w)) {
-    lo = -INFINITY, hi = -INFINITY;
-    return false;
-  }
-  if (r_drawn(cr)) return false;
   const float fn = (float)(int)s.y;
   float ra, rb;
   asm("rcp.approx.f32 %0, %1;" : "=f"(ra) : "f"(fn));
@@ -702,8 +701,19 @@ __device__ __forceinline__ bool puct_bounds(const uint4 s, float denominator, fl
   const float b = __fmul_rn(pvf, rb);
   const float u = __fadd_rn(a, b);
   const float d = __fmul_rn(__fadd_rn(fabsf(a), fabsf(b)), 0x1p-20f);
-  lo = __fadd_rn(__fsub_rn(u, d), 0.0f), hi = __fadd_rn(__fadd_rn(u, d), 0.0f);  // no -0.0 keys
-  return true;
+  const float ulo = __fadd_rn(__fsub_rn(u, d), 0.0f);  // + 0.0f: no -0.0 keys
+  const float uhi = __fadd_rn(__fadd_rn(u, d), 0.0f);
+  lo = unsel ? -INFINITY : (inexact ? ulo : pvf);
+  hi = unsel ? -INFINITY : (inexact ? uhi : pvf);
+  return inexact;
+}
+// order-preserving float <-> signed int (for redux.sync.max.s32); no -0.0 inputs
+__device__ __forceinline__ int skey(float f) {
+  const int b = __float_as_int(f);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float skey_inv(int k) {
+  return __int_as_float(k ^ ((k >> 31) & 0x7fffffff));
 }
 
 // ---- TrainMC::search (trainmc.cpp:602-696) --------------------------------------------------
@@ -722,6 +732,9 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
   // number of legal moves of the node we stand on: known from the parent's slot below the
   // root, so the slot loads do not wait for the header load (one memory round trip per level)
   int cur_n = (int)(c.base[node + 4] & 0xffu);
+  // the path (slot of every node below the root) goes straight into the pending record this
+  // search will queue if it ends in an evaluation request
+  uint32_t *pd_path = c.pending + c.n_pending * kPendWords + 2;
   while (!r_terminal(cur_result)) {
     const long long tl0 = CB_CLOCK();
     c.n_lvl += 1;
@@ -750,15 +763,15 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
       bool ina = false, inb = false;
       if (c.lane < n) ina = puct_bounds(sa, denominator, v_sqrt, loa, hia);
       if (n > 32 && c.lane + 32 < n) inb = puct_bounds(sb, denominator, v_sqrt, lob, hib);
-      const uint32_t lkey = __reduce_max_sync(kFull, fkey(fmaxf(loa, lob)));
-      if (lkey == kKeyNegInf) {
+      const float lmax = skey_inv(__reduce_max_sync(kFull, skey(fmaxf(loa, lob))));
+      if (lmax == -INFINITY) {
         none = true;
       } else {
-        const bool ca = fkey(hia) >= lkey, cb = fkey(hib) >= lkey;
+        const bool ca = hia >= lmax, cb = hib >= lmax;
         const unsigned ma = __ballot_sync(kFull, ca), mb = __ballot_sync(kFull, cb);
         const unsigned mi = __ballot_sync(kFull, (ca && ina) || (cb && inb));
         if (mi == 0u || __popc(ma) + __popc(mb) == 1)
-          emin = ma ? __ffs((int)ma) - 1 : 32 + __ffs((int)mb) - 1;
+          emin = __ffsll((long long)(((unsigned long long)mb << 32) | ma)) - 1;
       }
     }
     if (emin < 0 && !none) {
@@ -833,6 +846,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
         if (level > 0 && !s3_gc(cur_w3)) c.base[sm.slot[level] + 3] = cur_w3 | kS3Gc;
         sm.node[level + 1] = coff;
         sm.slot[level + 1] = so;
+        pd_path[level] = so;
       }
       ++level;
       node = coff;
@@ -852,6 +866,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     if (c.lane == 0) {
       sm.node[level] = ch_off;
       sm.slot[level] = so;
+      pd_path[level - 1] = so;
     }
     node = ch_off;
     __syncwarp();
@@ -911,7 +926,6 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
       pd[0] = node, pd[1] = (uint32_t)level | ((uint32_t)leaf_n << 8);
       c.leaf_state[c.n_pending] = make_ulonglong2(leaf_state.w0, leaf_state.w1);
     }
-    for (int lv = 1 + c.lane; lv <= level; lv += 32) pd[2 + lv - 1] = sm.slot[lv];
     c.n_pending += 1;
     __syncwarp();
   }
