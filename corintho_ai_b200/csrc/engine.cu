@@ -232,7 +232,7 @@ int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_
   const long prs = probs_move_major ? 1 : CB200_NUM_MOVES;
   const long pcs = probs_move_major ? (long)t->cap : 1;
   ProfScope ps(t, 3);
-  k_iterate<false, 8><<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
+  k_iterate<false, 4><<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
                                                        to_play, t->iterations_done,
                                                        t->stagger_div);
   CB_LAUNCHED();
@@ -880,8 +880,6 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   CB_CUDA(cudaStreamSynchronize(G().stream));
   int done_iters = 0, result = 0;
   long long live_games = t->P.num_games;
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device);
   // parking budget (TreeParams::yield_budget): a typical doIteration is ~16 searches x ~3 levels
   // = ~60 units; while many games are live, longer ones (end-game searches that keep hitting
   // terminal nodes) are cut into several launches. Once few games are left nobody gains from
@@ -891,15 +889,18 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   if (const char *e = getenv("CB200_YIELD_MIN_LIVE")) yield_min_live = atoi(e);
   while (max_iterations <= 0 || done_iters < max_iterations) {
     const int yb = live_games >= yield_min_live ? yield_budget : 0;
-    int variant = 8;
-    if (!getenv("CB200_FIXED_VARIANT")) {
-      const long long per_sm = (live_games + sms - 1) / sms;  // warps (= games) per SM
-      if (per_sm <= 3 * kTreeWarps) variant = 3;
-      else if (per_sm <= 4 * kTreeWarps) variant = 4;
-      else if (per_sm <= 5 * kTreeWarps) variant = 5;
-      else if (per_sm <= 6 * kTreeWarps) variant = 6;
-      else if (per_sm <= 7 * kTreeWarps) variant = 7;
+    // Register-budget variant of the game-step kernel. Measured on B200 (tools/sweep_yield.py,
+    // 4096 games x 800 sims): the 128-register build (no spills, 16 warps per SM, several waves
+    // while many games are live) beats the spilling high-occupancy builds (64-96 registers) by
+    // 10-25 % over the whole run and the 3-CTA build by 0.5 %, so it is the only one shipped;
+    // -DCB200_ALL_VARIANTS + CB200_FIXED_VARIANT=3..8 re-enable the others for experiments.
+#ifdef CB200_ALL_VARIANTS
+    int variant = 4;
+    if (const char *fv = getenv("CB200_FIXED_VARIANT")) {
+      variant = atoi(fv);
+      if (variant < 3 || variant > 8) variant = 4;
     }
+#endif
     int batch = 32;
     if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
     for (int i = 0; i < batch; ++i) {
@@ -930,13 +931,15 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
 #define CB_ITER(MB) \
   k_iterate<true, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, \
                                               t->stagger_div)
-          // register-budget variant by live games: one wave must hold every live game
+#ifdef CB200_ALL_VARIANTS
           if (variant == 3) CB_ITER(3);
-          else if (variant == 4) CB_ITER(4);
           else if (variant == 5) CB_ITER(5);
           else if (variant == 6) CB_ITER(6);
           else if (variant == 7) CB_ITER(7);
-          else CB_ITER(8);
+          else if (variant == 8) CB_ITER(8);
+          else
+#endif
+            CB_ITER(4);
 #undef CB_ITER
           CB_LAUNCHED();
         }

@@ -13,6 +13,9 @@ for g in groups:
     t.set_weights(w, 0, "bf16")
     t.run_selfplay(0, stagger=False)  # warm-up: full run
     for b in budgets:
+        b, _, fv = b.partition("/")
+        if fv: os.environ["CB200_FIXED_VARIANT"] = fv
+        else: os.environ.pop("CB200_FIXED_VARIANT", None)
         y, _, ml = b.partition(":")
         os.environ["CB200_YIELD"] = y
         if ml: os.environ["CB200_YIELD_MIN_LIVE"] = ml
@@ -24,5 +27,5 @@ for g in groups:
             t.run_selfplay(0, stagger=False)
             ts.append(time.perf_counter() - t0)
         c = t.counters()
-        print("groups %d yield %-8s min %.4f s med %.4f s  iterations %d  sims/s %.3e" % (g, b, min(ts), sorted(ts)[len(ts)//2], c["iterations"], c["simulations"] / min(ts)), flush=True)
+        print("groups %d yield %-8s min %.4f s med %.4f s  iterations %d  sims/s %.3e" % (g, b + ("/" + fv if fv else ""), min(ts), sorted(ts)[len(ts)//2], c["iterations"], c["simulations"] / min(ts)), flush=True)
     del t
