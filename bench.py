@@ -14,6 +14,7 @@ no collective on the hot path) and the finished samples are all-gathered over NC
 Under torchrun (N > 1) every rank runs; rank 0 prints the single JSON line.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -29,6 +30,10 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_SIM = 1670.0      # algorithmic bytes per simulation @800 sims
 FLOP_PER_EVAL = 253400.0         # unpadded dense FLOPs per leaf evaluation
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_iterate launch with all 4096 games live
+# (65 536 simulations = 109.4 MB algorithmic), from the `ncu --set full` capture summarised in
+# profiles/r01_ncu_k_iterate_k_mlp_tc_v2.txt; the same capture gives 1.36 MB for k_mlp_tc
+NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 132.301312e6 + 50.268160e6, "network": 1.357056e6 + 0.004096e6}
 
 
 def peaks():
@@ -304,9 +309,24 @@ def run_engine_arm(args, rank, world, local_rank):
         c = tr.counters()
         sims += c["simulations"]; moves += c["moves"]; evals += c["leaf_evals"]; iters += c["iterations"]
     launches = L.cb200_launch_count() - launches0
-    # ---- same steps again with a CUDA-event pair around every kernel launch (on the launching
-    # streams) for the per-kernel durations of the roofline; the event records cost host time,
-    # so `value` comes from the pass above and this pass is reported as ms_per_step_profiled
+    # ---- same steps again with a CUDA-event pair around every kernel launch for the per-kernel
+    # durations of the roofline. The timed pass above runs several stream groups whose kernels
+    # overlap; a launch duration is only the kernel's own when nothing else runs beside it, so
+    # this pass uses a second trainer with ONE stream group (same games, seeds and results).
+    # The event records cost host time: `value` comes from the pass above, this one is reported
+    # as ms_per_step_profiled.
+    sims_check = tr.counters()["simulations"]
+    del tr
+    gc.collect()
+    saved_groups = os.environ.get("CB200_GROUPS")
+    os.environ["CB200_GROUPS"] = "1"
+    tr = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
+                    total_games=G * world, first_game=rank * G)
+    if saved_groups is None:
+        del os.environ["CB200_GROUPS"]
+    else:
+        os.environ["CB200_GROUPS"] = saved_groups
+    tr.set_weights(flat, 0, args.precision)
     tr.set_profiling(True)
     prof_ms, prof_sims, prof_evals = 0.0, 0, 0
     for k in range(args.steps):
@@ -320,8 +340,17 @@ def run_engine_arm(args, rank, world, local_rank):
         prof_ms += e0.elapsed_time(e1)
         c = tr.counters()
         prof_sims += c["simulations"]; prof_evals += c["leaf_evals"]
+    if c["simulations"] != sims_check:
+        raise SystemExit("bench.py: the single-group pass played different games than the timed pass")
     kt = tr.kernel_times()
     tr.set_profiling(False)
+    del tr
+    gc.collect()
+    tr = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
+                    total_games=G * world, first_game=rank * G)
+    tr.set_weights(flat, 0, args.precision)
+    tr.reset(2000)
+    tr.run_selfplay(0, stagger=False)  # untimed: sizes the pinned sample buffers below
     clocks = sampler.stop() if rank == 0 else None
     game_logic = measure_game_logic(torch, cb, dev) if rank == 0 else None
 
@@ -333,6 +362,9 @@ def run_engine_arm(args, rank, world, local_rank):
     pin_gs = torch.empty((cap_rows, 70), dtype=torch.float32).pin_memory()
     pin_ev = torch.empty((cap_rows,), dtype=torch.float32).pin_memory()
     pin_pr = torch.empty((cap_rows, 96), dtype=torch.float32).pin_memory()
+    # one untimed end-to-end warm-up (first use allocates the device-side sample buffer)
+    n_w = tr.num_samples()
+    tr.writeSamples(pin_gs.numpy()[:n_w * 8], pin_ev.numpy()[:n_w * 8], pin_pr.numpy()[:n_w * 8])
     for k in range(args.steps):
         barrier()
         t0 = time.perf_counter()
@@ -380,22 +412,25 @@ def run_engine_arm(args, rank, world, local_rank):
         ach = per_launch_flop / (kt["network"]["ms"] / kt["network"]["launches"] * 1e-3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roof = {"kernel": "k_mlp (policy/value network)", "bound": "tensor", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None}
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_DENSE_LAUNCH["network"]}
     else:
         per_launch_bytes = ALGO_BYTES_PER_SIM * prof_sims / max(1, kt["game_step"]["launches"])
         ach = per_launch_bytes / (kt["game_step"]["ms"] / kt["game_step"]["launches"] * 1e-3) / 1e9
         peak = pk["hbm_gbs"]
         roof = {"kernel": "k_iterate (tree search game step)", "bound": "hbm", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None}
+                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_DENSE_LAUNCH["game_step"]}
+    roof["traffic_note"] = ("bytes of one launch with every game live (ncu --set full, profiles/"
+                            "r01_ncu_k_iterate_k_mlp_tc_v2.txt): 182.6 MB DRAM for 109.4 MB algorithmic; "
+                            "`achieved` averages over all launches of the run, most of which carry fewer games")
     roof["peak_source"] = pk["source"]
     roof["kernel_time_share"] = share
     roof["kernel_ms"] = {k: kt[k]["ms"] for k in kt}
     roof["kernel_launches"] = {k: kt[k]["launches"] for k in kt}
-    roof["note"] = ("per-launch durations from CUDA events recorded on the launching streams during a second "
-                    "pass of the same K steps; kernels of different stream groups overlap, so the summed kernel "
-                    "time exceeds the step time. Whole-step algorithmic rates: %.1f GB/s tree traffic, %.2f "
-                    "TFLOP/s network" % (ALGO_BYTES_PER_SIM * prof_sims / (prof_ms * 1e-3) / 1e9,
-                                         FLOP_PER_EVAL * prof_evals / (prof_ms * 1e-3) / 1e12))
+    roof["note"] = ("per-launch durations from CUDA events recorded on the launching stream during a second "
+                    "pass of the same K steps with a single stream group (kernels run alone, back to back). "
+                    "Whole-step algorithmic rates of the timed pass: %.1f GB/s tree traffic, %.2f TFLOP/s network"
+                    % (ALGO_BYTES_PER_SIM * sims / (dev_ms * 1e-3) / 1e9,
+                       FLOP_PER_EVAL * evals / (dev_ms * 1e-3) / 1e12))
     # secondary roofline of the other heavy kernel, for the record
     if kt["network"]["launches"]:
         roof["network_tflops"] = (FLOP_PER_EVAL * prof_evals / (kt["network"]["ms"] * 1e-3)) / 1e12
@@ -417,7 +452,7 @@ def run_engine_arm(args, rank, world, local_rank):
         "config": workload_desc(args, world),
         "moves_per_sec": moves / (dev_ms * 1e-3), "leaf_evals_per_sec": evals / (dev_ms * 1e-3),
         "simulations_per_step": sims / args.steps, "iterations_per_step": iters / args.steps,
-        "ms_per_step_profiled": prof_ms / args.steps, "stream_groups": int(os.environ.get("CB200_GROUPS", "1")),
+        "ms_per_step_profiled": prof_ms / args.steps, "stream_groups": int(os.environ.get("CB200_GROUPS", 4 if G >= 2048 else (2 if G >= 512 else 1))),
         "game_logic": game_logic,
         "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "seconds_per_step": e2e_s / args.steps,
