@@ -122,6 +122,9 @@ __device__ __forceinline__ bool r_won(int r) { return r == kDeducedWin; }
 __device__ __forceinline__ bool r_lost(int r) { return r == kResultLoss || r == kDeducedLoss; }
 __device__ __forceinline__ bool r_drawn(int r) { return r == kResultDraw || r == kDeducedDraw; }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ uint4 ld4(const uint32_t *p) {
   return *reinterpret_cast<const uint4 *>(p);
 }
@@ -1230,8 +1233,18 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
   c.leaf_state = P.leaf_state + (size_t)g * P.spe;
   c.sample_state = P.sample_state + (size_t)g * kMaxSamples;
   c.sample_probs = P.sample_probs + (size_t)g * kMaxSamples * CB200_NUM_MOVES;
-  load_tree(c, P, c.to_play);
   const int off = kFused ? ctl[CW_REQ_BASE] : offs[g];
+  if (kFused && c.n_pending > 0) {
+    // This launch will ingest evaluations: request everything whose address is already known
+    // (MT19937 state, pending records, this game's rows of the move-major probability matrix)
+    // so that the DRAM/L2 round trips overlap the control-block loads and each other.
+    for (int i = c.lane * 32; i < 624; i += 32 * 32) prefetch_l1(c.mt + i);
+    const int pw = c.n_pending * kPendWords;
+    for (int i = c.lane * 32; i < pw; i += 32 * 32) prefetch_l1(c.pending + i);
+    if (pcs > 1)
+      for (int m = c.lane; m < CB200_NUM_MOVES; m += 32) prefetch_l1(probs + (long)m * pcs + off);
+  }
+  load_tree(c, P, c.to_play);
   // SelfPlayer::doIteration (selfplayer.cpp:115-122) with chooseMoveAndContinue's loop
   // (selfplayer.cpp:246-291) unrolled here so that doIteration has a single call site
   bool done = false;
@@ -1272,7 +1285,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
     ctl[CW_SPARE] = c.spare, ctl[CW_MT_IDX] = c.mt_idx;
     if (done) ctl[CW_DONE] = 1;
     long long *cnt = P.counters + (size_t)g * 4;
-    cnt[0] += c.d_sims, cnt[1] += c.d_moves, cnt[2] += c.d_evals;
+    // reductions without a return value: nothing waits for the old counter values
+    if (c.d_sims) atomicAdd((unsigned long long *)cnt, (unsigned long long)c.d_sims);
+    if (c.d_moves) atomicAdd((unsigned long long *)cnt + 1, (unsigned long long)c.d_moves);
+    if (c.d_evals) atomicAdd((unsigned long long *)cnt + 2, (unsigned long long)c.d_evals);
     if (P.phase_prof) {
       atomicMax(P.phase_prof + 0, (unsigned long long)c.t_ingest);
       atomicMax(P.phase_prof + 1, (unsigned long long)c.t_search);
