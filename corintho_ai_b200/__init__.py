@@ -313,10 +313,10 @@ class Trainer:
         _check(lib().cb200_trainer_set_profiling(self._h, int(enable)))
 
     def kernel_times(self):
-        ms = np.zeros(4, np.float64)
-        ln = np.zeros(4, np.int64)
+        ms = np.zeros(8, np.float64)
+        ln = np.zeros(8, np.int64)
         _check(lib().cb200_trainer_kernel_times(self._h, _ptr(ms), _ptr(ln)))
-        names = ["scan", "pack", "network", "game_step"]
+        names = ["scan", "pack", "network", "game_step", "fused_tail"]
         return {n: {"ms": float(ms[i]), "launches": int(ln[i])} for i, n in enumerate(names)}
 
     def raw_samples(self):

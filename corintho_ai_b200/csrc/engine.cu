@@ -16,6 +16,7 @@
 #include "mlp.cuh"
 #include "mlp_tc.cuh"
 #include "tree.cuh"
+#include "persistent.cuh"
 
 using namespace cb200;
 
@@ -108,13 +109,24 @@ struct cb200_trainer {
   std::vector<int> g_begin, g_end;
   int32_t *d_gctr = nullptr;  // [n_groups][8] device counters (TreeParams::group_ctr)
   int32_t *h_gctr = nullptr;  // pinned mirror
+  // persistent fused tail (persistent.cuh): CTA-private request/answer rows and the live list
+  int ps_ctas = 0;                 // CTAs the device holds (one per SM)
+  int32_t *d_ps_list = nullptr;    // [num_games]
+  int32_t *d_ps_out = nullptr;     // [4] live, error, rounds
+  int32_t *h_ps_out = nullptr;     // pinned
+  float *d_ps_eval = nullptr;      // [ps_ctas * kPsRows]
+  float *d_ps_probs = nullptr;     // [96][ps_ctas * kPsRows] move-major
+  ulonglong2 *d_ps_packed = nullptr;
+  int ps_n = 0;                    // games in the live list
+  bool ps_active = false;          // the games now live in the persistent loop's rows
+  bool ps_first = false;           // next persistent launch reads the lock-step answers first
   // per-kernel-class CUDA-event timing (bench.py roofline): 0 scan, 1 pack, 2 network, 3 iterate
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;  // class of the pair starting at ev_pool[2*i]
   size_t ev_used = 0;
-  double class_ms[4] = {0, 0, 0, 0};
-  long long class_launches[4] = {0, 0, 0, 0};
+  double class_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long class_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -306,6 +318,7 @@ static int init_state(cb200_trainer *t) {
   CB_CUDA(cudaMemsetAsync(t->d_gctr, 0, (size_t)t->n_groups * 8 * sizeof(int32_t), s));
   CB_CUDA(cudaStreamSynchronize(s));
   t->iterations_done = 0;
+  t->ps_active = false, t->ps_first = false, t->ps_n = 0;
   return CB200_OK;
 }
 
@@ -473,7 +486,18 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     }
     t->g_stream.push_back(st), t->g_begin.push_back(b), t->g_end.push_back(e);
   }
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    t->ps_ctas = sms;
+  }
+  const size_t ps_rows = (size_t)t->ps_ctas * kPsRows;
   if (dmalloc(&t->d_gctr, (size_t)t->n_groups * 8) != CB200_OK ||
+      dmalloc(&t->d_ps_list, Gn) != CB200_OK || dmalloc(&t->d_ps_out, 4) != CB200_OK ||
+      dmalloc(&t->d_ps_eval, ps_rows) != CB200_OK ||
+      dmalloc(&t->d_ps_probs, ps_rows * CB200_NUM_MOVES) != CB200_OK ||
+      dmalloc(&t->d_ps_packed, ps_rows) != CB200_OK ||
+      cudaMallocHost((void **)&t->h_ps_out, 4 * sizeof(int32_t)) != cudaSuccess ||
       cudaMallocHost((void **)&t->h_gctr, (size_t)t->n_groups * 8 * sizeof(int32_t)) != cudaSuccess) {
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
     cb200_trainer_destroy(t);
@@ -530,16 +554,16 @@ int cb200_trainer_set_profiling(cb200_trainer *t, int enable) {
   CB_CUDA(cudaStreamSynchronize(G().stream));
   if ((rc = prof_drain(t)) != CB200_OK) return rc;
   t->profiling = enable != 0;
-  for (int i = 0; i < 4; ++i) t->class_ms[i] = 0, t->class_launches[i] = 0;
+  for (int i = 0; i < 8; ++i) t->class_ms[i] = 0, t->class_launches[i] = 0;
   return CB200_OK;
 }
 
-int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[4], int64_t out_launches[4]) {
+int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[8], int64_t out_launches[8]) {
   int rc = guard(t);
   if (rc) return rc;
   CB_CUDA(cudaStreamSynchronize(G().stream));
   if ((rc = prof_drain(t)) != CB200_OK) return rc;
-  for (int i = 0; i < 4; ++i) out_ms[i] = t->class_ms[i], out_launches[i] = t->class_launches[i];
+  for (int i = 0; i < 8; ++i) out_ms[i] = t->class_ms[i], out_launches[i] = t->class_launches[i];
   return CB200_OK;
 }
 
@@ -548,6 +572,8 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaSetDevice(t->device);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   TreeParams &P = t->P;
+  cudaFree(t->d_ps_list), cudaFree(t->d_ps_out), cudaFree(t->d_ps_eval), cudaFree(t->d_ps_probs);
+  cudaFree(t->d_ps_packed), cudaFreeHost(t->h_ps_out);
   cudaFree((void *)P.vsqrt), cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
   cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);
   cudaFree(t->d_eval), cudaFree(t->d_probs), cudaFree(t->d_rows), cudaFree(t->d_packed);
@@ -867,6 +893,60 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
   return CB200_OK;
 }
 
+// Persistent fused tail (persistent.cuh). Called with every stream idle. Runs the remaining games
+// (or `max_rounds` iterations of them); *all_done tells whether every game has finished.
+static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bool *all_done) {
+  static bool attr_set[16] = {false};
+  if (t->device < 16 && !attr_set[t->device]) {
+    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmemBytes));
+    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmemBytes));
+    attr_set[t->device] = true;
+  }
+  cudaStream_t st = t->g_stream[0];
+  *rounds_done = 0, *all_done = false;
+  if (t->ps_n == 0) {
+    *all_done = true;
+    return CB200_OK;
+  }
+  TreeParams P = t->P;
+  P.yield_budget = 0;
+  const NetTC &net = t->nettc[0];
+  const int ld = t->ps_ctas * kPsRows;
+  const int grid = (t->ps_n + kPsWarps - 1) / kPsWarps;
+  CB_CUDA(cudaMemsetAsync(t->d_ps_out, 0, 4 * sizeof(int32_t), st));
+  {
+    ProfScope ps(t, 4, st);
+    if (net.fp16)
+      k_selfplay_persistent<true><<<grid, kTcThreads, kPsSmemBytes, st>>>(
+          P, (const uint8_t *)net.w, t->d_ps_list, t->ps_n, t->d_eval, t->d_probs, (long)t->cap,
+          t->ps_first ? 1 : 0, t->d_ps_eval, t->d_ps_probs, ld, t->d_ps_packed, max_rounds,
+          t->iterations_done, t->d_ps_out);
+    else
+      k_selfplay_persistent<false><<<grid, kTcThreads, kPsSmemBytes, st>>>(
+          P, (const uint8_t *)net.w, t->d_ps_list, t->ps_n, t->d_eval, t->d_probs, (long)t->cap,
+          t->ps_first ? 1 : 0, t->d_ps_eval, t->d_ps_probs, ld, t->d_ps_packed, max_rounds,
+          t->iterations_done, t->d_ps_out);
+    CB_LAUNCHED();
+  }
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaMemcpyAsync(t->h_ps_out, t->d_ps_out, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  if (t->profiling) {
+    int rc = prof_drain(t);
+    if (rc != CB200_OK) return rc;
+  }
+  t->ps_first = false;
+  if (t->h_ps_out[1] != 0)
+    return set_error(t->h_ps_out[1], "a game overflowed its node arena / path / sample buffer (raise "
+                                     "CB200_ARENA_NODES) or reached an impossible state");
+  *rounds_done = t->h_ps_out[2];
+  *all_done = t->h_ps_out[0] == 0;
+  t->iterations_done += *rounds_done;
+  return CB200_OK;
+}
+
 // Fused training-mode loop: every stream group runs [network -> game step] per iteration on its
 // own stream; groups never wait for each other, so one slow game (a long re-rooting) only delays
 // its own group while the other groups keep the SMs and the tensor cores busy.
@@ -887,7 +967,47 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   int yield_budget = 96, yield_min_live = 128;
   if (const char *e = getenv("CB200_YIELD")) yield_budget = atoi(e);
   if (const char *e = getenv("CB200_YIELD_MIN_LIVE")) yield_min_live = atoi(e);
+  // Persistent tail: once every live game fits on the device at kPsWarps games per SM (and all
+  // games have started), the rest of the run is one kernel (persistent.cuh).
+  const bool ps_ok = tc && t->P.spe * kPsWarps <= kPsRows && !getenv("CB200_NO_PERSISTENT");
+  const long long ps_capacity = (long long)t->ps_ctas * kPsWarps;
+  const int stagger_span =
+      t->stagger_div > 0 ? (t->P.first_game + t->P.num_games - 1) / t->stagger_div : 0;
   while (max_iterations <= 0 || done_iters < max_iterations) {
+    if (!t->ps_active && ps_ok && live_games <= ps_capacity && t->iterations_done > stagger_span) {
+      // evaluate the requests queued by the last lock-step game step, then list the live games
+      const int it = t->iterations_done;
+      for (int g = 0; g < ng; ++g) {
+        if (!active[g]) continue;
+        const int gb = t->g_begin[g], ge = t->g_end[g];
+        const int row0 = gb * t->P.spe, rows = (ge - gb) * t->P.spe;
+        int32_t *ctr = t->d_gctr + g * 8;
+        ProfScope ps(t, 2, t->g_stream[g]);
+        int rc = launch_mlp_tc(t->nettc[model], t->d_packed + row0, ctr + (it & 1), 0, rows,
+                               t->d_eval + row0, t->d_probs + row0, (int)t->cap,
+                               ctr + ((it + 1) & 1), t->g_stream[g], true);
+        if (rc != CB200_OK) return rc;
+      }
+      for (int g = 0; g < ng; ++g)
+        if (active[g]) CB_CUDA(cudaStreamSynchronize(t->g_stream[g]));
+      k_live_list<<<1, 32, 0, t->g_stream[0]>>>(t->P, t->d_ps_list, t->d_ps_out + 3);
+      CB_LAUNCHED();
+      CB_CUDA(cudaMemcpyAsync(t->h_ps_out + 3, t->d_ps_out + 3, sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, t->g_stream[0]));
+      CB_CUDA(cudaStreamSynchronize(t->g_stream[0]));
+      t->ps_n = t->h_ps_out[3];
+      t->ps_active = true, t->ps_first = true;
+    }
+    if (t->ps_active) {
+      int rounds = 0;
+      bool all_done = false;
+      const int cap = max_iterations > 0 ? max_iterations - done_iters : (1 << 30);
+      int rc = run_persistent(t, cap, &rounds, &all_done);
+      if (rc != CB200_OK) return rc;
+      done_iters += rounds;
+      if (all_done) result = 1;
+      break;
+    }
     const int yb = live_games >= yield_min_live ? yield_budget : 0;
     // Register-budget variant of the game-step kernel. Measured on B200 (tools/sweep_yield.py,
     // 4096 games x 800 sims): the 128-register build (no spills, 16 warps per SM, several waves

@@ -197,34 +197,27 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-#if CB200_PHASE_PROF
-#define TC_CLK(v) const long long v = clock64()
-#else
-#define TC_CLK(v)
-#endif
-template <bool kFp16>
-__global__ void __launch_bounds__(kTcThreads, 2)
-    k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
-             const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
-             float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
-  TC_CLK(tk0);
-#if CB200_PHASE_PROF
-  long long tk_w = 0, tk_m = 0, tk_e = 0, tk_s = 0, tk_head = 0;
-#endif
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t *sA = smem;                                // 2 x kTcABytes
-  uint8_t *sW = smem + 2 * kTcABytes;                // 2 x kTcLayerBytes
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sW + 2 * kTcLayerBytes);  // wbar[2], mbar[2]
+// Per-CTA state of the tensor-core network: barriers, TMEM allocation and the phase counters of
+// the mbarriers, so that tc_forward() can be called any number of times between tc_setup() and
+// tc_teardown() (once per tile pair in k_mlp_tc, once per round in the persistent self-play kernel).
+struct TcState {
+  uint8_t *sA, *sW;
+  uint32_t wbar0, mbar0, tmem_base;
+  uint32_t wcount[2];  // completed waits per weight buffer
+  uint32_t mcount;     // completed waits on this warpgroup's MMA barrier
+};
+constexpr size_t kTcStateSmemBytes = kTcSmemBytes;  // sA[2] | sW[2] | 4 mbarriers | tmem slot
+
+__device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem) {
+  S.sA = smem;                                 // 2 x kTcABytes
+  S.sW = smem + 2 * kTcABytes;                 // 2 x kTcLayerBytes
+  uint64_t *bars = reinterpret_cast<uint64_t *>(S.sW + 2 * kTcLayerBytes);  // wbar[2], mbar[2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
   const int t = threadIdx.x, warp = t >> 5;
-  const int wg = t >> 7;                             // warpgroup = tile within the CTA
-  const int row = t & 127;                           // row of the tile owned by this thread
-  const int n = n_ptr ? *n_ptr : n_static;
-  if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;  // next parity's counters
-  const uint32_t wbar0 = smem_u32(bars), mbar0 = smem_u32(bars + 2);
+  S.wbar0 = smem_u32(bars), S.mbar0 = smem_u32(bars + 2);
   if (t == 0) {
-    mbar_init(wbar0, 1), mbar_init(wbar0 + 8, 1);
-    mbar_init(mbar0, 1), mbar_init(mbar0 + 8, 1);
+    mbar_init(S.wbar0, 1), mbar_init(S.wbar0 + 8, 1);
+    mbar_init(S.mbar0, 1), mbar_init(S.mbar0 + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -237,216 +230,226 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_tile = tmem_base + (uint32_t)wg * 128u;                  // column offset
-  const uint32_t tmem_row = tmem_tile + ((uint32_t)((warp & 3) * 32) << 16);   // lane offset
-  uint8_t *myA = sA + wg * kTcABytes;
-  const uint32_t aaddr = smem_u32(myA);
-  uint32_t wcount[2] = {0, 0};  // completed waits per weight buffer
-  uint32_t mcount = 0;          // completed waits on this warpgroup's MMA barrier
+  S.tmem_base = *tmem_slot;
+  S.wcount[0] = S.wcount[1] = 0;
+  S.mcount = 0;
+}
 
-  TC_CLK(tk1);
-  const int n_pairs = (n + 255) / 256;
-  for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-    if (t == 0) {  // both weight buffers are free here: fetch layers 0 and 1
-      for (int b = 0; b < 2; ++b) {
-        mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
-        bulk_g2s(smem_u32(sW + b * kTcLayerBytes), W + (size_t)b * kTcLayerBytes, kTcLayerBytes,
-                 wbar0 + 8 * b);
-      }
+__device__ __forceinline__ void tc_teardown(TcState &S) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base),
+                 "r"(kTcTmemCols)
+                 : "memory");
+  }
+}
+
+// One pair of 128-position tiles (positions [pair * 256, pair * 256 + 256) of `states`, n valid
+// positions in total) through all 13 layers. Called by all 256 threads of the CTA.
+template <bool kFp16>
+__device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict__ W,
+                                           const ulonglong2 *__restrict__ states, int n, int pair,
+                                           float *__restrict__ eval, float *__restrict__ probs,
+                                           int probs_ld) {
+  const int t = threadIdx.x, warp = t >> 5;
+  const int wg = t >> 7;    // warpgroup = tile within the CTA
+  const int row = t & 127;  // row of the tile owned by this thread
+  uint8_t *const sW = S.sW;
+  const uint32_t wbar0 = S.wbar0, mbar0 = S.mbar0;
+  const uint32_t tmem_tile = S.tmem_base + (uint32_t)wg * 128u;                  // column offset
+  const uint32_t tmem_row = tmem_tile + ((uint32_t)((warp & 3) * 32) << 16);     // lane offset
+  uint8_t *myA = S.sA + wg * kTcABytes;
+  const uint32_t aaddr = smem_u32(myA);
+  uint32_t wcount[2] = {S.wcount[0], S.wcount[1]};
+  uint32_t mcount = S.mcount;
+  if (t == 0) {  // both weight buffers are free here: fetch layers 0 and 1
+    for (int b = 0; b < 2; ++b) {
+      mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
+      bulk_g2s(smem_u32(sW + b * kTcLayerBytes), W + (size_t)b * kTcLayerBytes, kTcLayerBytes,
+               wbar0 + 8 * b);
     }
-    // ---- input encoding straight from the packed state into the A operand (bf16 exact)
-    const int p = pair * 256 + wg * 128 + row;
-    // a warpgroup whose tile holds no position (small batches) only keeps the barriers company
-    const bool tile_live = pair * 256 + wg * 128 < n;
+  }
+  // ---- input encoding straight from the packed state into the A operand (bf16 exact)
+  const int p = pair * 256 + wg * 128 + row;
+  // a warpgroup whose tile holds no position (small batches) only keeps the barriers company
+  const bool tile_live = pair * 256 + wg * 128 < n;
+  if (tile_live) {
+    CState st{0, 0};
+    if (p < n) {
+      const ulonglong2 v = states[p];
+      st.w0 = v.x, st.w1 = v.y;
+    }
+#pragma unroll
+    for (int c = 0; c < kTcChunks; ++c) {
+      uint32_t q[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int j = 8 * c + 2 * h;
+        const float a = j < CB200_STATE_SIZE ? encode_elem(st, j) : (j == kTcOnes ? 1.0f : 0.0f);
+        const float b = j + 1 < CB200_STATE_SIZE ? encode_elem(st, j + 1)
+                                                 : (j + 1 == kTcOnes + 1 ? 1.0f : 0.0f);
+        q[h] = pack16<kFp16>(a, b);
+      }
+      *reinterpret_cast<uint4 *>(myA + c * kTcAChunkBytes + row * 16) =
+          make_uint4(q[0], q[1], q[2], q[3]);
+    }
+  }
+  // make this thread's generic-proxy writes of A visible to the tensor core, then sync
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  for (int layer = 0; layer < kTcLayers; ++layer) {
+    const int b = layer & 1;
+    uint8_t *wbuf = sW + b * kTcLayerBytes;
+    mbar_wait(wbar0 + 8 * b, wcount[b] & 1);
+    wcount[b] += 1;
     if (tile_live) {
-      CState st{0, 0};
-      if (p < n) {
-        const ulonglong2 v = states[p];
-        st.w0 = v.x, st.w1 = v.y;
+    if (row == 0) {  // one thread per warpgroup issues the 7 MMAs of its tile
+      const uint32_t waddr = smem_u32(wbuf);
+#pragma unroll
+      for (int kk = 0; kk < kTcChunks / 2; ++kk) {
+        const uint64_t ad = umma_desc(aaddr + kk * 2 * kTcAChunkBytes, kTcAChunkBytes, 128);
+        const uint64_t bd = umma_desc(waddr + kk * 2 * kTcWChunkBytes, kTcWChunkBytes, 128);
+        umma_bf16(tmem_tile, ad, bd, kFp16 ? kTcIdescF16 : kTcIdesc, kk > 0 ? 1u : 0u);
       }
+      umma_commit(mbar0 + 8 * wg);
+    }
+    mbar_wait(mbar0 + 8 * wg, mcount & 1);
+    mcount += 1;
+    tc_fence_after();
+    if (layer < kTcLayers - 1) {
+      // ---- hidden-layer epilogue: ReLU + bf16 (bias already in the accumulator), the result
+      // becomes the next A operand. TMEM loads are batched: 64 columns, then 48.
+      {
+        uint32_t v[64];
+        tmem_ld32_nowait(tmem_row, v);
+        tmem_ld32_nowait(tmem_row + 32, v + 32);
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < kTcChunks; ++c) {
-        uint32_t q[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          const int j = 8 * c + 2 * h;
-          const float a = j < CB200_STATE_SIZE ? encode_elem(st, j) : (j == kTcOnes ? 1.0f : 0.0f);
-          const float b = j + 1 < CB200_STATE_SIZE ? encode_elem(st, j + 1)
-                                                   : (j + 1 == kTcOnes + 1 ? 1.0f : 0.0f);
-          q[h] = pack16<kFp16>(a, b);
+        for (int c8 = 0; c8 < 8; ++c8) {
+          const uint32_t *x = v + 8 * c8;
+          *reinterpret_cast<uint4 *>(myA + c8 * kTcAChunkBytes + row * 16) =
+              make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
+                         relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
         }
-        *reinterpret_cast<uint4 *>(myA + c * kTcAChunkBytes + row * 16) =
-            make_uint4(q[0], q[1], q[2], q[3]);
+      }
+      {
+        uint32_t v[48];
+        tmem_ld32_nowait(tmem_row + 64, v);
+        tmem_ld16_nowait(tmem_row + 96, v + 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c8 = 0; c8 < 6; ++c8) {
+          const uint32_t *x = v + 8 * c8;
+          *reinterpret_cast<uint4 *>(myA + (8 + c8) * kTcAChunkBytes + row * 16) =
+              make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
+                         relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
+        }
+      }
+    } else {
+      // ---- heads: column 0 = value (tanh), columns 1..96 = policy logits (softmax).
+      // Pass 1 finds the row maximum, pass 2 writes e = exp(x - max) back into TMEM over the
+      // logits while summing, pass 3 normalises and stores: one exponential per logit.
+      // Columns come in batches of 16: batch 0 holds the value in column 0, batches 1-5 are all
+      // logits, batch 6 holds the last logit (column 96) and padding.
+      float mx = -INFINITY, v0 = 0.0f;
+      {
+        uint32_t v[16];
+        tmem_ld16(tmem_row, v);
+        v0 = __uint_as_float(v[0]);
+#pragma unroll
+        for (int h = 1; h < 16; ++h) mx = fmaxf(mx, __uint_as_float(v[h]));
+#pragma unroll 1
+        for (int c0 = 16; c0 < 96; c0 += 16) {
+          tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+          for (int h = 0; h < 16; ++h) mx = fmaxf(mx, __uint_as_float(v[h]));
+        }
+        tmem_ld16(tmem_row + 96, v);
+        mx = fmaxf(mx, __uint_as_float(v[0]));
+      }
+      float sum = 0.0f;
+      {
+        uint32_t v[16];
+        tmem_ld16(tmem_row, v);
+#pragma unroll
+        for (int h = 1; h < 16; ++h) {
+          const float e = __expf(__uint_as_float(v[h]) - mx);
+          sum += e, v[h] = __float_as_uint(e);
+        }
+        tmem_st16(tmem_row, v);
+#pragma unroll 1
+        for (int c0 = 16; c0 < 96; c0 += 16) {
+          tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+          for (int h = 0; h < 16; ++h) {
+            const float e = __expf(__uint_as_float(v[h]) - mx);
+            sum += e, v[h] = __float_as_uint(e);
+          }
+          tmem_st16(tmem_row + c0, v);
+        }
+        tmem_ld16(tmem_row + 96, v);
+        const float e = __expf(__uint_as_float(v[0]) - mx);
+        sum += e, v[0] = __float_as_uint(e);
+        tmem_st16(tmem_row + 96, v);
+        tmem_wait_st();
+      }
+      const float inv = 1.0f / sum;
+      if (p < n) eval[p] = tanhf(v0);
+      {
+        // probabilities are written move-major ([96][ld]) so that a warp's stores coalesce;
+        // the TMEM loads are warp-collective, only the stores are per-row
+        const bool wr = p < n;
+        float *pp = probs + p;
+        uint32_t v[16];
+        tmem_ld16(tmem_row, v);
+#pragma unroll
+        for (int h = 1; h < 16; ++h, pp += probs_ld)
+          if (wr) *pp = __uint_as_float(v[h]) * inv;
+#pragma unroll 1
+        for (int c0 = 16; c0 < 96; c0 += 16) {
+          tmem_ld16(tmem_row + c0, v);
+#pragma unroll
+          for (int h = 0; h < 16; ++h, pp += probs_ld)
+            if (wr) *pp = __uint_as_float(v[h]) * inv;
+        }
+        tmem_ld16(tmem_row + 96, v);
+        if (wr) *pp = __uint_as_float(v[0]) * inv;
       }
     }
-    // make this thread's generic-proxy writes of A visible to the tensor core, then sync
+    }  // tile_live
+    // A (next layer's operand) is written, both tiles are done with this layer's
+    // weights/bias: publish, sync, refill the weight buffer two layers ahead
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    TC_CLK(tk2);
-    for (int layer = 0; layer < kTcLayers; ++layer) {
-      TC_CLK(ta);
-      const int b = layer & 1;
-      uint8_t *wbuf = sW + b * kTcLayerBytes;
-      mbar_wait(wbar0 + 8 * b, wcount[b] & 1);
-      wcount[b] += 1;
-      TC_CLK(tb);
-#if CB200_PHASE_PROF
-      long long tc_ = tb;
-#endif
-      if (tile_live) {
-      if (row == 0) {  // one thread per warpgroup issues the 7 MMAs of its tile
-        const uint32_t waddr = smem_u32(wbuf);
-#pragma unroll
-        for (int kk = 0; kk < kTcChunks / 2; ++kk) {
-          const uint64_t ad = umma_desc(aaddr + kk * 2 * kTcAChunkBytes, kTcAChunkBytes, 128);
-          const uint64_t bd = umma_desc(waddr + kk * 2 * kTcWChunkBytes, kTcWChunkBytes, 128);
-          umma_bf16(tmem_tile, ad, bd, kFp16 ? kTcIdescF16 : kTcIdesc, kk > 0 ? 1u : 0u);
-        }
-        umma_commit(mbar0 + 8 * wg);
-      }
-      mbar_wait(mbar0 + 8 * wg, mcount & 1);
-      mcount += 1;
-      tc_fence_after();
-#if CB200_PHASE_PROF
-      tc_ = clock64();
-#endif
-      if (layer < kTcLayers - 1) {
-        // ---- hidden-layer epilogue: ReLU + bf16 (bias already in the accumulator), the result
-        // becomes the next A operand. TMEM loads are batched: 64 columns, then 48.
-        {
-          uint32_t v[64];
-          tmem_ld32_nowait(tmem_row, v);
-          tmem_ld32_nowait(tmem_row + 32, v + 32);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            const uint32_t *x = v + 8 * c8;
-            *reinterpret_cast<uint4 *>(myA + c8 * kTcAChunkBytes + row * 16) =
-                make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
-                           relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
-          }
-        }
-        {
-          uint32_t v[48];
-          tmem_ld32_nowait(tmem_row + 64, v);
-          tmem_ld16_nowait(tmem_row + 96, v + 32);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c8 = 0; c8 < 6; ++c8) {
-            const uint32_t *x = v + 8 * c8;
-            *reinterpret_cast<uint4 *>(myA + (8 + c8) * kTcAChunkBytes + row * 16) =
-                make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
-                           relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
-          }
-        }
-      } else {
-        // ---- heads: column 0 = value (tanh), columns 1..96 = policy logits (softmax).
-        // Pass 1 finds the row maximum, pass 2 writes e = exp(x - max) back into TMEM over the
-        // logits while summing, pass 3 normalises and stores: one exponential per logit.
-        // Columns come in batches of 16: batch 0 holds the value in column 0, batches 1-5 are all
-        // logits, batch 6 holds the last logit (column 96) and padding.
-        float mx = -INFINITY, v0 = 0.0f;
-        {
-          uint32_t v[16];
-          tmem_ld16(tmem_row, v);
-          v0 = __uint_as_float(v[0]);
-#pragma unroll
-          for (int h = 1; h < 16; ++h) mx = fmaxf(mx, __uint_as_float(v[h]));
-#pragma unroll 1
-          for (int c0 = 16; c0 < 96; c0 += 16) {
-            tmem_ld16(tmem_row + c0, v);
-#pragma unroll
-            for (int h = 0; h < 16; ++h) mx = fmaxf(mx, __uint_as_float(v[h]));
-          }
-          tmem_ld16(tmem_row + 96, v);
-          mx = fmaxf(mx, __uint_as_float(v[0]));
-        }
-        float sum = 0.0f;
-        {
-          uint32_t v[16];
-          tmem_ld16(tmem_row, v);
-#pragma unroll
-          for (int h = 1; h < 16; ++h) {
-            const float e = __expf(__uint_as_float(v[h]) - mx);
-            sum += e, v[h] = __float_as_uint(e);
-          }
-          tmem_st16(tmem_row, v);
-#pragma unroll 1
-          for (int c0 = 16; c0 < 96; c0 += 16) {
-            tmem_ld16(tmem_row + c0, v);
-#pragma unroll
-            for (int h = 0; h < 16; ++h) {
-              const float e = __expf(__uint_as_float(v[h]) - mx);
-              sum += e, v[h] = __float_as_uint(e);
-            }
-            tmem_st16(tmem_row + c0, v);
-          }
-          tmem_ld16(tmem_row + 96, v);
-          const float e = __expf(__uint_as_float(v[0]) - mx);
-          sum += e, v[0] = __float_as_uint(e);
-          tmem_st16(tmem_row + 96, v);
-          tmem_wait_st();
-        }
-        const float inv = 1.0f / sum;
-        if (p < n) eval[p] = tanhf(v0);
-        {
-          // probabilities are written move-major ([96][ld]) so that a warp's stores coalesce;
-          // the TMEM loads are warp-collective, only the stores are per-row
-          const bool wr = p < n;
-          float *pp = probs + p;
-          uint32_t v[16];
-          tmem_ld16(tmem_row, v);
-#pragma unroll
-          for (int h = 1; h < 16; ++h, pp += probs_ld)
-            if (wr) *pp = __uint_as_float(v[h]) * inv;
-#pragma unroll 1
-          for (int c0 = 16; c0 < 96; c0 += 16) {
-            tmem_ld16(tmem_row + c0, v);
-#pragma unroll
-            for (int h = 0; h < 16; ++h, pp += probs_ld)
-              if (wr) *pp = __uint_as_float(v[h]) * inv;
-          }
-          tmem_ld16(tmem_row + 96, v);
-          if (wr) *pp = __uint_as_float(v[0]) * inv;
-        }
-      }
-      }  // tile_live
-      TC_CLK(td);
-      // A (next layer's operand) is written, both tiles are done with this layer's
-      // weights/bias: publish, sync, refill the weight buffer two layers ahead
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
-      if (t == 0 && layer + 2 < kTcLayers) {
-        mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
-        bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kTcLayerBytes, kTcLayerBytes,
-                 wbar0 + 8 * b);
-      }
-#if CB200_PHASE_PROF
-      {
-        const long long te_ = clock64();
-        tk_w += tb - ta, tk_m += tc_ - tb, tk_s += te_ - td;
-        if (layer < kTcLayers - 1) tk_e += td - tc_; else tk_head += td - tc_;
-      }
-#endif
+    if (t == 0 && layer + 2 < kTcLayers) {
+      mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
+      bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kTcLayerBytes, kTcLayerBytes,
+               wbar0 + 8 * b);
     }
-#if CB200_PHASE_PROF
-    if (blockIdx.x == 0 && (t == 0 || t == 128) && pair == blockIdx.x && n <= 512)
-      printf("mlp_tc wg%d n=%d: setup %lld encode %lld | 13 layers: wait-w %lld mma %lld epilogue(12) %lld head %lld sync %lld | total %lld\n",
-             wg, n, tk1 - tk0, tk2 - tk1, tk_w, tk_m, tk_e, tk_head, tk_s, clock64() - tk0);
-#endif
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(kTcTmemCols)
-                 : "memory");
-  }
+  S.wcount[0] = wcount[0], S.wcount[1] = wcount[1];
+  S.mcount = mcount;
+}
+
+template <bool kFp16>
+__global__ void __launch_bounds__(kTcThreads, 2)
+    k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
+             const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
+             float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int n = n_ptr ? *n_ptr : n_static;
+  if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;  // next parity's counters
+  TcState S;
+  tc_setup(S, smem);
+  const int n_pairs = (n + 255) / 256;
+  for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+    tc_forward<kFp16>(S, W, states, n, pair, eval, probs, probs_ld);
+  tc_teardown(S);
 }
 
 // Re-layout the C-ABI weight vector into per-layer UMMA images (bf16, zero padded) and upload.

@@ -1193,28 +1193,28 @@ __device__ __forceinline__ bool game_selected(const int32_t *ctl, int to_play) {
   return ctl[CW_TO_PLAY] == ((to_play + ctl[CW_PARITY]) & 1);
 }
 
-// One SelfPlayer::doIteration per warp. offs[g] = index of game g's first answer row in
-// eval/probs (exclusive prefix sum of the request counts the answers were produced for).
-// kFused: answers are read at the row the game was handed last time (ctl[CW_REQ_BASE]) and the
-// new leaf states are appended to the group's packed request list (parity `iteration & 1`).
-template <bool kFused, int kMinBlocks>
-__global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
-    k_iterate(TreeParams P, const float *__restrict__ eval, const float *__restrict__ probs,
-              long prs, long pcs, const int32_t *__restrict__ offs, int to_play, int iteration,
-              int stagger_div) {
-  __shared__ WarpSm sm_all[kTreeWarps];
-  const int warp = threadIdx.x >> 5;
-  const int g = (kFused ? P.game_begin : 0) + blockIdx.x * kTreeWarps + warp;
-  if (g >= (kFused ? P.game_end : P.num_games)) return;
+// One SelfPlayer::doIteration for game g, executed by one warp. offs[g] = index of game g's
+// first answer row in eval/probs (exclusive prefix sum of the request counts the answers were
+// produced for). kFused: answers are read at the row the game was handed last time
+// (ctl[CW_REQ_BASE]); the new leaf states are appended to `packed` at row0 + (rows handed out
+// by one atomicAdd on *req_ctr per game); *live_ctr counts the games that are not finished and
+// *err_ctr keeps the most negative error code.
+template <bool kFused>
+__device__ __forceinline__ void run_game(const TreeParams &P, int g, WarpSm &sm,
+                                         const float *__restrict__ eval,
+                                         const float *__restrict__ probs, long prs, long pcs,
+                                         const int32_t *__restrict__ offs, int to_play,
+                                         int iteration, int stagger_div, int32_t *req_ctr,
+                                         int32_t *live_ctr, int32_t *err_ctr, int row0,
+                                         ulonglong2 *packed) {
   int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
   if (!game_selected(ctl, to_play)) return;
   const bool training = (to_play != 0 && to_play != 1);
   // staggered start (trainer.cpp:184-186), on the global game index
   if (training && stagger_div > 0 && (P.first_game + g) / stagger_div > iteration) {
-    if (kFused && (threadIdx.x & 31) == 0) atomicAdd(P.group_ctr + 2 + ((iteration + 1) & 1), 1);
+    if (kFused && (threadIdx.x & 31) == 0) atomicAdd(live_ctr, 1);
     return;  // not started yet, but alive
   }
-  WarpSm &sm = sm_all[warp];
   Ctx c;
   c.lane = threadIdx.x & 31;
   c.to_play = ctl[CW_TO_PLAY], c.parity = ctl[CW_PARITY], c.result = ctl[CW_RESULT];
@@ -1234,7 +1234,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
   c.sample_state = P.sample_state + (size_t)g * kMaxSamples;
   c.sample_probs = P.sample_probs + (size_t)g * kMaxSamples * CB200_NUM_MOVES;
   const int off = kFused ? ctl[CW_REQ_BASE] : offs[g];
-  if (kFused && c.n_pending > 0) {
+  if (kFused && c.n_pending > 0 && !resume) {
     // This launch will ingest evaluations: request everything whose address is already known
     // (MT19937 state, pending records, this game's rows of the move-major probability matrix)
     // so that the DRAM/L2 round trips overlap the control-block loads and each other.
@@ -1265,18 +1265,16 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
   if (c.error) done = true;
   store_tree(c);
   if (kFused) {
-    const int par = (iteration + 1) & 1;
     int base = 0;
     if (c.lane == 0) {
-      if (c.n_pending > 0 && !c.yielded) base = atomicAdd(P.group_ctr + par, c.n_pending);
-      if (!done) atomicAdd(P.group_ctr + 2 + par, 1);
-      if (c.error) atomicMin(P.group_ctr + 4, c.error);
-      ctl[CW_REQ_BASE] = P.group_row0 + base;
+      if (c.n_pending > 0 && !c.yielded) base = atomicAdd(req_ctr, c.n_pending);
+      if (!done) atomicAdd(live_ctr, 1);
+      if (c.error) atomicMin(err_ctr, c.error);
+      ctl[CW_REQ_BASE] = row0 + base;
     }
     base = __shfl_sync(kFull, base, 0);
     if (!c.yielded)
-      for (int k = c.lane; k < c.n_pending; k += 32)
-        P.packed[P.group_row0 + base + k] = c.leaf_state[k];
+      for (int k = c.lane; k < c.n_pending; k += 32) packed[row0 + base + k] = c.leaf_state[k];
     if (c.lane == 0) ctl[CW_YIELD] = c.yielded;
   }
   if (c.lane == 0) {
@@ -1305,6 +1303,23 @@ __global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
       atomicAdd(P.phase_prof + 12, (unsigned long long)c.n_exact);
     }
   }
+}
+
+// Lock-step game step: one warp per game, all games of the trainer (or of one stream group).
+template <bool kFused, int kMinBlocks>
+__global__ void __launch_bounds__(kTreeWarps * 32, kMinBlocks)
+    k_iterate(TreeParams P, const float *__restrict__ eval, const float *__restrict__ probs,
+              long prs, long pcs, const int32_t *__restrict__ offs, int to_play, int iteration,
+              int stagger_div) {
+  __shared__ WarpSm sm_all[kTreeWarps];
+  const int warp = threadIdx.x >> 5;
+  const int g = (kFused ? P.game_begin : 0) + blockIdx.x * kTreeWarps + warp;
+  if (g >= (kFused ? P.game_end : P.num_games)) return;
+  const int par = (iteration + 1) & 1;
+  run_game<kFused>(P, g, sm_all[warp], eval, probs, prs, pcs, offs, to_play, iteration,
+                   stagger_div, kFused ? P.group_ctr + par : nullptr,
+                   kFused ? P.group_ctr + 2 + par : nullptr, kFused ? P.group_ctr + 4 : nullptr,
+                   P.group_row0, P.packed);
 }
 
 // Exclusive prefix sum of the request counts of the selected games (single CTA).

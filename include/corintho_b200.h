@@ -158,9 +158,10 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
 /* Re-initialise every game for a new run with `seed` (same shape, allocations reused). */
 int cb200_trainer_reset(cb200_trainer *t, int seed);
 /* Per-kernel-class device timing with CUDA events on the launch stream (bench.py roofline):
- * classes 0 request scan, 1 request pack, 2 network, 3 game step (tree). */
+ * classes 0 request scan, 1 request pack, 2 network, 3 game step (tree), 4 persistent fused
+ * tail (network + game step in one kernel); 5-7 unused. */
 int cb200_trainer_set_profiling(cb200_trainer *t, int enable);
-int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[4], int64_t out_launches[4]);
+int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[8], int64_t out_launches[8]);
 
 /* Debug: per-warp phase cycle maxima/sums of the game-step kernel since the last call:
  * out = {max ingest, max search, max move, sum ingest, sum search, sum move, rolled-back

@@ -186,6 +186,50 @@ def test_fused_selfplay_is_independent_of_parking_and_stream_groups(monkeypatch)
     assert default == base
 
 
+def test_persistent_tail_equals_lock_step(monkeypatch):
+    """Once the live games fit on the device at 8 per SM the run continues in one persistent
+    kernel (game step + network per CTA). It must play exactly the games of the lock-step loop,
+    also when the run is cut into bounded calls that stop and re-enter the persistent kernel."""
+    flat = cb.fold_batchnorm(cb.random_weights(12))
+    G, MS, SPE = 96, 80, 16
+
+    def result(t):
+        gs, ev, pr = t.write_samples()
+        c = t.counters()
+        return (gs.tobytes(), ev.tobytes(), pr.tobytes(), t.score().tobytes(),
+                (c["simulations"], c["moves"], c["leaf_evals"]))
+
+    monkeypatch.setenv("CB200_NO_PERSISTENT", "1")
+    a = cb.Trainer(G, "", 31, MS, SPE, 1.0, 0.25)
+    a.set_weights(flat, 0, "bf16")
+    assert a.run_selfplay(0, stagger=False)
+    base = result(a)
+    monkeypatch.delenv("CB200_NO_PERSISTENT")
+    b = cb.Trainer(G, "", 31, MS, SPE, 1.0, 0.25)
+    b.set_weights(flat, 0, "bf16")
+    b.set_profiling(True)
+    assert b.run_selfplay(0, stagger=False)
+    kt = b.kernel_times()
+    assert kt["fused_tail"]["launches"] >= 1 and kt["game_step"]["launches"] >= 1
+    assert result(b) == base
+    # bounded calls: 40 lock-step iterations, then the persistent kernel 7 rounds at a time
+    c = cb.Trainer(G, "", 31, MS, SPE, 1.0, 0.25)
+    c.set_weights(flat, 0, "fp16")
+    c.set_weights(flat, 0, "bf16")
+    done = c.run_selfplay(40, stagger=False)
+    calls = 0
+    while not done:
+        done = c.run_selfplay(7, stagger=False)
+        calls += 1
+        assert calls < 10000
+    assert calls > 3
+    assert result(c) == base
+    # and a run after reset() starts in lock-step mode again
+    c.reset(31)
+    assert c.run_selfplay(0, stagger=False)
+    assert result(c) == base
+
+
 def _trained_like_params(seed):
     """Random weights with non-trivial biases and BatchNorm statistics, so that the folded
     biases are non-zero (random init has b = 0, beta = 0)."""
