@@ -112,14 +112,16 @@ struct cb200_trainer {
   // persistent fused tail (persistent.cuh): CTA-private request/answer rows and the live list
   int ps_ctas = 0;                 // CTAs the device holds (one per SM)
   int32_t *d_ps_list = nullptr;    // [num_games]
-  int32_t *d_ps_out = nullptr;     // [4] live, error, rounds
+  int32_t *d_ps_out = nullptr;     // [8] live, error, rounds, finished | list length
   int32_t *h_ps_out = nullptr;     // pinned
-  float *d_ps_eval = nullptr;      // [ps_ctas * kPsRows]
-  float *d_ps_probs = nullptr;     // [96][ps_ctas * kPsRows] move-major
-  ulonglong2 *d_ps_packed = nullptr;
+  float *d_ps_eval[2] = {nullptr, nullptr};   // [ps_ld] answers, ping-pong between launches
+  float *d_ps_probs[2] = {nullptr, nullptr};  // [96][ps_ld] move-major
+  ulonglong2 *d_ps_packed = nullptr;          // [ps_ld] request rows (live within one round)
+  int ps_ld = 0;                   // rows = ps_ctas * 16 games * 16 requests
   int ps_n = 0;                    // games in the live list
+  int ps_cur = 0;                  // buffer holding the answers of the queued requests
   bool ps_active = false;          // the games now live in the persistent loop's rows
-  bool ps_first = false;           // next persistent launch reads the lock-step answers first
+  bool ps_from_lockstep = false;   // ... except that the next launch reads d_eval/d_probs first
   // per-kernel-class CUDA-event timing (bench.py roofline): 0 scan, 1 pack, 2 network, 3 iterate
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -318,7 +320,7 @@ static int init_state(cb200_trainer *t) {
   CB_CUDA(cudaMemsetAsync(t->d_gctr, 0, (size_t)t->n_groups * 8 * sizeof(int32_t), s));
   CB_CUDA(cudaStreamSynchronize(s));
   t->iterations_done = 0;
-  t->ps_active = false, t->ps_first = false, t->ps_n = 0;
+  t->ps_active = false, t->ps_from_lockstep = false, t->ps_n = 0, t->ps_cur = 0;
   return CB200_OK;
 }
 
@@ -491,13 +493,16 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     t->ps_ctas = sms;
   }
-  const size_t ps_rows = (size_t)t->ps_ctas * kPsRows;
+  t->ps_ld = t->ps_ctas * 16 * kPsRowsPerGame;
+  const size_t ps_rows = (size_t)t->ps_ld;
   if (dmalloc(&t->d_gctr, (size_t)t->n_groups * 8) != CB200_OK ||
-      dmalloc(&t->d_ps_list, Gn) != CB200_OK || dmalloc(&t->d_ps_out, 4) != CB200_OK ||
-      dmalloc(&t->d_ps_eval, ps_rows) != CB200_OK ||
-      dmalloc(&t->d_ps_probs, ps_rows * CB200_NUM_MOVES) != CB200_OK ||
+      dmalloc(&t->d_ps_list, Gn) != CB200_OK || dmalloc(&t->d_ps_out, 8) != CB200_OK ||
+      dmalloc(&t->d_ps_eval[0], ps_rows) != CB200_OK ||
+      dmalloc(&t->d_ps_eval[1], ps_rows) != CB200_OK ||
+      dmalloc(&t->d_ps_probs[0], ps_rows * CB200_NUM_MOVES) != CB200_OK ||
+      dmalloc(&t->d_ps_probs[1], ps_rows * CB200_NUM_MOVES) != CB200_OK ||
       dmalloc(&t->d_ps_packed, ps_rows) != CB200_OK ||
-      cudaMallocHost((void **)&t->h_ps_out, 4 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost((void **)&t->h_ps_out, 8 * sizeof(int32_t)) != cudaSuccess ||
       cudaMallocHost((void **)&t->h_gctr, (size_t)t->n_groups * 8 * sizeof(int32_t)) != cudaSuccess) {
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
     cb200_trainer_destroy(t);
@@ -572,7 +577,8 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaSetDevice(t->device);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   TreeParams &P = t->P;
-  cudaFree(t->d_ps_list), cudaFree(t->d_ps_out), cudaFree(t->d_ps_eval), cudaFree(t->d_ps_probs);
+  cudaFree(t->d_ps_list), cudaFree(t->d_ps_out), cudaFree(t->d_ps_eval[0]), cudaFree(t->d_ps_eval[1]);
+  cudaFree(t->d_ps_probs[0]), cudaFree(t->d_ps_probs[1]);
   cudaFree(t->d_ps_packed), cudaFreeHost(t->h_ps_out);
   cudaFree((void *)P.vsqrt), cudaFree(P.arenas), cudaFree(P.ctl), cudaFree(P.tree), cudaFree(P.mt), cudaFree(P.pending);
   cudaFree(P.leaf_state), cudaFree(P.sample_state), cudaFree(P.sample_probs), cudaFree(P.counters);
@@ -894,56 +900,94 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
 }
 
 // Persistent fused tail (persistent.cuh). Called with every stream idle. Runs the remaining games
-// (or `max_rounds` iterations of them); *all_done tells whether every game has finished.
-static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bool *all_done) {
+// (or `max_rounds` iterations of them) as a sequence of persistent launches; between launches
+// the live games are listed again so that they spread evenly over the SMs (8 games per CTA
+// once they fit, else 16). A launch reads the answers of the requests queued before it from the
+// buffer the previous launch (or the lock-step loop) wrote, and writes its own into the other.
+static int ps_list_games(cb200_trainer *t) {
+  cudaStream_t st = t->g_stream[0];
+  k_live_list<<<1, 32, 0, st>>>(t->P, t->d_ps_list, t->d_ps_out + 4);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaMemcpyAsync(t->h_ps_out + 4, t->d_ps_out + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  t->ps_n = t->h_ps_out[4];
+  return CB200_OK;
+}
+
+extern "C++" {
+template <bool kFp16, int kGames>
+static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit_done) {
   static bool attr_set[16] = {false};
   if (t->device < 16 && !attr_set[t->device]) {
-    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<false>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmemBytes));
-    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<true>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPsSmemBytes));
+    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<kFp16, kGames>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ps_smem_bytes<kGames>()));
     attr_set[t->device] = true;
   }
+  const float *ev0 = t->ps_from_lockstep ? t->d_eval : t->d_ps_eval[t->ps_cur];
+  const float *pr0 = t->ps_from_lockstep ? t->d_probs : t->d_ps_probs[t->ps_cur];
+  const long pcs0 = t->ps_from_lockstep ? (long)t->cap : (long)t->ps_ld;
+  const int nxt = 1 - t->ps_cur;
+  // one CTA per SM, games dealt round-robin (every CTA gets ceil or floor of ps_n / grid)
+  const int grid = t->ps_n < t->ps_ctas ? t->ps_n : t->ps_ctas;
+  k_selfplay_persistent<kFp16, kGames><<<grid, kGames * 32, ps_smem_bytes<kGames>(), t->g_stream[0]>>>(
+      P, (const uint8_t *)t->nettc[0].w, t->d_ps_list, t->ps_n, ev0, pr0, pcs0, t->d_ps_eval[nxt],
+      t->d_ps_probs[nxt], t->ps_ld, t->d_ps_packed, rounds, exit_done, t->iterations_done,
+      t->d_ps_out);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  return CB200_OK;
+}
+}  // extern "C++"
+
+static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bool *all_done) {
   cudaStream_t st = t->g_stream[0];
   *rounds_done = 0, *all_done = false;
-  if (t->ps_n == 0) {
-    *all_done = true;
-    return CB200_OK;
-  }
   TreeParams P = t->P;
   P.yield_budget = 0;
-  const NetTC &net = t->nettc[0];
-  const int ld = t->ps_ctas * kPsRows;
-  const int grid = (t->ps_n + kPsWarps - 1) / kPsWarps;
-  CB_CUDA(cudaMemsetAsync(t->d_ps_out, 0, 4 * sizeof(int32_t), st));
-  {
-    ProfScope ps(t, 4, st);
-    if (net.fp16)
-      k_selfplay_persistent<true><<<grid, kTcThreads, kPsSmemBytes, st>>>(
-          P, (const uint8_t *)net.w, t->d_ps_list, t->ps_n, t->d_eval, t->d_probs, (long)t->cap,
-          t->ps_first ? 1 : 0, t->d_ps_eval, t->d_ps_probs, ld, t->d_ps_packed, max_rounds,
-          t->iterations_done, t->d_ps_out);
-    else
-      k_selfplay_persistent<false><<<grid, kTcThreads, kPsSmemBytes, st>>>(
-          P, (const uint8_t *)net.w, t->d_ps_list, t->ps_n, t->d_eval, t->d_probs, (long)t->cap,
-          t->ps_first ? 1 : 0, t->d_ps_eval, t->d_ps_probs, ld, t->d_ps_packed, max_rounds,
-          t->iterations_done, t->d_ps_out);
-    CB_LAUNCHED();
-  }
-  CB_CUDA(cudaGetLastError());
-  CB_CUDA(cudaMemcpyAsync(t->h_ps_out, t->d_ps_out, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CB_CUDA(cudaStreamSynchronize(st));
-  if (t->profiling) {
-    int rc = prof_drain(t);
+  while (*rounds_done < max_rounds) {
+    if (t->ps_n == 0) {
+      *all_done = true;
+      break;
+    }
+    const int rounds = max_rounds - *rounds_done;
+    // deal the games again once half of them have finished (not worth it for the last few)
+    int exit_done = t->ps_n > 64 ? t->ps_n / 2 : 0x7fffffff;
+    if (getenv("CB200_PS_NO_REDEAL")) exit_done = 0x7fffffff;
+    const bool wide = t->ps_n > t->ps_ctas * 8;
+    CB_CUDA(cudaMemsetAsync(t->d_ps_out, 0, 4 * sizeof(int32_t), st));
+    int rc;
+    {
+      ProfScope ps(t, 4, st);
+      if (t->nettc[0].fp16)
+        rc = wide ? ps_launch<true, 16>(t, P, rounds, exit_done)
+                  : ps_launch<true, 8>(t, P, rounds, exit_done);
+      else
+        rc = wide ? ps_launch<false, 16>(t, P, rounds, exit_done)
+                  : ps_launch<false, 8>(t, P, rounds, exit_done);
+    }
     if (rc != CB200_OK) return rc;
+    CB_CUDA(cudaMemcpyAsync(t->h_ps_out, t->d_ps_out, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    if (t->profiling && (rc = prof_drain(t)) != CB200_OK) return rc;
+    t->ps_from_lockstep = false;
+    t->ps_cur = 1 - t->ps_cur;
+    if (t->h_ps_out[1] != 0)
+      return set_error(t->h_ps_out[1], "a game overflowed its node arena / path / sample buffer (raise "
+                                       "CB200_ARENA_NODES) or reached an impossible state");
+    // CTAs stop at different rounds (all games finished / the re-deal trigger): the launch
+    // advanced the run by at most out[2] iterations
+    const int ran = t->h_ps_out[2];
+    *rounds_done += ran;
+    t->iterations_done += ran;
+    if (t->h_ps_out[0] == 0) {
+      t->ps_n = 0;
+      *all_done = true;
+      break;
+    }
+    if ((rc = ps_list_games(t)) != CB200_OK) return rc;
   }
-  t->ps_first = false;
-  if (t->h_ps_out[1] != 0)
-    return set_error(t->h_ps_out[1], "a game overflowed its node arena / path / sample buffer (raise "
-                                     "CB200_ARENA_NODES) or reached an impossible state");
-  *rounds_done = t->h_ps_out[2];
-  *all_done = t->h_ps_out[0] == 0;
-  t->iterations_done += *rounds_done;
   return CB200_OK;
 }
 
@@ -967,10 +1011,12 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   int yield_budget = 96, yield_min_live = 128;
   if (const char *e = getenv("CB200_YIELD")) yield_budget = atoi(e);
   if (const char *e = getenv("CB200_YIELD_MIN_LIVE")) yield_min_live = atoi(e);
-  // Persistent tail: once every live game fits on the device at kPsWarps games per SM (and all
-  // games have started), the rest of the run is one kernel (persistent.cuh).
-  const bool ps_ok = tc && t->P.spe * kPsWarps <= kPsRows && !getenv("CB200_NO_PERSISTENT");
-  const long long ps_capacity = (long long)t->ps_ctas * kPsWarps;
+  // Persistent tail: once every live game fits on the device at 16 games per SM (and all games
+  // have started), the rest of the run happens inside persistent kernels (persistent.cuh).
+  const bool ps_ok = tc && t->P.spe <= kPsRowsPerGame && !getenv("CB200_NO_PERSISTENT");
+  long long ps_capacity = (long long)t->ps_ctas * 16;
+  if (const char *e = getenv("CB200_PS_CAPACITY")) ps_capacity = atoll(e);
+  if (ps_capacity > (long long)t->ps_ctas * 16) ps_capacity = (long long)t->ps_ctas * 16;
   const int stagger_span =
       t->stagger_div > 0 ? (t->P.first_game + t->P.num_games - 1) / t->stagger_div : 0;
   while (max_iterations <= 0 || done_iters < max_iterations) {
@@ -990,13 +1036,9 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       }
       for (int g = 0; g < ng; ++g)
         if (active[g]) CB_CUDA(cudaStreamSynchronize(t->g_stream[g]));
-      k_live_list<<<1, 32, 0, t->g_stream[0]>>>(t->P, t->d_ps_list, t->d_ps_out + 3);
-      CB_LAUNCHED();
-      CB_CUDA(cudaMemcpyAsync(t->h_ps_out + 3, t->d_ps_out + 3, sizeof(int32_t),
-                              cudaMemcpyDeviceToHost, t->g_stream[0]));
-      CB_CUDA(cudaStreamSynchronize(t->g_stream[0]));
-      t->ps_n = t->h_ps_out[3];
-      t->ps_active = true, t->ps_first = true;
+      int rc = ps_list_games(t);
+      if (rc != CB200_OK) return rc;
+      t->ps_active = true, t->ps_from_lockstep = true;
     }
     if (t->ps_active) {
       int rounds = 0;

@@ -197,6 +197,10 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// Barrier of the 256 threads that run the network (named barrier 1, so that a larger CTA can keep
+// its other warps out of it; in k_mlp_tc it is the whole CTA).
+__device__ __forceinline__ void tc_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 // Per-CTA state of the tensor-core network: barriers, TMEM allocation and the phase counters of
 // the mbarriers, so that tc_forward() can be called any number of times between tc_setup() and
 // tc_teardown() (once per tile pair in k_mlp_tc, once per round in the persistent self-play kernel).
@@ -228,7 +232,7 @@ __device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  tc_sync();
   tc_fence_after();
   S.tmem_base = *tmem_slot;
   S.wcount[0] = S.wcount[1] = 0;
@@ -237,7 +241,7 @@ __device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem) {
 
 __device__ __forceinline__ void tc_teardown(TcState &S) {
   tc_fence_before();
-  __syncthreads();
+  tc_sync();
   if ((threadIdx.x >> 5) == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base),
                  "r"(kTcTmemCols)
@@ -298,7 +302,7 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
   // make this thread's generic-proxy writes of A visible to the tensor core, then sync
   fence_proxy_async();
   tc_fence_before();
-  __syncthreads();
+  tc_sync();
   tc_fence_after();
   for (int layer = 0; layer < kTcLayers; ++layer) {
     const int b = layer & 1;
@@ -424,7 +428,7 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
     // weights/bias: publish, sync, refill the weight buffer two layers ahead
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    tc_sync();
     tc_fence_after();
     if (t == 0 && layer + 2 < kTcLayers) {
       mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);

@@ -17,10 +17,12 @@
 
 namespace cb200 {
 
-constexpr int kPsWarps = 8;                  // games per CTA
-constexpr int kPsRows = 128;                 // request rows per CTA = one network tile
+constexpr int kPsRowsPerGame = 16;           // request rows reserved per game (needs spe <= 16)
+template <int kGames>
+constexpr size_t ps_smem_bytes() {
+  return (kTcSmemBytes + 127) / 128 * 128 + kGames * sizeof(WarpSm);
+}
 constexpr size_t kPsTreeSmemOff = (kTcSmemBytes + 127) / 128 * 128;
-constexpr size_t kPsSmemBytes = kPsTreeSmemOff + kPsWarps * sizeof(WarpSm);
 
 // live games in ascending index order (single thread: a few thousand flags, once per switch)
 __global__ void k_live_list(TreeParams P, int32_t *__restrict__ list, int32_t *__restrict__ count) {
@@ -31,30 +33,42 @@ __global__ void k_live_list(TreeParams P, int32_t *__restrict__ list, int32_t *_
   *count = n;
 }
 
-// out[0] += games still live when the CTA stopped, out[1] = min error code, out[2] = max rounds
-template <bool kFp16>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// kGames = 8 (256 threads, one network tile) or 16 (512 threads, two tiles; the network is run
+// by warps 0-7). Games are dealt round-robin over the CTAs (slot = warp * gridDim.x + blockIdx.x)
+// so that every SM gets its share however few games are left. All CTAs stop at their next round
+// boundary once `exit_done` games of this launch have finished (the host then deals the
+// remaining games again). out[0] += games still live when the CTA stopped, out[1] = min error
+// code, out[2] = max rounds executed by a CTA, out[3] = games finished during the launch.
+template <bool kFp16, int kGames>
+__global__ void __launch_bounds__(kGames * 32, 1)
     k_selfplay_persistent(TreeParams P, const uint8_t *__restrict__ W,
                           const int32_t *__restrict__ game_list, int n_list,
-                          const float *eval0, const float *probs0, long pcs0, int first_external,
-                          float *eval, float *probs, int ld, ulonglong2 *packed, int max_rounds,
-                          int iteration0, int32_t *__restrict__ out) {
+                          const float *eval0, const float *probs0, long pcs0, float *eval,
+                          float *probs, int ld, ulonglong2 *packed, int max_rounds, int exit_done,
+                          int iteration0, int32_t *out) {
+  static_assert(kGames == 8 || kGames == 16, "one or two network tiles per CTA");
+  constexpr int kRows = kGames * kPsRowsPerGame;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int32_t s_ctr[4];  // [0] requests of this round, [1] live games, [2] error
+  __shared__ int32_t s_ctr[4];  // [0] requests of this round, [1] live games, [2] error, [3] stop
+  const bool net_thread = threadIdx.x < kTcThreads;
   TcState S;
-  tc_setup(S, smem);
+  if (net_thread) tc_setup(S, smem);
   WarpSm *sm_all = reinterpret_cast<WarpSm *>(smem + kPsTreeSmemOff);
   const int warp = threadIdx.x >> 5;
-  const int slot = blockIdx.x * kPsWarps + warp;
+  const int slot = warp * gridDim.x + blockIdx.x;
   const int g = slot < n_list ? game_list[slot] : -1;
-  const int row0 = blockIdx.x * kPsRows;
-  if (threadIdx.x == 0) s_ctr[2] = 0;  // published by the first barrier of the loop
+  const int row0 = blockIdx.x * kRows;
+  if (threadIdx.x == 0) s_ctr[2] = 0, s_ctr[3] = 0;  // published by the first barrier of the loop
+  // games dealt to this CTA (all live at launch)
+  int prev_live = ((int)n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  if (prev_live > kGames) prev_live = kGames;
+  if (prev_live < 0) prev_live = 0;
   int round = 0, live = 0;
   for (; round < max_rounds; ++round) {
     if (threadIdx.x == 0) s_ctr[0] = 0, s_ctr[1] = 0;
     __syncthreads();
     if (g >= 0) {
-      const bool ext = first_external && round == 0;
+      const bool ext = round == 0;  // answers of the requests queued before this launch
       run_game<true>(P, g, sm_all[warp], ext ? eval0 : eval, ext ? probs0 : probs, 1,
                      ext ? pcs0 : (long)ld, nullptr, -1, iteration0 + round, 0, &s_ctr[0],
                      &s_ctr[1], &s_ctr[2], row0, packed);
@@ -62,16 +76,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     __syncthreads();
     const int n = s_ctr[0];
     live = s_ctr[1];
-    __syncthreads();  // everybody has read the counters before thread 0 clears them again
+    if (threadIdx.x == 0) {
+      if (live < prev_live) atomicAdd(out + 3, prev_live - live);
+      prev_live = live;
+      if (*(volatile int32_t *)(out + 3) >= exit_done) s_ctr[3] = 1;
+    }
     // every round ends with the network, so the answers of all queued requests are in the
     // CTA's rows whenever the kernel stops (a later launch continues from there)
-    if (n > 0) tc_forward<kFp16>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
-    if (live == 0) {
+    if (net_thread && n > 0)
+      tc_forward<kFp16>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
+    __syncthreads();  // answers visible to every warp; counters read before they are cleared
+    if (live == 0 || s_ctr[3]) {
       ++round;
       break;
     }
   }
-  tc_teardown(S);
+  if (net_thread) tc_teardown(S);
   if (threadIdx.x == 0) {
     if (live) atomicAdd(out, live);
     if (s_ctr[2]) atomicMin(out + 1, s_ctr[2]);
