@@ -381,6 +381,11 @@ def run_engine_arm(args, rank, world, local_rank):
     # one untimed end-to-end warm-up (first use allocates the device-side sample buffer)
     n_w = tr.num_samples()
     tr.writeSamples(pin_gs.numpy()[:n_w * 8], pin_ev.numpy()[:n_w * 8], pin_pr.numpy()[:n_w * 8])
+    if dist is not None:  # ... and sizes NCCL's buffers / the allocator's blocks for the gather
+        from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
+        ptr, n_rows = tr.raw_samples_device()
+        all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
+        torch.cuda.synchronize()
     for k in range(args.steps):
         barrier()
         t0 = time.perf_counter()

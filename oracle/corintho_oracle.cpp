@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <string>
+#include <map>
 #include <vector>
 
 #include "oracle_tables.inc"
@@ -881,6 +882,121 @@ float game_score(const GameRec &g) {  // selfplayer.cpp:57-64
   return 0.5;
 }
 
+
+// ---- Match (match.h:33-101, match.cpp) ---------------------------------------------------------
+// One game between two players with their own search budgets (Player, match.h:13-31). A random
+// player has no tree (match.cpp:27-33). The authoritative position lives outside both trees
+// (Match::root_, match.h:96).
+struct MatchRec {
+  GameRec g;
+  Params p[2];
+  bool random[2] = {false, false};
+  int ids[2] = {0, 0};
+  int model_ids[2] = {0, 0};
+  State root;
+  int root_depth = 0;
+};
+
+// std::uniform_int_distribution<int32_t>(0, n - 1)(mt19937) as libstdc++ (GCC 11+) implements it:
+// Lemire's nearly divisionless method on a 64-bit product (bits/uniform_int_dist.h, _S_nd)
+int uniform_index(MT &rng, uint32_t n) {
+  uint64_t product = (uint64_t)rng.next() * (uint64_t)n;
+  uint32_t low = (uint32_t)product;
+  if (low < n) {
+    const uint32_t threshold = (0u - n) % n;
+    while (low < threshold) {
+      product = (uint64_t)rng.next() * (uint64_t)n;
+      low = (uint32_t)product;
+    }
+  }
+  return (int)(product >> 32);
+}
+
+// Match::chooseMoveAndContinue (match.cpp:208-251) incl. chooseMove (193-206), endGame (161-190)
+bool match_choose_move_and_continue(MatchRec &m) {
+  GameRec &g = m.g;
+  bool need_eval = false;
+  while (!need_eval) {
+    int choice;
+    if (m.random[g.to_play]) {
+      Mask lm;
+      legal_moves(m.root, lm);
+      int moves[kNumMoves], n = 0;
+      for (int id = 0; id < kNumMoves; ++id)
+        if (lm.get(id)) moves[n++] = id;
+      choice = moves[uniform_index(g.rng, (uint32_t)n)];
+    } else {
+      Tree &t = g.tree[g.to_play];
+      g.sims += t.searches_done;
+      g.moves += 1;
+      choice = choose_move(g, t, m.p[g.to_play], nullptr);
+      if (g.error) return true;
+    }
+    m.root = do_move(m.root, choice);
+    m.root_depth += 1;
+    Mask lm;
+    const bool lines = legal_moves(m.root, lm);
+    if (lm.count() == 0) {  // endGame
+      if (!lines)
+        g.result = kResultDraw;
+      else if (g.to_play == 1)
+        g.result = kResultLoss;
+      else
+        g.result = kResultWin;
+      drop_tree(g, g.tree[0]);
+      drop_tree(g, g.tree[1]);
+      g.pending.clear();
+      return true;
+    }
+    g.to_play = 1 - g.to_play;
+    if (m.random[g.to_play]) continue;
+    Tree &o = g.tree[g.to_play];
+    const Params &po = m.p[g.to_play];
+    if (!o.has_root) {
+      fresh_tree(g, o, po, m.root, m.root_depth);
+      o.searches_done = 0;
+      return tree_do_iteration(g, o, po, nullptr, nullptr);  // always false: root needs an eval
+    }
+    need_eval = receive_opponent_move(g, o, po, choice, m.root, m.root_depth);
+    if (!need_eval) need_eval = !tree_do_iteration(g, o, po, nullptr, nullptr);
+  }
+  return false;
+}
+
+// Match::doIteration (match.cpp:66-77)
+bool match_do_iteration(MatchRec &m, const float *eval, const float *probs) {
+  GameRec &g = m.g;
+  if (m.random[g.to_play]) return match_choose_move_and_continue(m);
+  bool done = tree_do_iteration(g, g.tree[g.to_play], m.p[g.to_play], eval, probs);
+  if (g.error) return true;
+  if (done) return match_choose_move_and_continue(m);
+  return false;
+}
+
+// Match::num_requests (match.cpp:44-48): the side to move's queue; a random player has none
+int match_num_requests(const MatchRec &m) {
+  if (m.random[m.g.to_play]) return 0;
+  return (int)m.g.pending.size();
+}
+
+struct PlayerCfg {
+  int model_id, max_searches, spe;
+  float c_puct, epsilon;
+  bool random;
+};
+
+struct TourneyRec {
+  std::vector<MatchRec *> matches;
+  std::vector<char> done;
+  std::map<int, PlayerCfg> players;
+  MT generator;  // std::mt19937 default seed (tourney.h:42)
+  int num_threads = 1;
+  TourneyRec() { generator.seed(5489u); }
+  ~TourneyRec() {
+    for (MatchRec *m : matches) delete m;
+  }
+};
+
 }  // namespace
 
 // ==========================================================================================
@@ -1102,6 +1218,126 @@ int orc_trainer_dump_tree(void *h, int game, int player, int64_t out[8], uint32_
     memcpy(words, g.arena[t.arena].data(), (size_t)n * 4);
   }
   return (int)t.used;
+}
+
+
+// ---- Tourney (tourney.h:12-46, tourney.cpp) ----------------------------------------------------
+void *orc_tourney_create(int num_threads, const char *log_folder) {
+  (void)log_folder;
+  TourneyRec *T = new TourneyRec();
+  T->num_threads = num_threads > 0 ? num_threads : 1;
+  return T;
+}
+void orc_tourney_destroy(void *h) { delete static_cast<TourneyRec *>(h); }
+
+void orc_tourney_add_player(void *h, int player_id, int model_id, int max_searches,
+                            int searches_per_eval, float c_puct, float epsilon, int random) {
+  static_cast<TourneyRec *>(h)->players[player_id] =
+      PlayerCfg{model_id, max_searches, searches_per_eval, c_puct, epsilon, random != 0};
+}
+
+// Tourney::addMatch (tourney.cpp:80-96): the match seed is the next draw of the tourney generator
+void orc_tourney_add_match(void *h, int player1, int player2, int logging) {
+  (void)logging;
+  TourneyRec *T = static_cast<TourneyRec *>(h);
+  MatchRec *m = new MatchRec();
+  const int pid[2] = {player1, player2};
+  int max_ms = 1, max_spe = 1;
+  for (int s = 0; s < 2; ++s) {
+    const PlayerCfg &c = T->players[pid[s]];
+    m->p[s] = Params{c.max_searches, c.spe, c.c_puct, c.epsilon, true, 0};
+    m->random[s] = c.random;
+    m->ids[s] = pid[s];
+    m->model_ids[s] = c.model_id;
+    if (c.max_searches > max_ms) max_ms = c.max_searches;
+    if (c.spe > max_spe) max_spe = c.spe;
+  }
+  const uint32_t words = (uint32_t)(((uint64_t)max_ms * 3 + 64) * (8 + 4 * 40));
+  m->p[0].arena_words = m->p[1].arena_words = words;
+  GameRec &g = m->g;
+  g.rng.seed(T->generator.next());
+  for (int a = 0; a < 3; ++a) g.arena[a].assign(words, 0);
+  g.tree[0].arena = 0;
+  g.tree[1].arena = 1;
+  g.spare = 2;
+  g.pending.reserve(max_spe);
+  m->root = start_state();
+  m->root_depth = 0;
+  T->matches.push_back(m);
+  T->done.push_back(0);
+}
+
+int orc_tourney_all_done(void *h) {
+  TourneyRec *T = static_cast<TourneyRec *>(h);
+  for (char d : T->done)
+    if (!d) return 0;
+  return 1;
+}
+
+static bool match_selected(const TourneyRec *T, size_t i, int id) {
+  return !T->done[i] && T->matches[i]->model_ids[T->matches[i]->g.to_play] == id;
+}
+
+int orc_tourney_num_requests(void *h, int id) {
+  TourneyRec *T = static_cast<TourneyRec *>(h);
+  int n = 0;
+  for (size_t i = 0; i < T->matches.size(); ++i)
+    if (match_selected(T, i, id)) n += match_num_requests(*T->matches[i]);
+  return n;
+}
+
+void orc_tourney_write_requests(void *h, float *game_states, int id) {
+  TourneyRec *T = static_cast<TourneyRec *>(h);
+  int64_t off = 0;
+  for (size_t i = 0; i < T->matches.size(); ++i) {
+    if (!match_selected(T, i, id)) continue;
+    MatchRec &m = *T->matches[i];
+    if (m.random[m.g.to_play]) continue;
+    GameRec &g = m.g;
+    Tree &t = g.tree[g.to_play];
+    for (size_t k = 0; k < g.pending.size(); ++k) {
+      encode_state(rec_state(rec(g, t, g.pending[k].leaf_off)), game_states + kStateSize * off);
+      ++off;
+    }
+  }
+}
+
+// Tourney::doIteration (tourney.cpp:54-72). The answer offset of match i is advanced by the
+// request count of match i-1 whenever match i itself is selected -- literally as written there
+// (SURVEY Q14); it equals the packing of writeRequests when the selected matches are adjacent.
+int orc_tourney_do_iteration(void *h, const float *eval, const float *probs, int id) {
+  TourneyRec *T = static_cast<TourneyRec *>(h);
+  const size_t n = T->matches.size();
+  std::vector<int64_t> offsets(n, 0);
+  int64_t off = 0;
+  for (size_t i = 1; i < n; ++i) {
+    if (match_selected(T, i, id)) off += match_num_requests(*T->matches[i - 1]);
+    offsets[i] = off;
+  }
+  omp_set_num_threads(T->num_threads);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (size_t i = 0; i < n; ++i) {
+    if (!match_selected(T, i, id)) continue;
+    if (match_do_iteration(*T->matches[i], eval + offsets[i], probs + kNumMoves * offsets[i]))
+      T->done[i] = 1;
+  }
+  for (size_t i = 0; i < n; ++i)
+    if (T->matches[i]->g.error) return -1;
+  return 0;
+}
+
+// Tourney::writeScores (tourney.cpp:34-42): "<player1> <player2> <score>" per finished match
+void orc_tourney_write_scores(void *h, const char *file) {
+  TourneyRec *T = static_cast<TourneyRec *>(h);
+  FILE *f = fopen(file, "w");
+  if (!f) return;
+  for (size_t i = 0; i < T->matches.size(); ++i) {
+    if (!T->done[i]) continue;
+    const MatchRec &m = *T->matches[i];
+    const float sc = game_score(m.g);
+    fprintf(f, "%d %d %s\n", m.ids[0], m.ids[1], sc == 0.5f ? "0.5" : (sc == 1.0f ? "1" : "0"));
+  }
+  fclose(f);
 }
 
 }  // extern "C"

@@ -57,6 +57,21 @@ void orc_trainer_counters(void *h, int64_t out[3]);
 int orc_trainer_dump_tree(void *h, int game, int player, int64_t out[8], uint32_t *words,
                           int cap);
 
+
+/* Tourney (corintho_ai/cpp/include/tourney.h:12-46) over Match (match.h:33-101): per-player
+ * search budgets, random players, requests batched per model id. do_iteration returns -1 on an
+ * arena/path overflow of any match, else 0. */
+void *orc_tourney_create(int num_threads, const char *log_folder);
+void orc_tourney_destroy(void *h);
+void orc_tourney_add_player(void *h, int player_id, int model_id, int max_searches,
+                            int searches_per_eval, float c_puct, float epsilon, int random);
+void orc_tourney_add_match(void *h, int player1, int player2, int logging);
+int orc_tourney_all_done(void *h);
+int orc_tourney_num_requests(void *h, int id);
+void orc_tourney_write_requests(void *h, float *game_states, int id);
+int orc_tourney_do_iteration(void *h, const float *eval, const float *probs, int id);
+void orc_tourney_write_scores(void *h, const char *file);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,9 @@ class _Lib:
     def trainer(self, *a, **kw):
         return _Trainer(self, *a, **kw)
 
+    def tourney(self, *a, **kw):
+        return _Tourney(self, *a, **kw)
+
 
 class _Trainer:
     """Mirror of the reference Trainer (cpp/include/trainer.h:17-53) over either library."""
@@ -169,6 +172,76 @@ class _Trainer:
 
     def avg_mate_length(self):
         return np.float32(self.L._t_mate(self.h))
+
+
+class _Tourney:
+    """Mirror of the reference Tourney (cpp/include/tourney.h:12-46) over either library."""
+
+    def __init__(self, L, num_threads=1, log_folder=""):
+        self.L = L
+        lib, p = L.lib, L.prefix
+
+        def fn(name, restype, argtypes):
+            f = getattr(lib, p + name)
+            f.restype, f.argtypes = restype, argtypes
+            return f
+
+        self._destroy = fn("tourney_destroy", None, [C.c_void_p])
+        self._add_player = fn("tourney_add_player", None,
+                              [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int])
+        self._add_match = fn("tourney_add_match", None, [C.c_void_p, C.c_int, C.c_int, C.c_int])
+        self._all_done = fn("tourney_all_done", C.c_int, [C.c_void_p])
+        self._nreq = fn("tourney_num_requests", C.c_int, [C.c_void_p, C.c_int])
+        self._wreq = fn("tourney_write_requests", None, [C.c_void_p, _f32p, C.c_int])
+        self._iter = fn("tourney_do_iteration", None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int])
+        self._wscores = fn("tourney_write_scores", None, [C.c_void_p, C.c_char_p])
+        self.h = fn("tourney_create", C.c_void_p, [C.c_int, C.c_char_p])(num_threads, log_folder.encode())
+        self.max_rows = 0   # upper bound of one model's request rows (sum of searches_per_eval)
+        self.model_ids = []
+        self._spe = {}
+
+    def close(self):
+        if self.h:
+            self._destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_player(self, player_id, model_id, max_searches=1600, searches_per_eval=16, c_puct=1.0,
+                   epsilon=0.25, random=False):
+        self._add_player(self.h, player_id, model_id, max_searches, searches_per_eval, c_puct,
+                         epsilon, int(random))
+        self._spe[player_id] = searches_per_eval
+        if model_id not in self.model_ids:
+            self.model_ids.append(model_id)
+
+    def add_match(self, player1, player2, logging=False):
+        self._add_match(self.h, player1, player2, int(logging))
+        self.max_rows += self._spe[player1] + self._spe[player2]
+
+    def all_done(self):
+        return bool(self._all_done(self.h))
+
+    def num_requests(self, model_id):
+        return self._nreq(self.h, model_id)
+
+    def write_requests(self, model_id):
+        n = self.num_requests(model_id)
+        out = np.zeros((max(n, 1), 70), np.float32)
+        self._wreq(self.h, out, model_id)
+        return out[:n]
+
+    def do_iteration(self, evals, probs, model_id):
+        self._iter(self.h, evals.ctypes.data, probs.ctypes.data, model_id)
+
+    def scores(self):
+        """writeScores (tourney.cpp:34-42) parsed back: rows (player1, player2, score)."""
+        import tempfile
+        with tempfile.NamedTemporaryFile("r", suffix=".txt") as f:
+            self._wscores(self.h, f.name.encode())
+            rows = [ln.split() for ln in open(f.name).read().splitlines() if ln.strip()]
+        return [(int(a), int(b), float(c)) for a, b, c in rows]
 
 
 class RefLib(_Lib):
@@ -266,3 +339,33 @@ def play_out(trainer, evaluator=synth_eval, to_play=-1, record=None, max_iters=1
         probs[:n] = p
         rounds += 1
     raise RuntimeError("play_out did not terminate")
+
+
+def play_tourney(tourney, evaluators=None, record=None, max_rounds=10_000_000):
+    """Drive a Tourney-like object exactly like rating/tourney.pyx:112-173 (play_games): for every
+    model id (negative ids are the random players' dummy models) fetch the requests, evaluate,
+    doIteration -- the answer buffers persist between calls as in the reference loop.
+
+    ``evaluators``: {model_id: f(rows) -> (eval, probs)}; default synth_eval for every model.
+    ``record``: optional list receiving (model_id, request_rows.copy()) per evaluation.
+    """
+    rows = max(tourney.max_rows, 1)
+    evals = np.zeros(rows, np.float32)
+    probs = np.zeros((rows, 96), np.float32)
+    rounds = 0
+    while not tourney.all_done():
+        for mid in tourney.model_ids:
+            n = tourney.num_requests(mid) if mid >= 0 else 0
+            if n > 0:
+                req = tourney.write_requests(mid)
+                if record is not None:
+                    record.append((mid, req.copy()))
+                f = (evaluators or {}).get(mid, synth_eval)
+                e, p = f(req)
+                evals[:n] = e
+                probs[:n] = p
+            tourney.do_iteration(evals, probs, mid)
+        rounds += 1
+        if rounds > max_rounds:
+            raise RuntimeError("play_tourney did not terminate")
+    return rounds

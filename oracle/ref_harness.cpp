@@ -3,7 +3,8 @@
 // C-ABI shim over the UNMODIFIED reference sources (compiled where they lie under
 // /root/reference by oracle/Makefile; nothing from the reference is copied into this repo).
 // It exposes the reference's public classes -- Game (cpp/include/game.h:19-135), Move codec
-// (cpp/include/move.h:21-67), Trainer (cpp/include/trainer.h:17-53) -- plus the rule tables of
+// (cpp/include/move.h:21-67), Trainer (cpp/include/trainer.h:17-53), Tourney
+// (cpp/include/tourney.h:12-46) -- plus the rule tables of
 // cpp/include/util.h as plain functions so that Python tests (ctypes) and bench.py's
 // cpu_baseline / --impl reference legs can run the real reference side by side with the
 // oracle restatement (oracle/corintho_oracle.cpp) and with the CUDA engine.
@@ -24,6 +25,7 @@
 
 #include "game.h"
 #include "move.h"
+#include "tourney.h"
 #include "trainer.h"
 #include "util.h"
 
@@ -217,6 +219,32 @@ float ref_trainer_avg_mate_length(void *h) {
 }
 void ref_trainer_write_scores(void *h, const char *file) {
   static_cast<Trainer *>(h)->writeScores(std::string(file));
+}
+
+
+// ---- Tourney (tourney.h:12-46; Match behind it, match.h:33-101) -------------------------------
+void *ref_tourney_create(int num_threads, const char *log_folder) {
+  return new Tourney(num_threads, std::string(log_folder ? log_folder : ""));
+}
+void ref_tourney_destroy(void *h) { delete static_cast<Tourney *>(h); }
+void ref_tourney_add_player(void *h, int player_id, int model_id, int max_searches,
+                            int searches_per_eval, float c_puct, float epsilon, int random) {
+  static_cast<Tourney *>(h)->addPlayer(player_id, model_id, max_searches, searches_per_eval, c_puct,
+                                       epsilon, random != 0);
+}
+void ref_tourney_add_match(void *h, int player1, int player2, int logging) {
+  static_cast<Tourney *>(h)->addMatch(player1, player2, logging != 0);
+}
+int ref_tourney_all_done(void *h) { return static_cast<Tourney *>(h)->all_done() ? 1 : 0; }
+int ref_tourney_num_requests(void *h, int id) { return static_cast<Tourney *>(h)->num_requests(id); }
+void ref_tourney_write_requests(void *h, float *game_states, int id) {
+  static_cast<Tourney *>(h)->writeRequests(game_states, id);
+}
+void ref_tourney_do_iteration(void *h, float *eval, float *probs, int id) {
+  static_cast<Tourney *>(h)->doIteration(eval, probs, id);
+}
+void ref_tourney_write_scores(void *h, const char *file) {
+  static_cast<Tourney *>(h)->writeScores(std::string(file));
 }
 
 }  // extern "C"

@@ -11,6 +11,9 @@ Outputs (small, committed):
                             evaluator oracle.pyoracle.synth_eval: request counts per round,
                             sha256 of every request row, samples (hash; full arrays for the
                             small configs), score, avg mate length
+  tests/golden/tourney.npz  digests of full Tourney runs (per-player budgets, random players):
+                            model id and row count of every evaluation, sha256 of all request
+                            rows, final scores
 """
 import os
 import sys
@@ -22,7 +25,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle.pyoracle import RefLib, synth_eval  # noqa: E402
-from util import TRAINER_GRID, grid_key, run_trainer, step_rnd  # noqa: E402
+from util import (TOURNEY_CASES, TRAINER_GRID, grid_key, make_tourney, run_tourney, run_trainer,  # noqa: E402
+                  step_rnd)
 
 
 def main():
@@ -54,6 +58,17 @@ def main():
                 out[k + "/gs"], out[k + "/ev"], out[k + "/pr"] = gs, ev, pr
         print(k, r["rounds"], r["num_samples"], r["score"])
     np.savez_compressed(os.path.join(HERE, "trainer.npz"), **out)
+    # Tourney / Match transcripts (tourney.h:12-46) under the same synthetic evaluator
+    tout = {}
+    for name in TOURNEY_CASES:
+        r = run_tourney(make_tourney(R, name))
+        tout[name + "/rounds"] = np.int64(r["rounds"])
+        tout[name + "/models"] = r["models"]
+        tout[name + "/counts"] = r["counts"]
+        tout[name + "/req_hash"] = np.frombuffer(r["req_hash"].encode(), np.uint8)
+        tout[name + "/scores"] = r["scores"]
+        print("tourney", name, r["rounds"], "rounds,", len(r["counts"]), "evaluations", r["scores"][:, 2])
+    np.savez_compressed(os.path.join(HERE, "tourney.npz"), **tout)
 
 
 if __name__ == "__main__":

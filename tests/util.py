@@ -66,3 +66,44 @@ TRAINER_GRID = [
 def grid_key(cfg):
     g, seed, ms, spe, cp, eps, testing = cfg
     return f"g{g}_s{seed}_m{ms}_e{spe}_c{cp}_x{eps}_t{int(testing)}"
+
+
+# ---- Tourney / Match -------------------------------------------------------------
+# name -> (players [(player_id, model_id, max_searches, spe, c_puct, epsilon, random)], matches)
+TOURNEY_CASES = {
+    "two_models": ([(0, 0, 64, 8, 1.0, 0.25, False), (1, 1, 48, 4, 1.5, 0.1, False)],
+                   [(0, 1), (1, 0), (0, 1), (1, 0), (0, 0)]),
+    "with_random": ([(0, 0, 64, 8, 1.0, 0.25, False), (1, 1, 48, 4, 1.5, 0.1, False),
+                     (2, -1, 1, 1, 1.0, 0.25, True), (3, 0, 32, 16, 1.0, 0.0, False)],
+                    [(0, 1), (1, 0), (0, 2), (2, 1), (3, 0), (1, 3), (2, 3), (2, 2)]),
+    "deeper": ([(10, 3, 200, 16, 1.0, 0.25, False), (11, 5, 120, 16, 2.0, 0.0, False),
+                (12, -2, 1, 1, 1.0, 0.25, True)],
+               [(10, 11), (11, 10), (12, 10), (11, 12), (10, 10)]),
+}
+
+
+def make_tourney(L, name, num_threads=2):
+    players, matches = TOURNEY_CASES[name]
+    t = L.tourney(num_threads, "")
+    for pl in players:
+        t.add_player(*pl)
+    for a, b in matches:
+        t.add_match(a, b)
+    return t
+
+
+def run_tourney(tourney, evaluators=None):
+    """Drive a Tourney-like object through rating/tourney.pyx:112-173's loop and digest what
+    the reference API exposes: per-evaluation model id + request rows, and the final scores."""
+    import hashlib
+    from oracle.pyoracle import play_tourney
+    rec = []
+    rounds = play_tourney(tourney, evaluators, record=rec)
+    h = hashlib.sha256()
+    for mid, req in rec:
+        h.update(np.int32(mid).tobytes())
+        h.update(np.ascontiguousarray(req, np.float32).tobytes())
+    return {"rounds": rounds, "models": np.array([m for m, _ in rec], np.int32),
+            "counts": np.array([r.shape[0] for _, r in rec], np.int32),
+            "req_hash": h.hexdigest(),
+            "scores": np.array(tourney.scores(), np.float64).reshape(-1, 3)}
