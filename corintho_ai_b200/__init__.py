@@ -88,6 +88,16 @@ def lib():
         "cb200_trainer_phase_profile": (i32, [vp, i32, vp]),
         "cb200_trainer_set_profiling": (i32, [vp, i32]),
         "cb200_trainer_kernel_times": (i32, [vp, vp, vp]),
+        "cb200_tourney_create": (vp, [i32, C.c_char_p]),
+        "cb200_tourney_destroy": (None, [vp]),
+        "cb200_tourney_add_player": (i32, [vp, i32, i32, i32, i32, f32, f32, i32]),
+        "cb200_tourney_add_match": (i32, [vp, i32, i32, i32]),
+        "cb200_tourney_all_done": (i32, [vp]),
+        "cb200_tourney_num_requests": (i32, [vp, i32]),
+        "cb200_tourney_write_requests": (i32, [vp, vp, i32]),
+        "cb200_tourney_do_iteration": (i32, [vp, vp, vp, i32, i32]),
+        "cb200_tourney_write_scores": (i32, [vp, C.c_char_p]),
+        "cb200_tourney_counters": (i32, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -345,3 +355,80 @@ class Trainer:
         words = np.zeros(cap, np.uint32)
         used = _check(lib().cb200_trainer_dump_tree(self._h, game, player, _ptr(out), _ptr(words), cap))
         return out, words[:min(used, cap)]
+
+
+class Tourney:
+    """Mirror of the reference Tourney (corintho_ai/cpp/include/tourney.h:12-46) as the Cython
+    binding exposes it (corintho_ai/rating/tourney.pyx:13-25): addPlayer, addMatch, all_done,
+    num_requests, writeRequests, doIteration, writeScores -- same argument meaning. Matches run on
+    the GPU (csrc/match.cuh); the network stays with the caller, one model id at a time."""
+
+    def __init__(self, num_threads=1, log_folder=""):
+        self._h = lib().cb200_tourney_create(int(num_threads), str(log_folder).encode())
+        if not self._h:
+            raise Corintho200Error(lib().cb200_last_error().decode())
+        self.model_ids = []   # in first-seen order, like tourney.pyx builds its list
+        self.max_rows = 0     # upper bound of one call's request rows
+        self._spe = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().cb200_tourney_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def addPlayer(self, player_id, model_id, max_searches=1600, searches_per_eval=16, c_puct=1.0,
+                  epsilon=0.25, random=False):
+        _check(lib().cb200_tourney_add_player(self._h, player_id, model_id, max_searches,
+                                              searches_per_eval, c_puct, epsilon, int(random)))
+        self._spe[player_id] = searches_per_eval
+        if model_id not in self.model_ids:
+            self.model_ids.append(model_id)
+
+    def addMatch(self, player1, player2, logging=False):
+        _check(lib().cb200_tourney_add_match(self._h, player1, player2, int(logging)))
+        self.max_rows += self._spe[player1] + self._spe[player2]
+
+    def all_done(self):
+        return bool(_check(lib().cb200_tourney_all_done(self._h)))
+
+    def num_requests(self, model_id):
+        return _check(lib().cb200_tourney_num_requests(self._h, int(model_id)))
+
+    def writeRequests(self, game_states, model_id):
+        _check(lib().cb200_tourney_write_requests(self._h, _ptr(game_states), int(model_id)))
+
+    def doIteration(self, evals, probs, model_id):
+        evals = np.ascontiguousarray(evals, np.float32)
+        probs = np.ascontiguousarray(probs, np.float32)
+        rows = min(evals.shape[0], probs.shape[0])
+        _check(lib().cb200_tourney_do_iteration(self._h, _ptr(evals), _ptr(probs), rows, int(model_id)))
+
+    def writeScores(self, filename):
+        _check(lib().cb200_tourney_write_scores(self._h, str(filename).encode()))
+
+    def counters(self):
+        out = np.zeros(4, np.int64)
+        _check(lib().cb200_tourney_counters(self._h, _ptr(out)))
+        return {"simulations": int(out[0]), "moves": int(out[1]), "leaf_evals": int(out[2]),
+                "iterations": int(out[3])}
+
+    # snake_case conveniences shared with the test drivers
+    add_player = addPlayer
+    add_match = addMatch
+    do_iteration = doIteration
+
+    def write_requests(self, model_id):
+        n = self.num_requests(model_id)
+        out = np.zeros((max(n, 1), STATE_SIZE), np.float32)
+        self.writeRequests(out, model_id)
+        return out[:n]
+
+    def scores(self):
+        import tempfile
+        with tempfile.NamedTemporaryFile("r", suffix=".txt") as f:
+            self.writeScores(f.name)
+            rows = [ln.split() for ln in open(f.name).read().splitlines() if ln.strip()]
+        return [(int(a), int(b), float(c)) for a, b, c in rows]

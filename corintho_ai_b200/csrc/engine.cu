@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <fstream>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -17,6 +18,7 @@
 #include "mlp_tc.cuh"
 #include "tree.cuh"
 #include "persistent.cuh"
+#include "match.cuh"
 
 using namespace cb200;
 
@@ -1203,6 +1205,198 @@ int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[
                        (size_t)n * 4, cudaMemcpyDeviceToHost));
   }
   return used;
+}
+
+
+// ==============================================================================================
+// Tourney (corintho_ai/cpp/include/tourney.h:12-46) over Match (match.h:33-101); device side in
+// match.cuh. The matches share the per-game storage of a trainer created when the first call
+// needs the device (all players and matches must have been added by then).
+struct cb200_tourney {
+  int num_threads = 1;
+  std::string log_folder;
+  std::map<int, MatchSide> players;
+  std::vector<std::pair<int, int>> matches;
+  cb200_trainer *t = nullptr;
+  MatchSide *d_sides = nullptr;
+  int32_t *d_pack_offs = nullptr, *d_iter_offs = nullptr;
+};
+
+static int tourney_ready(cb200_tourney *T) {
+  if (!T) return set_error(CB200_ERR_ARG, "null tourney");
+  if (T->t) return CB200_OK;
+  const int n = (int)T->matches.size();
+  if (n == 0) return set_error(CB200_ERR_STATE, "tourney has no matches");
+  int max_ms = 1, max_spe = 1;
+  std::vector<MatchSide> sides(2 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const int pid[2] = {T->matches[i].first, T->matches[i].second};
+    for (int s = 0; s < 2; ++s) {
+      sides[2 * i + s] = T->players[pid[s]];
+      if (sides[2 * i + s].max_searches > max_ms) max_ms = sides[2 * i + s].max_searches;
+      if (sides[2 * i + s].spe > max_spe) max_spe = sides[2 * i + s].spe;
+    }
+  }
+  if (max_spe > max_ms) max_ms = max_spe;
+  // match seeds = successive draws of a default-seeded std::mt19937 (tourney.h:42, tourney.cpp:86)
+  T->t = cb200_trainer_create_shard(n, 0, n, T->log_folder.c_str(), 5489, max_ms, max_spe, 1.0f,
+                                    0.25f, 0, 1);
+  if (!T->t) return CB200_ERR_CUDA;
+  cb200_trainer *t = T->t;
+  int rc = fetch_ctl(t);
+  if (rc != CB200_OK) return rc;
+  const CState st = start_state();
+  for (int g = 0; g < n; ++g) {
+    int32_t *c = t->h_ctl.data() + (size_t)g * kCtlWords;
+    c[MW_ROOT0] = (int32_t)(uint32_t)st.w0, c[MW_ROOT1] = (int32_t)(uint32_t)(st.w0 >> 32);
+    c[MW_ROOT2] = (int32_t)(uint32_t)st.w1, c[MW_ROOT3] = (int32_t)(uint32_t)(st.w1 >> 32);
+    c[MW_DEPTH] = 0;
+  }
+  CB_CUDA(cudaMemcpy(t->P.ctl, t->h_ctl.data(), t->h_ctl.size() * 4, cudaMemcpyHostToDevice));
+  if ((rc = dmalloc(&T->d_sides, sides.size())) != CB200_OK ||
+      (rc = dmalloc(&T->d_pack_offs, (size_t)n)) != CB200_OK ||
+      (rc = dmalloc(&T->d_iter_offs, (size_t)n)) != CB200_OK)
+    return rc;
+  CB_CUDA(cudaMemcpy(T->d_sides, sides.data(), sides.size() * sizeof(MatchSide), cudaMemcpyHostToDevice));
+  return CB200_OK;
+}
+
+// offsets + summary for one model id; h_summary = {requests, live matches, error, rows read}
+static int tourney_scan(cb200_tourney *T, int id) {
+  cb200_trainer *t = T->t;
+  k_match_scan<<<1, 32, 0, G().stream>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs,
+                                         t->d_summary);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  return fetch_summary(t);
+}
+
+cb200_tourney *cb200_tourney_create(int num_threads, const char *log_folder) {
+  if (num_threads <= 0) {
+    set_error(CB200_ERR_ARG, "cb200_tourney_create: num_threads must be positive");
+    return nullptr;
+  }
+  cb200_tourney *T = new cb200_tourney();
+  T->num_threads = num_threads;
+  T->log_folder = log_folder ? log_folder : "";
+  return T;
+}
+
+void cb200_tourney_destroy(cb200_tourney *T) {
+  if (!T) return;
+  cudaFree(T->d_sides), cudaFree(T->d_pack_offs), cudaFree(T->d_iter_offs);
+  if (T->t) cb200_trainer_destroy(T->t);
+  delete T;
+}
+
+int cb200_tourney_add_player(cb200_tourney *T, int player_id, int model_id, int max_searches,
+                             int searches_per_eval, float c_puct, float epsilon, int random) {
+  if (!T) return set_error(CB200_ERR_ARG, "null tourney");
+  if (T->t) return set_error(CB200_ERR_STATE, "players must be added before the first iteration");
+  if (!random && (max_searches <= 0 || searches_per_eval <= 0 || searches_per_eval > 64 ||
+                  !(c_puct > 0.0f) || !(epsilon >= 0.0f) || !(epsilon <= 1.0f)))
+    return set_error(CB200_ERR_ARG, "cb200_tourney_add_player: invalid search parameters");
+  MatchSide s;
+  s.model_id = model_id, s.max_searches = max_searches > 0 ? max_searches : 1;
+  s.spe = searches_per_eval > 0 ? searches_per_eval : 1, s.random = random ? 1 : 0;
+  s.c_puct = c_puct, s.epsilon = epsilon, s.player_id = player_id, s.pad = 0;
+  T->players[player_id] = s;
+  return CB200_OK;
+}
+
+int cb200_tourney_add_match(cb200_tourney *T, int player1, int player2, int logging) {
+  (void)logging;  // per-match text logs are not produced (out of scope)
+  if (!T) return set_error(CB200_ERR_ARG, "null tourney");
+  if (T->t) return set_error(CB200_ERR_STATE, "matches must be added before the first iteration");
+  if (!T->players.count(player1) || !T->players.count(player2))
+    return set_error(CB200_ERR_ARG, "cb200_tourney_add_match: unknown player id");
+  T->matches.emplace_back(player1, player2);
+  return CB200_OK;
+}
+
+int cb200_tourney_all_done(cb200_tourney *T) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  if ((rc = tourney_scan(T, 0x7fffffff)) != CB200_OK) return rc;
+  return T->t->h_summary[1] == 0 ? 1 : 0;
+}
+
+int cb200_tourney_num_requests(cb200_tourney *T, int id) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  if ((rc = tourney_scan(T, id)) != CB200_OK) return rc;
+  return T->t->h_summary[0];
+}
+
+int cb200_tourney_write_requests(cb200_tourney *T, float *game_states, int id) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  if (!game_states) return set_error(CB200_ERR_ARG, "null game_states");
+  if ((rc = tourney_scan(T, id)) != CB200_OK) return rc;
+  cb200_trainer *t = T->t;
+  const int n = t->h_summary[0];
+  if (n <= 0) return CB200_OK;
+  k_match_pack<<<(t->P.num_games + 7) / 8, 256, 0, G().stream>>>(t->P, T->d_sides, id,
+                                                                 T->d_pack_offs, t->d_rows);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  CB_CUDA(cudaMemcpyAsync(game_states, t->d_rows, (size_t)n * CB200_STATE_SIZE * sizeof(float),
+                          cudaMemcpyDeviceToHost, G().stream));
+  CB_CUDA(cudaStreamSynchronize(G().stream));
+  return CB200_OK;
+}
+
+int cb200_tourney_do_iteration(cb200_tourney *T, const float *eval, const float *probs, int rows,
+                               int id) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  if ((rc = tourney_scan(T, id)) != CB200_OK) return rc;
+  cb200_trainer *t = T->t;
+  const int need = t->h_summary[3];  // rows the matches will read (reference offset rule)
+  if (need > 0) {
+    if (!eval || !probs) return set_error(CB200_ERR_ARG, "requests pending but eval/probs null");
+    if (need > rows || (size_t)need > t->cap)
+      return set_error(CB200_ERR_ARG, "cb200_tourney_do_iteration: the answer offsets of "
+                                      "tourney.cpp:54-62 reach past the caller's buffers");
+    CB_CUDA(cudaMemcpyAsync(t->d_eval, eval, (size_t)need * sizeof(float), cudaMemcpyHostToDevice,
+                            G().stream));
+    CB_CUDA(cudaMemcpyAsync(t->d_probs, probs, (size_t)need * CB200_NUM_MOVES * sizeof(float),
+                            cudaMemcpyHostToDevice, G().stream));
+  }
+  const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
+  k_match_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, T->d_sides, t->d_eval, t->d_probs,
+                                                            T->d_iter_offs, id);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
+  if ((rc = tourney_scan(T, id)) != CB200_OK) return rc;
+  if (t->h_summary[2] != 0)
+    return set_error(t->h_summary[2], "a match overflowed its node arena / path buffer (raise "
+                                      "CB200_ARENA_NODES) or reached an impossible state");
+  ++t->iterations_done;
+  return CB200_OK;
+}
+
+// Tourney::writeScores (tourney.cpp:34-42): "<player1> <player2> <score>" per finished match
+int cb200_tourney_write_scores(cb200_tourney *T, const char *file) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  if (!file) return set_error(CB200_ERR_ARG, "null file name");
+  cb200_trainer *t = T->t;
+  if ((rc = fetch_ctl(t)) != CB200_OK) return rc;
+  std::ofstream f(file, std::ofstream::out);
+  if (!f) return set_error(CB200_ERR_ARG, std::string("cannot open ") + file);
+  for (int g = 0; g < t->P.num_games; ++g) {
+    const int32_t *c = t->h_ctl.data() + (size_t)g * kCtlWords;
+    if (!c[CW_DONE]) continue;
+    f << T->matches[g].first << ' ' << T->matches[g].second << ' ' << game_score(c[CW_RESULT]) << '\n';
+  }
+  return CB200_OK;
+}
+
+int cb200_tourney_counters(cb200_tourney *T, int64_t out[4]) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  return cb200_trainer_counters(T->t, out);
 }
 
 }  // extern "C"

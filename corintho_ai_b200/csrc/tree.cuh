@@ -47,7 +47,7 @@ constexpr int kTreeWarps = 4;  // games per CTA
 // The game-step kernel is compiled for several register budgets (resident CTAs per SM):
 // 8 -> 64 regs (32 warps/SM, spills; best while every SM is full), 5 -> 96, 4 -> 128,
 // 3 -> ~156 regs (no spills, shortest serial chain; best once few games are live).
-constexpr int kCtlWords = 16;
+constexpr int kCtlWords = 20;  // CW_* below; words 12-16 belong to Match (match.cuh)
 constexpr int kTreeCtlWords = 12;
 
 enum CtlWord {
@@ -753,7 +753,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     // sqrt(float) binds to double sqrt(double); small arguments come from a table
     // filled by the host with the same expression
     float v_sqrt;
-    if ((unsigned)cur_visits < (unsigned)kVsqrtCap)
+    if (P.vsqrt != nullptr && (unsigned)cur_visits < (unsigned)kVsqrtCap)
       v_sqrt = __ldg(P.vsqrt + cur_visits);
     else
       v_sqrt = __double2float_rn(__dmul_rn((double)P.c_puct, sqrt((double)(float)cur_visits)));

@@ -174,6 +174,31 @@ int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[16]);
 int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[8],
                             uint32_t *words, int cap);
 
+/* ---- Tourney: matches between players with their own search budgets (rating runs) ----------
+ * Replaces class Tourney (corintho_ai/cpp/include/tourney.h:12-46, bound by Cython in
+ * corintho_ai/rating/tourney.pyx:13-25) with class Match behind it (cpp/include/match.h:33-101):
+ * per-player max_searches / searches_per_eval / c_puct / epsilon, random players (no search, one
+ * uniform draw per move), requests batched per MODEL id. External-evaluator protocol exactly as
+ * rating/tourney.pyx:112-173 drives it: for every model id (negative ids = random players) ->
+ * num_requests, write_requests, evaluate, do_iteration; until all_done. The answer offsets follow
+ * tourney.cpp:54-62 literally. All players and matches must be added before the first call that
+ * needs the device (add_* return CB200_ERR_STATE afterwards); `logging` is accepted and ignored.
+ * `rows` = number of rows the caller's eval / probs buffers hold. */
+typedef struct cb200_tourney cb200_tourney;
+cb200_tourney *cb200_tourney_create(int num_threads, const char *log_folder);
+void cb200_tourney_destroy(cb200_tourney *t);
+int cb200_tourney_add_player(cb200_tourney *t, int player_id, int model_id, int max_searches,
+                             int searches_per_eval, float c_puct, float epsilon, int random);
+int cb200_tourney_add_match(cb200_tourney *t, int player1, int player2, int logging);
+int cb200_tourney_all_done(cb200_tourney *t);                 /* 1 / 0, negative = error */
+int cb200_tourney_num_requests(cb200_tourney *t, int model_id);
+int cb200_tourney_write_requests(cb200_tourney *t, float *game_states, int model_id);
+int cb200_tourney_do_iteration(cb200_tourney *t, const float *eval, const float *probs, int rows,
+                               int model_id);
+int cb200_tourney_write_scores(cb200_tourney *t, const char *file);
+/* out = {simulations, moves, leaf evaluations, do_iteration calls} over all matches */
+int cb200_tourney_counters(cb200_tourney *t, int64_t out[4]);
+
 #ifdef __cplusplus
 }
 #endif
