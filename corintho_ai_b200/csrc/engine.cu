@@ -7,7 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <fstream>
+#include <iomanip>
+#include <memory>
 #include <map>
 #include <string>
 #include <vector>
@@ -111,6 +114,11 @@ struct cb200_trainer {
   std::vector<int> g_begin, g_end;
   int32_t *d_gctr = nullptr;  // [n_groups][8] device counters (TreeParams::group_ctr)
   int32_t *h_gctr = nullptr;  // pinned mirror
+  // per-game text logs of the first num_logged games (trainer.cpp:243-250)
+  std::vector<std::unique_ptr<std::ofstream>> log_files;  // [P.n_logged]; null = could not open
+  std::vector<int> log_written;                           // records already formatted
+  std::vector<int32_t> h_log_count;
+  std::vector<uint32_t> h_log_rec;
   // persistent fused tail (persistent.cuh): CTA-private request/answer rows and the live list
   int ps_ctas = 0;                 // CTAs the device holds (one per SM)
   int32_t *d_ps_list = nullptr;    // [num_games]
@@ -286,6 +294,151 @@ int guard(cb200_trainer *t) {
 }  // namespace
 
 
+// ---- per-game text logs ------------------------------------------------------------------------
+// The statements below follow the reference's stream output one by one (same libstdc++
+// formatting, including the sticky std::fixed << setprecision(6) that SelfPlayer::writeEval
+// leaves on the stream), fed from the device's per-move records (tree.cuh, log_pre_move).
+static const char *str_result(int r) {  // strResult, util.cpp:5-25
+  switch (r) {
+    case kResultLoss: return "L";
+    case kResultDraw: return "D";
+    case kResultWin: return "W";
+    case kDeducedLoss: return "DL";
+    case kDeducedDraw: return "DD";
+    case kDeducedWin: return "DW";
+    default: return "N";
+  }
+}
+static void put_move(std::ostream &os, int id) {  // operator<<(Move), move.cpp:56-78
+  static const char cols[] = "abcd";  // getColName, util.cpp
+  if (id >= 48) {
+    const int piece = (id - 48) / 16, row = ((id - 48) % 16) / 4, col = (id - 48) % 4;
+    os << "BCA"[piece] << cols[col] << 4 - row;
+    return;
+  }
+  int r0, c0;
+  char dir;
+  if (id < 12) r0 = id / 3, c0 = id % 3, dir = 'R';            // right: (r, c) -> (r, c + 1)
+  else if (id < 24) r0 = (id - 12) / 4, c0 = (id - 12) % 4, dir = 'D';   // down
+  else if (id < 36) r0 = (id - 24) / 3, c0 = (id - 24) % 3 + 1, dir = 'L';  // left
+  else r0 = (id - 36) / 4 + 1, c0 = (id - 36) % 4, dir = 'U';  // up
+  os << cols[c0] << 4 - r0 << dir;
+}
+static void put_eval(std::ostream &os, int result, float evaluation, int visits) {  // writeEval
+  if (result != kResultNone) {
+    os << str_result(result);
+    return;
+  }
+  os << std::fixed << std::setprecision(6) << evaluation / visits;
+}
+static void put_game(std::ostream &os, const uint32_t w[4]) {  // operator<<(Game), game.cpp:98-139
+  const uint64_t w0 = (uint64_t)w[0] | ((uint64_t)w[1] << 32), w1 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+  for (int row = 0; row < 4; ++row) {
+    for (int col = 0; col < 4; ++col) {
+      const int b = row * 4 + col;  // cstate planes: base, column, capital, frozen (16 bits each)
+      os << (((w0 >> b) & 1) ? 'B' : ' ') << (((w0 >> (16 + b)) & 1) ? 'C' : ' ')
+         << (((w0 >> (32 + b)) & 1) ? 'A' : ' ') << (((w0 >> (48 + b)) & 1) ? '#' : ' ');
+      if (col < 3) os << '|';
+    }
+    if (row < 3) os << "\n-------------------\n";
+  }
+  os << '\n';
+  for (int player = 0; player < 2; ++player) {
+    os << "Player " << player + 1 << ": ";
+    os << "B: " << (int)((w1 >> (8 * (player * 3 + 0))) & 0xff) << ' ';
+    os << "C: " << (int)((w1 >> (8 * (player * 3 + 1))) & 0xff) << ' ';
+    os << "A: " << (int)((w1 >> (8 * (player * 3 + 2))) & 0xff) << '\n';
+  }
+  os << "Player " << (int)((w1 >> 48) & 0xff) + 1 << " to play";
+}
+static float bits_to_float(uint32_t b) {
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+static void format_log_record(std::ostream &os, const uint32_t *rec) {
+  // writePreMoveLogs (selfplayer.cpp:177-188)
+  os << "TURN " << (int32_t)rec[0] << "\nPLAYER " << (int32_t)(rec[1] + 1) << " TO PLAY\nVISITS: "
+     << (int32_t)rec[2] << '\n';
+  os << "POSITION EVALUATION: ";
+  put_eval(os, (int)rec[4], bits_to_float(rec[3]), (int)rec[2]);
+  os << '\n';
+  // writeMoves (selfplayer.cpp:137-175): main line (node.cpp:197-239), then the other moves
+  os << "LEGAL MOVES:\n";
+  for (uint32_t i = 0; i < rec[5]; ++i) {
+    const uint32_t *m = rec + kLogMain + 6 * i;
+    os << (int32_t)m[0] << ". ";
+    put_move(os, (int)m[1]);
+    os << " V: " << (int32_t)m[2] << " E: ";
+    if ((int)m[4] != kResultNone)
+      os << str_result((int)m[4]);
+    else
+      os << bits_to_float(m[3]) / (float)(int32_t)m[2];
+    os << " p: " << bits_to_float(m[5]) << '\t';
+  }
+  os << '\n';
+  struct MoveData {
+    int32_t visits;
+    float evaluation, probability;
+    int32_t move, result;
+    float eval_sum;
+  };
+  std::vector<MoveData> moves;
+  for (uint32_t j = 0; j < rec[6]; ++j) {
+    const uint32_t *k = rec + kLogKids + 5 * j;
+    const int32_t vis = (int32_t)k[1];
+    moves.push_back(MoveData{vis, bits_to_float(k[2]) / static_cast<float>(vis), bits_to_float(k[3]),
+                             (int32_t)k[0], (int32_t)k[4], bits_to_float(k[2])});
+  }
+  std::sort(moves.begin(), moves.end(), [](const MoveData &a, const MoveData &b) -> bool {
+    if (a.visits != b.visits) return a.visits > b.visits;
+    if (a.evaluation != b.evaluation) return a.evaluation > b.evaluation;
+    if (a.probability != b.probability) return a.probability > b.probability;
+    return a.move < b.move;
+  });
+  for (size_t i = 1; i < moves.size(); ++i) {
+    put_move(os, moves[i].move);
+    os << " V: " << moves[i].visits << " E: ";
+    put_eval(os, moves[i].result, moves[i].eval_sum, moves[i].visits);
+    os << " P: " << moves[i].probability << '\t';
+  }
+  os << '\n';
+  // writeMoveChoice (selfplayer.cpp:190-194)
+  os << "CHOSE MOVE ";
+  put_move(os, (int)rec[7]);
+  os << "\nNEW POSITION:\n";
+  put_game(os, rec + 8);
+  os << "\n\n";
+  if (rec[12] != 0) {  // endGame (selfplayer.cpp:217-224)
+    if ((int)rec[12] - 1 == kResultDraw)
+      os << "GAME IS DRAWN.\n";
+    else
+      os << "PLAYER " << (int32_t)rec[1] + 1 << " WON!\n";
+  }
+}
+
+// append the records written since the last call to the log files
+static int drain_logs(cb200_trainer *t) {
+  TreeParams &P = t->P;
+  if (P.n_logged <= 0) return CB200_OK;
+  t->h_log_count.resize(P.n_logged);
+  CB_CUDA(cudaMemcpy(t->h_log_count.data(), P.log_count, (size_t)P.n_logged * sizeof(int32_t),
+                     cudaMemcpyDeviceToHost));
+  for (int g = 0; g < P.n_logged; ++g) {
+    const int have = t->h_log_count[g], done = t->log_written[g];
+    if (have <= done) continue;
+    t->log_written[g] = have;
+    if (!t->log_files[g]) continue;
+    t->h_log_rec.resize((size_t)(have - done) * kLogWords);
+    CB_CUDA(cudaMemcpy(t->h_log_rec.data(), P.log_buf + ((size_t)g * kLogMaxMoves + done) * kLogWords,
+                       t->h_log_rec.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < have - done; ++k)
+      format_log_record(*t->log_files[g], t->h_log_rec.data() + (size_t)k * kLogWords);
+    t->log_files[g]->flush();
+  }
+  return CB200_OK;
+}
+
 // host-side initialisation: per-game seeds (trainer.cpp:238-256) and control blocks
 static int init_state(cb200_trainer *t) {
   TreeParams &P = t->P;
@@ -321,6 +474,10 @@ static int init_state(cb200_trainer *t) {
   CB_CUDA(cudaMemsetAsync(t->d_probs, 0, t->cap * CB200_NUM_MOVES * sizeof(float), s));
   CB_CUDA(cudaMemsetAsync(t->d_gctr, 0, (size_t)t->n_groups * 8 * sizeof(int32_t), s));
   CB_CUDA(cudaStreamSynchronize(s));
+  if (P.n_logged > 0) {
+    CB_CUDA(cudaMemset(P.log_count, 0, (size_t)P.n_logged * sizeof(int32_t)));
+    std::fill(t->log_written.begin(), t->log_written.end(), 0);
+  }
   t->iterations_done = 0;
   t->ps_active = false, t->ps_from_lockstep = false, t->ps_n = 0, t->ps_cur = 0;
   return CB200_OK;
@@ -390,7 +547,6 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
                                           const char *log_folder, int seed, int max_searches,
                                           int searches_per_eval, float c_puct, float epsilon,
                                           int num_logged, int testing) {
-  (void)num_logged;
   // the reference only assert()s these (trainer.cpp:25-34); here they are hard errors
   if (num_games <= 0 || total_games < num_games || first_game < 0 ||
       first_game + num_games > total_games || max_searches <= 0 || searches_per_eval <= 0 ||
@@ -461,6 +617,25 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
          cudaMemcpy(d_vsqrt, vs.data(), sizeof(float) * kVsqrtCap, cudaMemcpyHostToDevice) ==
              cudaSuccess;
     P.vsqrt = d_vsqrt;
+  }
+  if (ok) {
+    // logged games = global indices [0, num_logged) (trainer.cpp:243-250) that fall in this shard
+    long long nl = (long long)num_logged - first_game;
+    if (nl < 0) nl = 0;
+    if (nl > num_games) nl = num_games;
+    P.n_logged = (int)nl;
+    if (P.n_logged > 0) {
+      ok = dmalloc(&P.log_buf, (size_t)P.n_logged * kLogMaxMoves * kLogWords) == CB200_OK &&
+           dmalloc(&P.log_count, (size_t)P.n_logged) == CB200_OK;
+      t->log_written.assign(P.n_logged, 0);
+      for (int i = 0; i < P.n_logged; ++i) {
+        // like the reference, a missing folder silently produces no log
+        auto f = std::make_unique<std::ofstream>(
+            t->log_folder + "/game_" + std::to_string(first_game + i) + ".txt", std::ofstream::out);
+        if (!f->is_open()) f.reset();
+        t->log_files.push_back(std::move(f));
+      }
+    }
   }
   if (!ok) {
     if (last_error_ref().empty()) set_error(CB200_ERR_CUDA, "allocation failed");
@@ -579,6 +754,7 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaSetDevice(t->device);
   for (cudaEvent_t e : t->ev_pool) cudaEventDestroy(e);
   TreeParams &P = t->P;
+  cudaFree(P.log_buf), cudaFree(P.log_count);
   cudaFree(t->d_ps_list), cudaFree(t->d_ps_out), cudaFree(t->d_ps_eval[0]), cudaFree(t->d_ps_eval[1]);
   cudaFree(t->d_ps_probs[0]), cudaFree(t->d_ps_probs[1]);
   cudaFree(t->d_ps_packed), cudaFreeHost(t->h_ps_out);
@@ -641,6 +817,7 @@ int cb200_trainer_do_iteration(cb200_trainer *t, const float *eval, const float 
   if ((rc = iterate(t, t->d_eval, t->d_probs, to_play)) != CB200_OK) return rc;
   if ((rc = scan(t, to_play)) != CB200_OK) return rc;
   if ((rc = fetch_summary(t)) != CB200_OK) return rc;
+  if ((rc = drain_logs(t)) != CB200_OK) return rc;
   return t->h_summary[1] == 0 ? 1 : 0;
 }
 
@@ -1153,6 +1330,10 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
   if (!testing) {
     rc = run_selfplay_groups(t, max_iterations);
     t->stagger_div = saved_div;
+    if (rc >= 0) {
+      const int lr = drain_logs(t);
+      if (lr != CB200_OK) return lr;
+    }
     return rc;
   }
   // two-model (gating match) mode: single lock-step group, requests packed per side
@@ -1181,6 +1362,7 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
     }
   }
   t->stagger_div = saved_div;
+  if (rc == CB200_OK) rc = drain_logs(t);
   return rc != CB200_OK ? rc : result;
 }
 

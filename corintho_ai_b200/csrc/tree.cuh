@@ -85,6 +85,11 @@ struct TreeParams {
   // one launch parks (keeps its partial request list, asks for no evaluation) and resumes in the
   // next launch, so that one long iteration does not hold back every other game; 0 = never
   int yield_budget;
+  // per-game text logs (selfplayer.cpp:124-204): the first n_logged games of this trainer write
+  // one record per move (layout: kLog* below) that the host formats; null = no logged games
+  int n_logged;
+  uint32_t *log_buf;         // [n_logged][kLogMaxMoves][kLogWords]
+  int32_t *log_count;        // [n_logged] records written
   // optional straggler instrumentation (null = off): [0..2] max cycles of one warp in ingest /
   // search / move phases, [3..5] summed cycles, [6] rolled-back searches, [7] words re-rooted
   unsigned long long *phase_prof;
@@ -1115,6 +1120,78 @@ __device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &
   return true;
 }
 
+// ---- per-move log records (SelfPlayer::writePreMoveLogs / writeMoves / writeMoveChoice,
+// selfplayer.cpp:124-204; Node::printMainLine, node.cpp:197-239). The device stores the numbers,
+// the host prints them with the reference's stream formatting (engine.cu, format_log_record).
+// Record: [0] root depth, [1] to_play, [2] root visits, [3] root evaluation bits, [4] root
+// result, [5] main-line entries, [6] visited root children, [7] chosen move, [8..11] position
+// after the move, [12] 0 or 1 + game result when the move ended the game;
+// main line at kLogMain: {depth, move, visits, evaluation bits, result, probability bits};
+// children at kLogKids: {move, visits, evaluation bits, probability bits, result}.
+constexpr int kLogWords = 1024, kLogMain = 16, kLogMainMax = 64, kLogKids = kLogMain + 6 * kLogMainMax;
+constexpr int kLogMaxMoves = 130;
+static_assert(kLogKids + 5 * CB200_NUM_MOVES <= kLogWords, "log record too small");
+
+__device__ __forceinline__ uint32_t *log_record(const Ctx &c, const TreeParams &P) {
+  if (P.log_buf == nullptr) return nullptr;
+  const int g = (int)((c.tree_ctl - P.tree) / (2 * kTreeCtlWords));
+  if (g >= P.n_logged) return nullptr;
+  const int k = P.log_count[g];
+  if (k >= kLogMaxMoves) return nullptr;
+  return P.log_buf + ((size_t)g * kLogMaxMoves + k) * kLogWords;
+}
+
+__device__ __noinline__ void log_pre_move(const uint32_t *base, uint32_t root_off, int to_play,
+                                          int root_visits, float root_eval, int root_result,
+                                          uint32_t *rec) {
+  const uint32_t *r = base + root_off;
+  rec[0] = (r[4] >> 8) & 0xffu, rec[1] = (uint32_t)to_play, rec[2] = (uint32_t)root_visits;
+  rec[3] = __float_as_uint(root_eval), rec[4] = (uint32_t)root_result;
+  {  // visited children of the root, in edge order
+    const int n = (int)(r[4] & 0xffu);
+    const float denom = __uint_as_float(r[5]);
+    int nk = 0;
+    for (int e = 0; e < n; ++e) {
+      const uint4 s = ld4(r + 8 + 4 * e);
+      if (!s3_has(s.w)) continue;
+      uint32_t *k = rec + kLogKids + 5 * nk++;
+      k[0] = (uint32_t)s3_move(s.w), k[1] = s.y, k[2] = s.x;
+      k[3] = __float_as_uint(__fmul_rn((float)s3_prior(s.w), denom)), k[4] = (uint32_t)s3_result(s.w);
+    }
+    rec[6] = (uint32_t)nk;
+  }
+  int nm = 0;
+  uint32_t node = root_off;
+  while (nm < kLogMainMax) {  // Node::printMainLine
+    const uint32_t *rn = base + node;
+    const int n = (int)(rn[4] & 0xffu);
+    const float denom = __uint_as_float(rn[5]);
+    int best = -1, max_visits = 0;
+    float max_eval = 0.0f, prob = 0.0f;
+    uint4 bs = make_uint4(0, 0, 0, 0);
+    for (int e = 0; e < n; ++e) {
+      const uint4 s = ld4(rn + 8 + 4 * e);
+      if (!s3_has(s.w)) continue;
+      const int cr = s3_result(s.w), vis = (int)s.y;
+      const float ev = __uint_as_float(s.x);
+      if (cr == kDeducedLoss || cr == kResultLoss) {
+        best = e, max_visits = vis, prob = __fmul_rn((float)s3_prior(s.w), denom), bs = s;
+        break;
+      }
+      if (vis > max_visits || (vis == max_visits && ev > max_eval)) {
+        best = e, max_visits = vis, max_eval = ev, bs = s;
+        prob = __fmul_rn((float)s3_prior(s.w), denom);
+      }
+    }
+    if (best < 0) break;
+    uint32_t *m = rec + kLogMain + 6 * nm++;
+    m[0] = ((rn[4] >> 8) & 0xffu) + 1u, m[1] = (uint32_t)s3_move(bs.w), m[2] = (uint32_t)max_visits;
+    m[3] = __float_as_uint(max_eval), m[4] = (uint32_t)s3_result(bs.w), m[5] = __float_as_uint(prob);
+    node = bs.z;
+  }
+  rec[5] = (uint32_t)nm;
+}
+
 // ---- SelfPlayer::chooseMoveAndContinue (selfplayer.cpp:246-291) -----------------------------
 // defer_search (fused mode only): after handing the move to the opponent, do not run the
 // opponent's searches inside this call; the next game step finds no pending answers and
@@ -1134,6 +1211,12 @@ __device__ __forceinline__ int choose_move_and_continue(Ctx &c, const TreeParams
     if (c.d_moves > 128) {  // no Corintho game has this many plies: refuse to spin
       c.error = CB200_ERR_STATE;
       return kTurnOver;
+    }
+    uint32_t *log_rec = log_record(c, P);
+    if (log_rec != nullptr) {
+      if (c.lane == 0)
+        log_pre_move(c.base, c.root_off, c.to_play, c.root_visits, c.root_eval, c.root_result, log_rec);
+      __syncwarp();
     }
     int choice;
     if (!P.testing) {  // SelfPlayer::chooseMove (selfplayer.cpp:234-244)
@@ -1156,6 +1239,16 @@ __device__ __forceinline__ int choose_move_and_continue(Ctx &c, const TreeParams
     }
     if (c.error) return kTurnOver;
     __syncwarp();
+    if (log_rec != nullptr && c.lane == 0) {  // writeMoveChoice + endGame's result line
+      const uint4 h = ld4(c.base + c.root_off);
+      log_rec[7] = (uint32_t)choice, log_rec[8] = h.x, log_rec[9] = h.y, log_rec[10] = h.z, log_rec[11] = h.w;
+      int res = 0;
+      if (r_terminal(c.root_result))
+        res = 1 + (c.root_result == kResultDraw ? kResultDraw : (c.to_play == 1 ? kResultLoss : kResultWin));
+      log_rec[12] = (uint32_t)res;
+      __threadfence();
+      P.log_count[(c.tree_ctl - P.tree) / (2 * kTreeCtlWords)] += 1;
+    }
     if (r_terminal(c.root_result)) {  // endGame (selfplayer.cpp:206-232)
       if (c.root_result == kResultDraw)
         c.result = kResultDraw;

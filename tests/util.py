@@ -107,3 +107,12 @@ def run_tourney(tourney, evaluators=None):
             "counts": np.array([r.shape[0] for _, r in rec], np.int32),
             "req_hash": h.hexdigest(),
             "scores": np.array(tourney.scores(), np.float64).reshape(-1, 3)}
+
+
+# ---- per-game text logs: name -> (Trainer kwargs, first to_play of the driver) ----
+LOG_CASES = {
+    "train": (dict(num_games=5, seed=7, max_searches=40, searches_per_eval=8, c_puct=1.0, epsilon=0.25,
+                   num_logged=3), -1),
+    "test": (dict(num_games=4, seed=11, max_searches=32, searches_per_eval=4, c_puct=1.5, epsilon=0.0,
+                  num_logged=2, testing=True), 0),
+}
