@@ -78,6 +78,8 @@ typedef struct cb200_trainer cb200_trainer;
  *                  epsilon, num_logged, num_threads, testing)        trainer.cpp:18-37
  * Game i is seeded with the i-th output of mt19937(seed) and has parity i%2 (trainer.cpp:238-256).
  * num_threads is accepted for signature compatibility (the GPU engine has no host threads).
+ * The first num_logged games write log_folder/game_<i>.txt like the reference
+ * (selfplayer.cpp:124-204; a folder that does not exist silently yields no log).
  * Returns NULL on error. */
 cb200_trainer *cb200_trainer_create(int num_games, const char *log_folder, int seed,
                                     int max_searches, int searches_per_eval, float c_puct,
