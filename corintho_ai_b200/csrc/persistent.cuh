@@ -24,13 +24,19 @@ constexpr size_t ps_smem_bytes() {
 }
 constexpr size_t kPsTreeSmemOff = (kTcSmemBytes + 127) / 128 * 128;
 
-// live games in ascending index order (single thread: a few thousand flags, once per switch)
+// live games in ascending index order: one warp, 32 flags per trip, ballot-ordered append
 __global__ void k_live_list(TreeParams P, int32_t *__restrict__ list, int32_t *__restrict__ count) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
   int n = 0;
-  for (int g = 0; g < P.num_games; ++g)
-    if (!P.ctl[(size_t)g * kCtlWords + CW_DONE]) list[n++] = g;
-  *count = n;
+  for (int g0 = 0; g0 < P.num_games; g0 += 32) {
+    const int g = g0 + lane;
+    const bool live = g < P.num_games && !P.ctl[(size_t)g * kCtlWords + CW_DONE];
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (live) list[n + __popc(m & ((1u << lane) - 1u))] = g;
+    n += __popc(m);
+  }
+  if (lane == 0) *count = n;
 }
 
 // kGames = 8 (256 threads, one network tile) or 16 (512 threads, two tiles; the network is run
