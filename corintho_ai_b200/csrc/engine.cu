@@ -127,7 +127,7 @@ struct cb200_trainer {
   float *d_ps_eval[2] = {nullptr, nullptr};   // [ps_ld] answers, ping-pong between launches
   float *d_ps_probs[2] = {nullptr, nullptr};  // [96][ps_ld] move-major
   ulonglong2 *d_ps_packed = nullptr;          // [ps_ld] request rows (live within one round)
-  int ps_ld = 0;                   // rows = ps_ctas * 16 games * 16 requests
+  int ps_ld = 0;                   // rows = ps_ctas * 16 games * 16 requests * 2 models
   int ps_n = 0;                    // games in the live list
   int ps_cur = 0;                  // buffer holding the answers of the queued requests
   bool ps_active = false;          // the games now live in the persistent loop's rows
@@ -670,7 +670,7 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     t->ps_ctas = sms;
   }
-  t->ps_ld = t->ps_ctas * 16 * kPsRowsPerGame;
+  t->ps_ld = t->ps_ctas * 16 * kPsRowsPerGame * 2;  // x2: two row regions in two-model runs
   const size_t ps_rows = (size_t)t->ps_ld;
   if (dmalloc(&t->d_gctr, (size_t)t->n_groups * 8) != CB200_OK ||
       dmalloc(&t->d_ps_list, Gn) != CB200_OK || dmalloc(&t->d_ps_out, 8) != CB200_OK ||
@@ -1110,8 +1110,10 @@ static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit
   const int nxt = 1 - t->ps_cur;
   // one CTA per SM, games dealt round-robin (every CTA gets ceil or floor of ps_n / grid)
   const int grid = t->ps_n < t->ps_ctas ? t->ps_n : t->ps_ctas;
+  // two-model (gating match) runs: model 1 answers the other side's requests
+  const uint8_t *w1 = P.testing ? (const uint8_t *)t->nettc[1].w : nullptr;
   k_selfplay_persistent<kFp16, kGames><<<grid, kGames * 32, ps_smem_bytes<kGames>(), t->g_stream[0]>>>(
-      P, (const uint8_t *)t->nettc[0].w, t->d_ps_list, t->ps_n, ev0, pr0, pcs0, t->d_ps_eval[nxt],
+      P, (const uint8_t *)t->nettc[0].w, w1, t->d_ps_list, t->ps_n, ev0, pr0, pcs0, t->d_ps_eval[nxt],
       t->d_ps_probs[nxt], t->ps_ld, t->d_ps_packed, rounds, exit_done, t->iterations_done,
       t->d_ps_out);
   CB_LAUNCHED();
@@ -1336,7 +1338,25 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
     }
     return rc;
   }
-  // two-model (gating match) mode: single lock-step group, requests packed per side
+  // two-model (gating match) mode. With both networks on the tensor cores (same operand format)
+  // and every game resident at <= 16 per SM, the whole match runs in the persistent kernel
+  // (persistent.cuh; each game's requests go to the row region of the model that owns its side).
+  if ((t->iterations_done == 0 || t->ps_active) && t->precision[0] == 1 && t->precision[1] == 1 &&
+      t->nettc[0].fp16 == t->nettc[1].fp16 && t->P.spe <= kPsRowsPerGame &&
+      t->P.num_games <= t->ps_ctas * 16 && !getenv("CB200_NO_PERSISTENT")) {
+    CB_CUDA(cudaStreamSynchronize(G().stream));
+    if (!t->ps_active) {
+      if ((rc = ps_list_games(t)) != CB200_OK) return rc;
+      t->ps_active = true, t->ps_from_lockstep = false;
+    }
+    int rounds = 0;
+    bool all_done = false;
+    rc = run_persistent(t, max_iterations > 0 ? max_iterations : (1 << 30), &rounds, &all_done);
+    t->stagger_div = saved_div;
+    if (rc == CB200_OK) rc = drain_logs(t);
+    return rc != CB200_OK ? rc : (all_done ? 1 : 0);
+  }
+  // otherwise: single lock-step group, requests packed per side
   const int n_max = (int)t->cap;
   int done_iters = 0;
   int result = 0;

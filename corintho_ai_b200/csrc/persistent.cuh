@@ -48,22 +48,25 @@ __global__ void k_live_list(TreeParams P, int32_t *__restrict__ list, int32_t *_
 template <bool kFp16, int kGames>
 __global__ void __launch_bounds__(kGames * 32, 1)
     k_selfplay_persistent(TreeParams P, const uint8_t *__restrict__ W,
-                          const int32_t *__restrict__ game_list, int n_list,
-                          const float *eval0, const float *probs0, long pcs0, float *eval,
-                          float *probs, int ld, ulonglong2 *packed, int max_rounds, int exit_done,
-                          int iteration0, int32_t *out) {
+                          const uint8_t *__restrict__ W1, const int32_t *__restrict__ game_list,
+                          int n_list, const float *eval0, const float *probs0, long pcs0,
+                          float *eval, float *probs, int ld, ulonglong2 *packed, int max_rounds,
+                          int exit_done, int iteration0, int32_t *out) {
   static_assert(kGames == 8 || kGames == 16, "one or two network tiles per CTA");
   constexpr int kRows = kGames * kPsRowsPerGame;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ int32_t s_ctr[4];  // [0] requests of this round, [1] live games, [2] error, [3] stop
+  // [0] requests of this round (model 0), [1] live games, [2] error, [3] stop, [4] requests
+  // for model 1 (two-model runs: W1 != nullptr, every CTA owns two row regions of kRows)
+  __shared__ int32_t s_ctr[8];
   const bool net_thread = threadIdx.x < kTcThreads;
+  const bool two = W1 != nullptr;
   TcState S;
   if (net_thread) tc_setup(S, smem);
   WarpSm *sm_all = reinterpret_cast<WarpSm *>(smem + kPsTreeSmemOff);
   const int warp = threadIdx.x >> 5;
   const int slot = warp * gridDim.x + blockIdx.x;
   const int g = slot < n_list ? game_list[slot] : -1;
-  const int row0 = blockIdx.x * kRows;
+  const int row0 = blockIdx.x * kRows * (two ? 2 : 1);
   if (threadIdx.x == 0) s_ctr[2] = 0, s_ctr[3] = 0;  // published by the first barrier of the loop
   // games dealt to this CTA (all live at launch)
   int prev_live = ((int)n_list - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -71,16 +74,16 @@ __global__ void __launch_bounds__(kGames * 32, 1)
   if (prev_live < 0) prev_live = 0;
   int round = 0, live = 0;
   for (; round < max_rounds; ++round) {
-    if (threadIdx.x == 0) s_ctr[0] = 0, s_ctr[1] = 0;
+    if (threadIdx.x == 0) s_ctr[0] = 0, s_ctr[1] = 0, s_ctr[4] = 0;
     __syncthreads();
     if (g >= 0) {
       const bool ext = round == 0;  // answers of the requests queued before this launch
       run_game<true>(P, g, sm_all[warp], ext ? eval0 : eval, ext ? probs0 : probs, 1,
                      ext ? pcs0 : (long)ld, nullptr, -1, iteration0 + round, 0, &s_ctr[0],
-                     &s_ctr[1], &s_ctr[2], row0, packed);
+                     &s_ctr[1], &s_ctr[2], row0, packed, two ? kRows : 0);
     }
     __syncthreads();
-    const int n = s_ctr[0];
+    const int n = s_ctr[0], n1 = s_ctr[4];
     live = s_ctr[1];
     if (threadIdx.x == 0) {
       if (live < prev_live) atomicAdd(out + 3, prev_live - live);
@@ -91,6 +94,9 @@ __global__ void __launch_bounds__(kGames * 32, 1)
     // CTA's rows whenever the kernel stops (a later launch continues from there)
     if (net_thread && n > 0)
       tc_forward<kFp16>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
+    if (net_thread && n1 > 0)
+      tc_forward<kFp16>(S, W1, packed + row0 + kRows, n1, 0, eval + row0 + kRows,
+                        probs + row0 + kRows, ld);
     __syncthreads();  // answers visible to every warp; counters read before they are cleared
     if (live == 0 || s_ctr[3]) {
       ++round;

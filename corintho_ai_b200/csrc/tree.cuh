@@ -1299,7 +1299,7 @@ __device__ __forceinline__ void run_game(const TreeParams &P, int g, WarpSm &sm,
                                          const int32_t *__restrict__ offs, int to_play,
                                          int iteration, int stagger_div, int32_t *req_ctr,
                                          int32_t *live_ctr, int32_t *err_ctr, int row0,
-                                         ulonglong2 *packed) {
+                                         ulonglong2 *packed, int rows_per_model = 0) {
   int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
   if (!game_selected(ctl, to_play)) return;
   const bool training = (to_play != 0 && to_play != 1);
@@ -1358,6 +1358,10 @@ __device__ __forceinline__ void run_game(const TreeParams &P, int g, WarpSm &sm,
   if (c.error) done = true;
   store_tree(c);
   if (kFused) {
+    // two-model runs (rows_per_model > 0): the requests of the side now to move are answered by
+    // model (to_play + parity) & 1 (trainer.cpp:166, main.pyx:74-81); each model has its own row
+    // region and request counter (req_ctr[0], req_ctr[4])
+    if (rows_per_model > 0 && ((c.to_play + c.parity) & 1)) row0 += rows_per_model, req_ctr += 4;
     int base = 0;
     if (c.lane == 0) {
       if (c.n_pending > 0 && !c.yielded) base = atomicAdd(req_ctr, c.n_pending);

@@ -108,6 +108,50 @@ def test_fused_testing_mode_two_models(oracle):
     assert (t.game_results() != 0).all()
 
 
+def test_fused_testing_mode_two_models_persistent(oracle, monkeypatch):
+    """Same match with both networks on the tensor cores: the whole run happens in the persistent
+    kernel, where every CTA keeps one row region per model. Compared with the oracle driven by
+    the same two networks, and with the engine's own lock-step path."""
+    fa, fb = cb.fold_batchnorm(cb.random_weights(5)), cb.fold_batchnorm(cb.random_weights(6))
+    G, MS, SPE = 40, 48, 8
+
+    def engine_run():
+        t = cb.Trainer(G, "", 4, MS, SPE, 1.0, 0.0, 0, 1, True)
+        t.set_weights(fa, 0, "bf16")
+        t.set_weights(fb, 1, "bf16")
+        t.set_profiling(True)
+        assert t.run_selfplay(0)
+        return t
+
+    t = engine_run()
+    assert t.kernel_times()["fused_tail"]["launches"] >= 1
+    h = [cb.Trainer(G, "", 1, 16, SPE) for _ in range(2)]
+    h[0].set_weights(fa, 0, "bf16")
+    h[1].set_weights(fb, 0, "bf16")
+    o = oracle.trainer(num_games=G, seed=4, max_searches=MS, searches_per_eval=SPE, c_puct=1.0,
+                       epsilon=0.0, testing=True)
+    ev = np.zeros(G * SPE, np.float32)
+    pr = np.zeros((G * SPE, 96), np.float32)
+    done, tp = False, 0
+    while not done:
+        n = o.num_requests(tp)
+        if n:
+            e, p = h[tp].evaluate(o.write_requests(tp))
+            ev[:n], pr[:n] = e, p
+        done = o.do_iteration(ev, pr, tp)
+        tp = 1 - tp
+    oc, ec = oracle.counters(o), t.counters()
+    assert t.score().tobytes() == o.score().tobytes()
+    assert (oc["simulations"], oc["moves"], oc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
+    assert (t.game_results() != 0).all()
+    monkeypatch.setenv("CB200_NO_PERSISTENT", "1")
+    u = engine_run()
+    assert u.kernel_times()["fused_tail"]["launches"] == 0
+    assert (u.game_results() == t.game_results()).all() and u.score().tobytes() == t.score().tobytes()
+    uc = u.counters()
+    assert (uc["simulations"], uc["moves"], uc["leaf_evals"]) == (ec["simulations"], ec["moves"], ec["leaf_evals"])
+
+
 def test_bf16_tensor_core_network(oracle):
     """tcgen05 bf16 kernel. Stated tolerance (BASELINE.json north_star): 2e-2 in bf16 against
     the fp32 network; against a numpy emulation that rounds weights and activations to bf16 the
