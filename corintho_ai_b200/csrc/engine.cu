@@ -803,6 +803,9 @@ int cb200_trainer_do_iteration(cb200_trainer *t, const float *eval, const float 
                                int to_play) {
   int rc = guard(t);
   if (rc) return rc;
+  if (t->ps_active)
+    return set_error(CB200_ERR_STATE, "cb200_trainer_do_iteration: this trainer is in the middle of a "
+                                      "fused run (persistent kernel); call cb200_trainer_reset first");
   // offsets of the answers = prefix sums of the request counts they were written for
   if ((rc = scan(t, to_play)) != CB200_OK) return rc;
   if ((rc = fetch_summary(t)) != CB200_OK) return rc;
