@@ -59,7 +59,7 @@ def test_fused_selfplay_equals_oracle_driven_by_the_same_network(oracle):
                        cfg["c_puct"], cfg["epsilon"])
     fused.set_weights(flat, 0, "fp32")
     assert fused.run_selfplay(0, stagger=True)
-    helper = cb.Trainer(cfg["num_games"], "", 1, 16, cfg["searches_per_eval"])
+    helper = cb.Trainer(cfg["num_games"], "", 1, 64, cfg["searches_per_eval"])
     helper.set_weights(flat, 0, "fp32")
     o = oracle.trainer(**cfg)
     r = run_trainer(o, lambda req: helper.evaluate(req))
@@ -177,16 +177,19 @@ def test_bf16_tensor_core_network(oracle):
         assert e2.tobytes() == ev[:n].tobytes() and p2.tobytes() == pr[:n].tobytes()
 
 
-def test_fused_selfplay_bf16_equals_oracle_driven_by_the_same_network(oracle):
+@pytest.mark.parametrize("spe", [16, 20])
+def test_fused_selfplay_bf16_equals_oracle_driven_by_the_same_network(oracle, spe):
     """Same as the fp32 fused test with the tensor-core evaluator: the kernel is deterministic
-    per position, so the oracle fed with its outputs must reproduce the fused run exactly."""
+    per position, so the oracle fed with its outputs must reproduce the fused run exactly.
+    searches_per_eval 16 ends in the persistent kernel, 20 (more than its 16 rows per game)
+    stays in the lock-step loop."""
     flat = cb.fold_batchnorm(cb.random_weights(33))
-    cfg = dict(num_games=40, seed=5, max_searches=48, searches_per_eval=16, c_puct=1.0, epsilon=0.25)
+    cfg = dict(num_games=40, seed=5, max_searches=48, searches_per_eval=spe, c_puct=1.0, epsilon=0.25)
     fused = cb.Trainer(cfg["num_games"], "", cfg["seed"], cfg["max_searches"], cfg["searches_per_eval"],
                        cfg["c_puct"], cfg["epsilon"])
     fused.set_weights(flat, 0, "bf16")
     assert fused.run_selfplay(0, stagger=True)
-    helper = cb.Trainer(cfg["num_games"], "", 1, 16, cfg["searches_per_eval"])
+    helper = cb.Trainer(cfg["num_games"], "", 1, 64, cfg["searches_per_eval"])
     helper.set_weights(flat, 0, "bf16")
     o = oracle.trainer(**cfg)
     r = run_trainer(o, lambda req: helper.evaluate(req))
