@@ -592,6 +592,11 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
   if (t->stagger_div < 1) t->stagger_div = 1;
   const size_t Gn = (size_t)num_games;
   t->cap = Gn * searches_per_eval;
+  if (t->cap * CB200_NUM_MOVES >= (size_t)1 << 31) {  // the kernels index answers with 31 bits
+    set_error(CB200_ERR_ARG, "cb200_trainer_create: num_games * searches_per_eval too large for one trainer");
+    delete t;
+    return nullptr;
+  }
   bool ok = dmalloc(&P.arenas, Gn * 3 * P.arena_words) == CB200_OK &&
             dmalloc(&P.ctl, Gn * kCtlWords) == CB200_OK &&
             dmalloc(&P.tree, Gn * 2 * kTreeCtlWords) == CB200_OK &&

@@ -423,6 +423,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
                                           long pcs) {
   const int np_all = c.n_pending;
   const int lane = c.lane;
+  const int prs32 = (int)prs, pcs32 = (int)pcs;  // element offsets fit 31 bits (<= 96 * rows)
   for (int b0 = 0; b0 < np_all; b0 += 32) {
   const int np = min(32, np_all - b0);
   const float *eval_b = eval + b0;
@@ -450,9 +451,12 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
   __syncwarp();
   for (int k0 = 0; k0 < np;) {
     // chunk [k0, k1): as many leaves as fit in the scratch arrays
-    int k1 = k0 + 1;
     const int base_i = sm.l_pre[k0];
-    while (k1 < np && sm.l_pre[k1 + 1] - base_i <= kFlatCap) ++k1;
+    // first leaf k >= k0 whose end no longer fits (prefix sums are monotone): one ballot
+    const bool fits = lane >= k0 && lane < np && sm.l_pre[lane + 1] - base_i <= kFlatCap;
+    const unsigned fm = __ballot_sync(kFull, fits) >> k0;
+    int k1 = k0 + (fm == 0xffffffffu ? 32 : __ffs((int)~fm) - 1);
+    if (k1 == k0) k1 = k0 + 1;  // a single leaf always goes through (checked below)
     const int T = sm.l_pre[k1] - base_i;
     if (T > kFlatCap) {  // a single leaf with more than kFlatCap moves cannot exist (<= 96)
       c.error = CB200_ERR_STATE;
@@ -462,6 +466,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
     const int my_i0 = sm.l_pre[lane] - base_i;
     const int my_cnt = mine ? my_n : 0;
     const int nmax = __reduce_max_sync(kFull, my_cnt);
+#pragma unroll 4
     for (int j = 0; j < nmax; ++j)
       if (j < my_cnt) sm.own[my_i0 + j] = (uint8_t)lane;
     __syncwarp();
@@ -486,7 +491,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
         const int i = i0 + lane + 32 * u;
         w3[u] = w3n[u];
         pv4[u] = 0.0f;
-        if (i < T) pv4[u] = probs_b[(long)sm.own[i] * prs + (long)s3_move(w3[u]) * pcs];
+        if (i < T) pv4[u] = probs_b[(int)sm.own[i] * prs32 + s3_move(w3[u]) * pcs32];
       }
       if (i0 + 128 < T) {
 #pragma unroll
@@ -533,6 +538,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
     // scalar = 1/sum * (1 - eps), dscalar = 1/noise sum * eps
     {
       float sum = 0.0f, dsum = 0.0f;
+#pragma unroll 4
       for (int j = 0; j < nmax; ++j)
         if (j < my_cnt) {
           sum = __fadd_rn(sum, sm.fval[my_i0 + j]);
@@ -556,6 +562,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
     // ---- leaf phase 5: max (from 0.0f), denom = 511 / max
     {
       float mx = 0.0f;
+#pragma unroll 4
       for (int j = 0; j < nmax; ++j)
         if (j < my_cnt) mx = fmaxf(mx, sm.fval[my_i0 + j]);
       if (mine) sm.l_a[lane] = __fdiv_rn(511.0f, mx);
@@ -577,6 +584,7 @@ __device__ __forceinline__ void receive_eval(Ctx &c, const TreeParams &P, WarpSm
     // ---- leaf phase 7: denominator = 1 / float(sum of integer priors)
     {
       int qsum = 0;
+#pragma unroll 4
       for (int j = 0; j < nmax; ++j)
         if (j < my_cnt) qsum += __float_as_int(sm.dval[my_i0 + j]);
       if (mine) c.base[my_off + 5] = __float_as_uint(__double2float_rn(__drcp_rn((double)(float)qsum)));
