@@ -702,11 +702,14 @@ __device__ __forceinline__ bool puct_bounds(const uint4 s, float denominator, fl
                                             float &lo, float &hi) {
   // straight-line (select-only) code: result codes are classified with bit tables
   const uint32_t w = s.w;
-  const uint32_t cr = (w >> 16) & 7u;
-  const bool has = (w >> 20) & 1u;
-  // not selectable: pending/exhausted child, or a decided (non-drawn) result {1, 3, 4, 6}
-  const bool unsel = has && ((((w >> 19) | (0x5Au >> cr)) & 1u) != 0u);
-  const bool inexact = has && !unsel && ((0x24u >> cr) & 1u) == 0u;  // drawn {2, 5} is exact
+  // classify by the 5 bits {has_child, all_visited, result[3]} = w[20:16] with two bit tables.
+  // With a child: not selectable if pending/exhausted (all_visited) or decided and not drawn
+  // (results {1, 3, 4, 6}); the value is inexact unless the child is drawn {2, 5}.
+  const uint32_t cls = (w >> 16) & 31u;
+  constexpr uint32_t kUnsel = 0xFF5A0000u;    // has=1: allv=1 -> all; allv=0 -> results 1,3,4,6
+  constexpr uint32_t kInexact = 0x00810000u;  // has=1, allv=0, results 0 and 7 (7 is unused)
+  const bool unsel = (kUnsel >> cls) & 1u;
+  const bool inexact = (kInexact >> cls) & 1u;
   const float prob = __fmul_rn((float)s3_prior(w), denominator);
   const float pvf = __fadd_rn(__fmul_rn(prob, v_sqrt), 0.0f);
   const float fn = (float)(int)s.y;
@@ -787,7 +790,7 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
         const unsigned ma = __ballot_sync(kFull, ca), mb = __ballot_sync(kFull, cb);
         const unsigned mi = __ballot_sync(kFull, (ca && ina) || (cb && inb));
         if (mi == 0u || __popc(ma) + __popc(mb) == 1)
-          emin = __ffsll((long long)(((unsigned long long)mb << 32) | ma)) - 1;
+          emin = ma ? __ffs((int)ma) - 1 : 31 + __ffs((int)mb);
       }
     }
     if (emin < 0 && !none) {
