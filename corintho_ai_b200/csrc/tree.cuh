@@ -720,10 +720,11 @@ __device__ __forceinline__ bool puct_bounds(const uint4 s, float denominator, fl
   const float b = __fmul_rn(pvf, rb);
   const float u = __fadd_rn(a, b);
   const float d = __fmul_rn(__fadd_rn(fabsf(a), fabsf(b)), 0x1p-20f);
-  const float ulo = __fadd_rn(__fsub_rn(u, d), 0.0f);  // + 0.0f: no -0.0 keys
-  const float uhi = __fadd_rn(__fadd_rn(u, d), 0.0f);
-  lo = unsel ? -INFINITY : (inexact ? ulo : pvf);
-  hi = unsel ? -INFINITY : (inexact ? uhi : pvf);
+  // centre and half-width by selection, then one subtraction and one addition. Neither bound can
+  // be -0.0: b >= +0 makes u = a + b a +0.0 when it is zero, x - x is +0.0, and pvf was normalised.
+  const float centre = unsel ? -INFINITY : (inexact ? u : pvf);
+  const float half = inexact ? d : 0.0f;
+  lo = __fsub_rn(centre, half), hi = __fadd_rn(centre, half);
   return inexact;
 }
 // order-preserving float <-> signed int (for redux.sync.max.s32); no -0.0 inputs
