@@ -761,7 +761,8 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     c.work += 1;
     const uint32_t *r = c.base + node;
     const int n = cur_n;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    // lanes past the last slot hold a word that classifies as "not selectable"
+    const uint4 zero4 = make_uint4(0, 0, 0, kS3Has | kS3Allv);
     const uint4 sa = c.lane < n ? ld4(r + 8 + 4 * c.lane) : zero4;
     const uint4 sb = c.lane + 32 < n ? ld4(r + 8 + 4 * (c.lane + 32)) : zero4;
     const uint4 h1 = ld4(r + 4);
@@ -779,10 +780,10 @@ __device__ __forceinline__ void search(Ctx &c, const TreeParams &P, WarpSm &sm) 
     if (n <= 64) {
       // screening pass: interval per slot, decide when a single slot (or only exact ones) can
       // hold the maximum
-      float loa = -INFINITY, hia = -INFINITY, lob = -INFINITY, hib = -INFINITY;
-      bool ina = false, inb = false;
-      if (c.lane < n) ina = puct_bounds(sa, denominator, v_sqrt, loa, hia);
-      if (n > 32 && c.lane + 32 < n) inb = puct_bounds(sb, denominator, v_sqrt, lob, hib);
+      float loa, hia, lob = -INFINITY, hib = -INFINITY;
+      bool inb = false;
+      const bool ina = puct_bounds(sa, denominator, v_sqrt, loa, hia);  // every lane, no branch
+      if (n > 32) inb = puct_bounds(sb, denominator, v_sqrt, lob, hib);  // warp-uniform
       const float lmax = skey_inv(__reduce_max_sync(kFull, skey(fmaxf(loa, lob))));
       if (lmax == -INFINITY) {
         none = true;
