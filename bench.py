@@ -32,8 +32,8 @@ ALGO_BYTES_PER_SIM = 1670.0      # algorithmic bytes per simulat
 FLOP_PER_EVAL = 253400.0         # unpadded dense FLOPs per leaf evaluation
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_iterate launch with all 4096 games live
 # (65 536 simulations = 109.4 MB algorithmic), from the `ncu --set full` capture summarised in
-# profiles/r01_ncu_k_iterate_k_mlp_tc_v2.txt; the same capture gives 1.36 MB for k_mlp_tc
-NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 132.301312e6 + 50.268160e6, "network": 1.357056e6 + 0.004096e6}
+# profiles/r01_ncu_k_iterate_k_mlp_tc_v3.txt; the same capture gives 1.36 MB for k_mlp_tc
+NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 146.107136e6 + 54.567680e6, "network": 1.356800e6 + 0.008960e6}
 
 
 def peaks():
@@ -441,7 +441,7 @@ def run_engine_arm(args, rank, world, local_rank):
         roof = {"kernel": "k_iterate (tree search game step)", "bound": "hbm", "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_DENSE_LAUNCH["game_step"]}
     roof["traffic_note"] = ("bytes of one launch with every game live (ncu --set full, profiles/"
-                            "r01_ncu_k_iterate_k_mlp_tc_v2.txt): 182.6 MB DRAM for 109.4 MB algorithmic; "
+                            "r01_ncu_k_iterate_k_mlp_tc_v3.txt): 200.7 MB DRAM for 109.4 MB algorithmic; "
                             "`achieved` averages over all launches of the run, most of which carry fewer games")
     roof["peak_source"] = pk["source"]
     roof["kernel_time_share"] = share
