@@ -1,4 +1,6 @@
-"""Small end-to-end run of every kernel for compute-sanitizer (memcheck / racecheck)."""
+"""Small end-to-end run of every kernel and execution mode (fused lock-step, parking, persistent
+tail, two-model persistent, external evaluator, fp32 network, tourney, text logs): a quick
+sanity run on a GPU box, also suitable for compute-sanitizer where that is available."""
 import os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
