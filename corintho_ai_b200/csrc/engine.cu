@@ -439,19 +439,31 @@ static int drain_logs(cb200_trainer *t) {
   return CB200_OK;
 }
 
-// host-side initialisation: per-game seeds (trainer.cpp:238-256) and control blocks
+// std::mt19937(seed) state expansion (one thread per game; the recurrence is sequential)
+__global__ void k_seed_mt(int n, const uint32_t *__restrict__ seeds, uint32_t *__restrict__ mt) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  uint32_t *m = mt + (size_t)g * 624;
+  uint32_t prev = seeds[g];
+  m[0] = prev;
+  for (int i = 1; i < 624; ++i) {
+    prev = 1812433253u * (prev ^ (prev >> 30)) + (uint32_t)i;
+    m[i] = prev;
+  }
+}
+
+// initialisation: per-game seeds (trainer.cpp:238-256) from the host generator, MT19937 states
+// expanded on the device, control blocks
 static int init_state(cb200_trainer *t) {
   TreeParams &P = t->P;
   const size_t Gn = (size_t)P.num_games;
   std::vector<int32_t> ctl(Gn * kCtlWords, 0), tree(Gn * 2 * kTreeCtlWords, 0);
-  std::vector<uint32_t> mt(Gn * 624);
+  std::vector<uint32_t> seeds(Gn);
   HostMT gen;
   gen.seed((uint32_t)t->seed);
   for (int i = 0; i < P.first_game; ++i) gen.next();
   for (size_t g = 0; g < Gn; ++g) {
-    uint32_t *m = mt.data() + g * 624;
-    m[0] = gen.next();
-    for (int i = 1; i < 624; ++i) m[i] = mt_seed_word(m[i - 1], i);
+    seeds[g] = gen.next();
     int32_t *c = ctl.data() + g * kCtlWords;
     c[CW_PARITY] = (int)((P.first_game + g) & 1);
     c[CW_SPARE] = 2;
@@ -466,7 +478,11 @@ static int init_state(cb200_trainer *t) {
   cudaStream_t s = G().stream;
   CB_CUDA(cudaMemcpyAsync(P.ctl, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMemcpyAsync(P.tree, tree.data(), tree.size() * 4, cudaMemcpyHostToDevice, s));
-  CB_CUDA(cudaMemcpyAsync(P.mt, mt.data(), mt.size() * 4, cudaMemcpyHostToDevice, s));
+  // the seeds travel through the (still unused) request-offset buffer
+  CB_CUDA(cudaMemcpyAsync(t->d_offs, seeds.data(), Gn * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  k_seed_mt<<<(int)((Gn + 127) / 128), 128, 0, s>>>((int)Gn, (const uint32_t *)t->d_offs, P.mt);
+  CB_LAUNCHED();
+  CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemsetAsync(P.counters, 0, Gn * 4 * sizeof(long long), s));
   CB_CUDA(cudaMemsetAsync(t->d_offs, 0, Gn * sizeof(int32_t), s));
   CB_CUDA(cudaMemsetAsync(t->d_summary, 0, 4 * sizeof(int32_t), s));
