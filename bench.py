@@ -407,7 +407,7 @@ def run_engine_arm(args, rank, world, local_rank):
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
         e2e_sims += tr.counters()["simulations"]
-        h2d += flat.nbytes + G * (16 + 16 + 624) * 4
+        h2d += flat.nbytes + G * (20 + 24 + 1) * 4  # weights + control blocks, tree headers, seeds
         d2h += gs.nbytes + ev.nbytes + pr.nbytes
 
     # ---- aggregate over ranks: max time, summed work
@@ -473,7 +473,7 @@ def run_engine_arm(args, rank, world, local_rank):
         "config": workload_desc(args, world),
         "moves_per_sec": moves / (dev_ms * 1e-3), "leaf_evals_per_sec": evals / (dev_ms * 1e-3),
         "simulations_per_step": sims / args.steps, "iterations_per_step": iters / args.steps,
-        "ms_per_step_profiled": prof_ms / args.steps, "stream_groups": int(os.environ.get("CB200_GROUPS", 4 if G >= 2048 else (2 if G >= 512 else 1))),
+        "ms_per_step_profiled": prof_ms / args.steps, "stream_groups": int(os.environ.get("CB200_GROUPS", 6 if G >= 2048 else (2 if G >= 512 else 1))),
         "game_logic": game_logic,
         "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "seconds_per_step": e2e_s / args.steps,

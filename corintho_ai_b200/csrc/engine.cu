@@ -666,7 +666,7 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
   // stream groups for the fused loop
   // A launch ends when its slowest game does, so large batches are split over a few independent
   // streams (a group only waits for its own stragglers); CB200_GROUPS overrides.
-  int ng = num_games >= 2048 ? 4 : (num_games >= 512 ? 2 : 1);
+  int ng = num_games >= 2048 ? 6 : (num_games >= 512 ? 2 : 1);
   if (const char *env = getenv("CB200_GROUPS")) ng = atoi(env);
   if (ng < 1) ng = 1;
   while (ng > 1 && num_games / ng < 64) ng /= 2;
@@ -1224,6 +1224,10 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   if (ps_capacity > (long long)t->ps_ctas * 16) ps_capacity = (long long)t->ps_ctas * 16;
   const int stagger_span =
       t->stagger_div > 0 ? (t->P.first_game + t->P.num_games - 1) / t->stagger_div : 0;
+  // With several stream groups the game step runs in its 96-register build (four CTAs leave
+  // 16 K registers per SM) and the network in single-tile CTAs of 128 threads that fit beside
+  // them, so that one group's network overlaps the other groups' tree work (2-3 % per run).
+  const bool overlap = tc && ng > 1 && getenv("CB200_NO_OVERLAP") == nullptr;
   while (max_iterations <= 0 || done_iters < max_iterations) {
     if (!t->ps_active && ps_ok && live_games <= ps_capacity && t->iterations_done > stagger_span) {
       // evaluate the requests queued by the last lock-step game step, then list the live games
@@ -1283,7 +1287,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
           ProfScope ps(t, 2, st);
           if (tc)
             rc = launch_mlp_tc(t->nettc[model], t->d_packed + row0, ctr + (it & 1), 0, rows, t->d_eval + row0,
-                               t->d_probs + row0, (int)t->cap, ctr + ((it + 1) & 1), st, true);
+                               t->d_probs + row0, (int)t->cap, ctr + ((it + 1) & 1), st, true, overlap);
           else
             rc = launch_mlp_f32(t->net32[model], t->d_packed + row0, ctr + (it & 1), 0, rows, t->d_eval + row0,
                                 t->d_probs + (size_t)row0 * CB200_NUM_MOVES, ctr + ((it + 1) & 1), st, true);
@@ -1298,9 +1302,10 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
 #define CB_ITER(MB) \
   k_iterate<true, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, \
                                               t->stagger_div)
+          if (overlap) CB_ITER(5);
+          else
 #ifdef CB200_ALL_VARIANTS
           if (variant == 3) CB_ITER(3);
-          else if (variant == 5) CB_ITER(5);
           else if (variant == 6) CB_ITER(6);
           else if (variant == 7) CB_ITER(7);
           else if (variant == 8) CB_ITER(8);

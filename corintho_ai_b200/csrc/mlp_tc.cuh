@@ -199,7 +199,9 @@ __device__ __forceinline__ uint32_t pack16(float a, float b) {
 
 // Barrier of the 256 threads that run the network (named barrier 1, so that a larger CTA can keep
 // its other warps out of it; in k_mlp_tc it is the whole CTA).
-__device__ __forceinline__ void tc_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tc_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
 // Per-CTA state of the tensor-core network: barriers, TMEM allocation and the phase counters of
 // the mbarriers, so that tc_forward() can be called any number of times between tc_setup() and
@@ -207,12 +209,16 @@ __device__ __forceinline__ void tc_sync() { asm volatile("bar.sync 1, 256;" ::: 
 struct TcState {
   uint8_t *sA, *sW;
   uint32_t wbar0, mbar0, tmem_base;
+  int nthreads;        // threads running the network: 256 (two tiles) or 128 (one tile)
+  uint32_t tmem_cols;  // 128 TMEM columns per tile
   uint32_t wcount[2];  // completed waits per weight buffer
   uint32_t mcount;     // completed waits on this warpgroup's MMA barrier
 };
 constexpr size_t kTcStateSmemBytes = kTcSmemBytes;  // sA[2] | sW[2] | 4 mbarriers | tmem slot
 
-__device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem) {
+__device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem, int nthreads = kTcThreads) {
+  S.nthreads = nthreads;
+  S.tmem_cols = nthreads == kTcThreads ? kTcTmemCols : kTcTmemCols / 2;
   S.sA = smem;                                 // 2 x kTcABytes
   S.sW = smem + 2 * kTcABytes;                 // 2 x kTcLayerBytes
   uint64_t *bars = reinterpret_cast<uint64_t *>(S.sW + 2 * kTcLayerBytes);  // wbar[2], mbar[2]
@@ -227,12 +233,12 @@ __device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem) {
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "r"(kTcTmemCols)
+                 "r"(S.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  tc_sync();
+  tc_sync(S.nthreads);
   tc_fence_after();
   S.tmem_base = *tmem_slot;
   S.wcount[0] = S.wcount[1] = 0;
@@ -241,10 +247,10 @@ __device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem) {
 
 __device__ __forceinline__ void tc_teardown(TcState &S) {
   tc_fence_before();
-  tc_sync();
+  tc_sync(S.nthreads);
   if ((threadIdx.x >> 5) == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(S.tmem_base),
-                 "r"(kTcTmemCols)
+                 "r"(S.tmem_cols)
                  : "memory");
   }
 }
@@ -302,7 +308,7 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
   // make this thread's generic-proxy writes of A visible to the tensor core, then sync
   fence_proxy_async();
   tc_fence_before();
-  tc_sync();
+  tc_sync(S.nthreads);
   tc_fence_after();
   for (int layer = 0; layer < kTcLayers; ++layer) {
     const int b = layer & 1;
@@ -428,7 +434,7 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
     // weights/bias: publish, sync, refill the weight buffer two layers ahead
     fence_proxy_async();
     tc_fence_before();
-    tc_sync();
+    tc_sync(S.nthreads);
     tc_fence_after();
     if (t == 0 && layer + 2 < kTcLayers) {
       mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
@@ -453,6 +459,26 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int n_pairs = (n + 255) / 256;
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
     tc_forward<kFp16>(S, W, states, n, pair, eval, probs, probs_ld);
+  tc_teardown(S);
+}
+
+// One tile per CTA (128 threads, 16 K registers): small enough to share an SM with four 96-register
+// game-step CTAs, so that one stream group's network overlaps the other groups' tree work.
+template <bool kFp16>
+__global__ void __launch_bounds__(128, 4)
+    k_mlp_tc1(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
+              const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
+              float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int n = n_ptr ? *n_ptr : n_static;
+  if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;
+  TcState S;
+  tc_setup(S, smem, 128);
+  for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
+    const int rows = n - tile * 128 < 128 ? n - tile * 128 : 128;
+    tc_forward<kFp16>(S, W, states + tile * 128, rows, 0, eval + tile * 128, probs + tile * 128,
+                      probs_ld);
+  }
   tc_teardown(S);
 }
 
@@ -514,7 +540,7 @@ inline void net_tc_free(NetTC &net) {
 inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int32_t *d_n,
                          int n_static, int n_max, float *d_eval, float *d_probs, int probs_ld,
                          int32_t *zero2 = nullptr, cudaStream_t stream = nullptr,
-                         bool use_stream = false) {
+                         bool use_stream = false, bool single_tile = false) {
   static bool attr_set[16] = {false};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -527,6 +553,27 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
     attr_set[dev] = true;
   }
   if (n_max <= 0) return CB200_OK;
+  if (single_tile) {
+    static bool attr1[16] = {false};
+    if (dev < 16 && !attr1[dev]) {
+      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kTcSmemBytes));
+      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kTcSmemBytes));
+      attr1[dev] = true;
+    }
+    const int tiles = (n_max + 127) / 128;
+    const int g1 = tiles < sms ? tiles : sms;
+    if (net.fp16)
+      k_mlp_tc1<true><<<g1, 128, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+          (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
+    else
+      k_mlp_tc1<false><<<g1, 128, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+          (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
+    CB_LAUNCHED();
+    CB_CUDA(cudaGetLastError());
+    return CB200_OK;
+  }
   const int pairs = (n_max + 255) / 256;
   const int grid = pairs < 2 * sms ? pairs : 2 * sms;
   if (net.fp16)
