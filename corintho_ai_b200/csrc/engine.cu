@@ -1260,18 +1260,6 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       break;
     }
     const int yb = live_games >= yield_min_live ? yield_budget : 0;
-    // Register-budget variant of the game-step kernel. Measured on B200 (tools/sweep_yield.py,
-    // 4096 games x 800 sims): the 128-register build (no spills, 16 warps per SM, several waves
-    // while many games are live) beats the spilling high-occupancy builds (64-96 registers) by
-    // 10-25 % over the whole run and the 3-CTA build by 0.5 %, so it is the only one shipped;
-    // -DCB200_ALL_VARIANTS + CB200_FIXED_VARIANT=3..8 re-enable the others for experiments.
-#ifdef CB200_ALL_VARIANTS
-    int variant = 4;
-    if (const char *fv = getenv("CB200_FIXED_VARIANT")) {
-      variant = atoi(fv);
-      if (variant < 3 || variant > 8) variant = 4;
-    }
-#endif
     int batch = 32;
     if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
     for (int i = 0; i < batch; ++i) {
@@ -1302,16 +1290,10 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
 #define CB_ITER(MB) \
   k_iterate<true, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, \
                                               t->stagger_div)
+          // register budget of the game step (measured over whole runs): 128
+          // registers without spills, or 96 when network CTAs are to share the SM
           if (overlap) CB_ITER(5);
-          else
-#ifdef CB200_ALL_VARIANTS
-          if (variant == 3) CB_ITER(3);
-          else if (variant == 6) CB_ITER(6);
-          else if (variant == 7) CB_ITER(7);
-          else if (variant == 8) CB_ITER(8);
-          else
-#endif
-            CB_ITER(4);
+          else CB_ITER(4);
 #undef CB_ITER
           CB_LAUNCHED();
         }

@@ -44,9 +44,10 @@ constexpr int kPendWords = 2 + kMaxPath;  // leaf_off, path_len, path[kMaxPath]
 constexpr int kMaxSamples = 64;
 constexpr int kVsqrtCap = 2048;  // entries of the c_puct*sqrt(visits) table
 constexpr int kTreeWarps = 4;  // games per CTA
-// The game-step kernel is compiled for several register budgets (resident CTAs per SM):
-// 8 -> 64 regs (32 warps/SM, spills; best while every SM is full), 5 -> 96, 4 -> 128,
-// 3 -> ~156 regs (no spills, shortest serial chain; best once few games are live).
+// The lock-step game-step kernel k_iterate<fused, kMinBlocks> ships in two register budgets
+// (resident CTAs per SM): 4 -> 128 registers (no spills; the default) and 5 -> 96 registers
+// (leaves room on the SM for the single-tile network CTAs of mlp_tc.cuh when several stream
+// groups run); other budgets (64-156 registers) were measured and dropped.
 constexpr int kCtlWords = 20;  // CW_* below; words 12-16 belong to Match (match.cuh)
 constexpr int kTreeCtlWords = 12;
 

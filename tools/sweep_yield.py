@@ -13,9 +13,7 @@ for g in groups:
     t.set_weights(w, 0, "bf16")
     t.run_selfplay(0, stagger=False)  # warm-up: full run
     for b in budgets:
-        b, _, fv = b.partition("/")
-        if fv: os.environ["CB200_FIXED_VARIANT"] = fv
-        else: os.environ.pop("CB200_FIXED_VARIANT", None)
+        fv = ""
         y, _, ml = b.partition(":")
         os.environ["CB200_YIELD"] = y
         if ml: os.environ["CB200_YIELD_MIN_LIVE"] = ml
