@@ -356,7 +356,12 @@ static float bits_to_float(uint32_t b) {
   memcpy(&f, &b, 4);
   return f;
 }
+static void format_move_choice(std::ostream &os, const uint32_t *rec);
 static void format_log_record(std::ostream &os, const uint32_t *rec) {
+  if (rec[13] != 0) {  // a Match's random player: no pre-move section (match.cpp:213-215)
+    format_move_choice(os, rec);
+    return;
+  }
   // writePreMoveLogs (selfplayer.cpp:177-188)
   os << "TURN " << (int32_t)rec[0] << "\nPLAYER " << (int32_t)(rec[1] + 1) << " TO PLAY\nVISITS: "
      << (int32_t)rec[2] << '\n';
@@ -403,6 +408,9 @@ static void format_log_record(std::ostream &os, const uint32_t *rec) {
     os << " P: " << moves[i].probability << '\t';
   }
   os << '\n';
+  format_move_choice(os, rec);
+}
+static void format_move_choice(std::ostream &os, const uint32_t *rec) {
   // writeMoveChoice (selfplayer.cpp:190-194)
   os << "CHOSE MOVE ";
   put_move(os, (int)rec[7]);
@@ -648,6 +656,7 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     if (P.n_logged > 0) {
       ok = dmalloc(&P.log_buf, (size_t)P.n_logged * kLogMaxMoves * kLogWords) == CB200_OK &&
            dmalloc(&P.log_count, (size_t)P.n_logged) == CB200_OK;
+      if (ok) ok = cudaMemset(P.log_count, 0, (size_t)P.n_logged * sizeof(int32_t)) == cudaSuccess;
       t->log_written.assign(P.n_logged, 0);
       for (int i = 0; i < P.n_logged; ++i) {
         // like the reference, a missing folder silently produces no log
@@ -1430,6 +1439,9 @@ struct cb200_tourney {
   std::string log_folder;
   std::map<int, MatchSide> players;
   std::vector<std::pair<int, int>> matches;
+  std::vector<char> logging;  // per match (Tourney::addMatch, tourney.cpp:80-96)
+  std::vector<std::unique_ptr<std::ofstream>> log_files;  // per logged match; null = not opened
+  std::vector<int> log_written;
   cb200_trainer *t = nullptr;
   MatchSide *d_sides = nullptr;
   int32_t *d_pack_offs = nullptr, *d_iter_offs = nullptr;
@@ -1442,14 +1454,25 @@ static int tourney_ready(cb200_tourney *T) {
   if (n == 0) return set_error(CB200_ERR_STATE, "tourney has no matches");
   int max_ms = 1, max_spe = 1;
   std::vector<MatchSide> sides(2 * (size_t)n);
+  int n_log = 0;
   for (int i = 0; i < n; ++i) {
     const int pid[2] = {T->matches[i].first, T->matches[i].second};
     for (int s = 0; s < 2; ++s) {
       sides[2 * i + s] = T->players[pid[s]];
+      sides[2 * i + s].log_slot = -1;
       if (sides[2 * i + s].max_searches > max_ms) max_ms = sides[2 * i + s].max_searches;
       if (sides[2 * i + s].spe > max_spe) max_spe = sides[2 * i + s].spe;
     }
+    if (T->logging[i]) {  // log_folder/match_<p1>_<p2>_<index>.txt (tourney.cpp:88-93)
+      sides[2 * i].log_slot = n_log++;
+      auto f = std::make_unique<std::ofstream>(T->log_folder + "/match_" + std::to_string(pid[0]) + "_" +
+                                                   std::to_string(pid[1]) + "_" + std::to_string(i) + ".txt",
+                                               std::ofstream::out);
+      if (!f->is_open()) f.reset();
+      T->log_files.push_back(std::move(f));
+    }
   }
+  T->log_written.assign(n_log, 0);
   if (max_spe > max_ms) max_ms = max_spe;
   // match seeds = successive draws of a default-seeded std::mt19937 (tourney.h:42, tourney.cpp:86)
   T->t = cb200_trainer_create_shard(n, 0, n, T->log_folder.c_str(), 5489, max_ms, max_spe, 1.0f,
@@ -1471,6 +1494,34 @@ static int tourney_ready(cb200_tourney *T) {
       (rc = dmalloc(&T->d_iter_offs, (size_t)n)) != CB200_OK)
     return rc;
   CB_CUDA(cudaMemcpy(T->d_sides, sides.data(), sides.size() * sizeof(MatchSide), cudaMemcpyHostToDevice));
+  if (n_log > 0) {  // the trainer owns (and frees) the log areas
+    if ((rc = dmalloc(&t->P.log_buf, (size_t)n_log * kLogMaxMoves * kLogWords)) != CB200_OK ||
+        (rc = dmalloc(&t->P.log_count, (size_t)n_log)) != CB200_OK)
+      return rc;
+    CB_CUDA(cudaMemset(t->P.log_count, 0, (size_t)n_log * sizeof(int32_t)));
+  }
+  return CB200_OK;
+}
+
+// append the records the matches wrote since the last call to their log files
+static int tourney_drain_logs(cb200_tourney *T) {
+  const int n_log = (int)T->log_written.size();
+  if (n_log == 0) return CB200_OK;
+  cb200_trainer *t = T->t;
+  t->h_log_count.resize(n_log);
+  CB_CUDA(cudaMemcpy(t->h_log_count.data(), t->P.log_count, (size_t)n_log * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (int g = 0; g < n_log; ++g) {
+    const int have = t->h_log_count[g], done = T->log_written[g];
+    if (have <= done) continue;
+    T->log_written[g] = have;
+    if (!T->log_files[g]) continue;
+    t->h_log_rec.resize((size_t)(have - done) * kLogWords);
+    CB_CUDA(cudaMemcpy(t->h_log_rec.data(), t->P.log_buf + ((size_t)g * kLogMaxMoves + done) * kLogWords,
+                       t->h_log_rec.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < have - done; ++k)
+      format_log_record(*T->log_files[g], t->h_log_rec.data() + (size_t)k * kLogWords);
+    T->log_files[g]->flush();
+  }
   return CB200_OK;
 }
 
@@ -1512,18 +1563,18 @@ int cb200_tourney_add_player(cb200_tourney *T, int player_id, int model_id, int 
   MatchSide s;
   s.model_id = model_id, s.max_searches = max_searches > 0 ? max_searches : 1;
   s.spe = searches_per_eval > 0 ? searches_per_eval : 1, s.random = random ? 1 : 0;
-  s.c_puct = c_puct, s.epsilon = epsilon, s.player_id = player_id, s.pad = 0;
+  s.c_puct = c_puct, s.epsilon = epsilon, s.player_id = player_id, s.log_slot = -1;
   T->players[player_id] = s;
   return CB200_OK;
 }
 
 int cb200_tourney_add_match(cb200_tourney *T, int player1, int player2, int logging) {
-  (void)logging;  // per-match text logs are not produced (out of scope)
   if (!T) return set_error(CB200_ERR_ARG, "null tourney");
   if (T->t) return set_error(CB200_ERR_STATE, "matches must be added before the first iteration");
   if (!T->players.count(player1) || !T->players.count(player2))
     return set_error(CB200_ERR_ARG, "cb200_tourney_add_match: unknown player id");
   T->matches.emplace_back(player1, player2);
+  T->logging.push_back(logging ? 1 : 0);
   return CB200_OK;
 }
 
@@ -1586,7 +1637,7 @@ int cb200_tourney_do_iteration(cb200_tourney *T, const float *eval, const float 
     return set_error(t->h_summary[2], "a match overflowed its node arena / path buffer (raise "
                                       "CB200_ARENA_NODES) or reached an impossible state");
   ++t->iterations_done;
-  return CB200_OK;
+  return tourney_drain_logs(T);
 }
 
 // Tourney::writeScores (tourney.cpp:34-42): "<player1> <player2> <score>" per finished match

@@ -15,7 +15,8 @@ namespace cb200 {
 struct MatchSide {  // one Player as seen by one match
   int32_t model_id, max_searches, spe, random;
   float c_puct, epsilon;
-  int32_t player_id, pad;
+  int32_t player_id;
+  int32_t log_slot;  // side 0 only: index of the match's text-log area, -1 = not logged
 };
 
 // control-block words of a match beyond the self-play ones (CW_* in tree.cuh)
@@ -92,6 +93,10 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
   if (!is_random) load_tree(c, Pm, c.to_play);
   const long off = offs[g];
   const float *ev_p = eval + off, *pr_p = probs + off * CB200_NUM_MOVES;
+  // per-match text log (Match::writePreMoveLogs / writeMoveChoice / endGame, match.cpp:79-180):
+  // same records as self-play (tree.cuh, log_pre_move); [13] = 1 when a random player moved
+  const int log_slot = P.log_buf != nullptr ? sides[0].log_slot : -1;
+  int log_n = log_slot >= 0 ? P.log_count[log_slot] : 0;
   bool done = false;
   for (;;) {
     // Match::doIteration: a random player moves at once, a searching player iterates first
@@ -99,6 +104,18 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
     if (!is_random) turn_done = tree_do_iteration(c, Pm, sm, ev_p, pr_p, CB200_NUM_MOVES, 1);
     if (c.error || !turn_done) break;
     // one pass of Match::chooseMoveAndContinue's loop
+    uint32_t *lrec = nullptr;
+    if (log_slot >= 0 && log_n < kLogMaxMoves)
+      lrec = P.log_buf + ((size_t)log_slot * kLogMaxMoves + log_n) * kLogWords;
+    if (lrec != nullptr) {
+      if (c.lane == 0) {
+        lrec[13] = is_random ? 1u : 0u;
+        lrec[1] = (uint32_t)c.to_play, lrec[5] = 0u, lrec[6] = 0u;
+        if (!is_random)
+          log_pre_move(c.base, c.root_off, c.to_play, c.root_visits, c.root_eval, c.root_result, lrec);
+      }
+      __syncwarp();
+    }
     int choice;
     if (is_random) {
       uint32_t m[3];
@@ -116,6 +133,18 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
     depth += 1;
     uint32_t m[3];
     const bool lines = legal_moves(root, m, DeviceLB());
+    if (lrec != nullptr) {
+      if (c.lane == 0) {
+        lrec[7] = (uint32_t)choice;
+        lrec[8] = (uint32_t)root.w0, lrec[9] = (uint32_t)(root.w0 >> 32);
+        lrec[10] = (uint32_t)root.w1, lrec[11] = (uint32_t)(root.w1 >> 32);
+        int res = 0;
+        if ((m[0] | m[1] | m[2]) == 0u)
+          res = 1 + (!lines ? kResultDraw : (c.to_play == 1 ? kResultLoss : kResultWin));
+        lrec[12] = (uint32_t)res;
+      }
+      log_n += 1;
+    }
     if ((m[0] | m[1] | m[2]) == 0u) {  // endGame (match.cpp:161-190)
       c.result = !lines ? kResultDraw : (c.to_play == 1 ? kResultLoss : kResultWin);
       if (!is_random) {
@@ -155,6 +184,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
     ctl[MW_ROOT0] = (int32_t)(uint32_t)root.w0, ctl[MW_ROOT1] = (int32_t)(uint32_t)(root.w0 >> 32);
     ctl[MW_ROOT2] = (int32_t)(uint32_t)root.w1, ctl[MW_ROOT3] = (int32_t)(uint32_t)(root.w1 >> 32);
     ctl[MW_DEPTH] = depth;
+    if (log_slot >= 0) P.log_count[log_slot] = log_n;
     if (done) ctl[CW_DONE] = 1;
     long long *cnt = P.counters + (size_t)g * 4;
     cnt[0] += c.d_sims, cnt[1] += c.d_moves, cnt[2] += c.d_evals;

@@ -1139,7 +1139,8 @@ __device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &
 // the host prints them with the reference's stream formatting (engine.cu, format_log_record).
 // Record: [0] root depth, [1] to_play, [2] root visits, [3] root evaluation bits, [4] root
 // result, [5] main-line entries, [6] visited root children, [7] chosen move, [8..11] position
-// after the move, [12] 0 or 1 + game result when the move ended the game;
+// after the move, [12] 0 or 1 + game result when the move ended the game, [13] 1 = a Match's
+// random player moved (no pre-move section);
 // main line at kLogMain: {depth, move, visits, evaluation bits, result, probability bits};
 // children at kLogKids: {move, visits, evaluation bits, probability bits, result}.
 constexpr int kLogWords = 1024, kLogMain = 16, kLogMainMax = 64, kLogKids = kLogMain + 6 * kLogMainMax;
@@ -1259,7 +1260,7 @@ __device__ __forceinline__ int choose_move_and_continue(Ctx &c, const TreeParams
       int res = 0;
       if (r_terminal(c.root_result))
         res = 1 + (c.root_result == kResultDraw ? kResultDraw : (c.to_play == 1 ? kResultLoss : kResultWin));
-      log_rec[12] = (uint32_t)res;
+      log_rec[12] = (uint32_t)res, log_rec[13] = 0u;
       __threadfence();
       P.log_count[(c.tree_ctl - P.tree) / (2 * kTreeCtlWords)] += 1;
     }

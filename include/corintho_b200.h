@@ -184,7 +184,8 @@ int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[
  * rating/tourney.pyx:112-173 drives it: for every model id (negative ids = random players) ->
  * num_requests, write_requests, evaluate, do_iteration; until all_done. The answer offsets follow
  * tourney.cpp:54-62 literally. All players and matches must be added before the first call that
- * needs the device (add_* return CB200_ERR_STATE afterwards); `logging` is accepted and ignored.
+ * needs the device (add_* return CB200_ERR_STATE afterwards). Matches added with logging != 0
+ * write log_folder/match_<p1>_<p2>_<index>.txt like the reference (match.cpp:79-180).
  * `rows` = number of rows the caller's eval / probs buffers hold. */
 typedef struct cb200_tourney cb200_tourney;
 cb200_tourney *cb200_tourney_create(int num_threads, const char *log_folder);

@@ -116,3 +116,5 @@ LOG_CASES = {
     "test": (dict(num_games=4, seed=11, max_searches=32, searches_per_eval=4, c_puct=1.5, epsilon=0.0,
                   num_logged=2, testing=True), 0),
 }
+
+LOGGED_MATCHES = (0, 2, 3, 7)  # indices into TOURNEY_CASES["with_random"][1] written as text logs
