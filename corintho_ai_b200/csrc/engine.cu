@@ -1167,7 +1167,11 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
     }
     const int rounds = max_rounds - *rounds_done;
     // deal the games again once half of them have finished (not worth it for the last few)
-    int exit_done = t->ps_n > 64 ? t->ps_n / 2 : 0x7fffffff;
+    int redeal_pct = 50, redeal_min = 64;
+    if (const char *e = getenv("CB200_PS_REDEAL_PCT")) redeal_pct = atoi(e);
+    if (const char *e = getenv("CB200_PS_REDEAL_MIN")) redeal_min = atoi(e);
+    int exit_done = t->ps_n > redeal_min ? (int)((long long)t->ps_n * redeal_pct / 100) : 0x7fffffff;
+    if (exit_done < 1) exit_done = 1;
     if (getenv("CB200_PS_NO_REDEAL")) exit_done = 0x7fffffff;
     const bool wide = t->ps_n > t->ps_ctas * 8;
     CB_CUDA(cudaMemsetAsync(t->d_ps_out, 0, 4 * sizeof(int32_t), st));
