@@ -51,3 +51,20 @@ def test_random_only_and_wide_budget_tourneys(oracle):
     a, b = run_tourney(build(oracle)), run_tourney(build(E()))
     assert a["rounds"] == b["rounds"] and a["req_hash"] == b["req_hash"]
     assert (a["scores"] == b["scores"]).all() and (a["counts"] == b["counts"]).all()
+
+
+def test_arena_overflow_in_fused_and_persistent_runs_fails_loudly(monkeypatch):
+    """A node arena that is too small must end the fused run with CB200_ERR_OVERFLOW -- from the
+    lock-step loop and from inside the persistent kernel alike -- never with a hang or bad data."""
+    monkeypatch.setenv("CB200_ARENA_NODES", "24")
+    flat = cb.fold_batchnorm(cb.random_weights(2))
+    for no_persistent in ("1", None):
+        if no_persistent:
+            monkeypatch.setenv("CB200_NO_PERSISTENT", no_persistent)
+        else:
+            monkeypatch.delenv("CB200_NO_PERSISTENT")
+        t = cb.Trainer(16, "", 3, 64, 16, 1.0, 0.25)
+        t.set_weights(flat, 0, "bf16")
+        with pytest.raises(cb.Corintho200Error) as e:
+            t.run_selfplay(0, stagger=False)
+        assert "arena" in str(e.value)
