@@ -46,7 +46,7 @@ inline Globals &G() {
 
 // ---- device-resident rule data (uploaded once per device by ensure_tables) ------------------
 // line-breaker masks padded to 4 words so one 128-bit load fetches a mask
-__device__ uint32_t d_line_breakers[103 * 4];  // entry 102 = all ones (no line)
+__device__ __align__(16) uint32_t d_line_breakers[103 * 4];  // entry 102 = all ones (no line)
 __device__ float d_gamma[1024];
 
 struct DeviceLB {

@@ -68,6 +68,19 @@ CB_HD uint32_t compress3(uint32_t v) {
   return (v & 0x7u) | ((v >> 1) & 0x38u) | ((v >> 2) & 0x1C0u) | ((v >> 3) & 0xE00u);
 }
 
+// AND the 96-bit line-breaker mask `idx` into (m0, m1, m2). Device tables are padded to four
+// 16-byte-aligned words, so one 128-bit load fetches a mask.
+template <class LBFn>
+CB_HD void lb_and(LBFn LB, int idx, uint32_t &m0, uint32_t &m1, uint32_t &m2) {
+  const uint32_t *lb = LB(idx);
+#ifdef __CUDA_ARCH__
+  const uint4 v = *reinterpret_cast<const uint4 *>(lb);
+  m0 &= v.x, m1 &= v.y, m2 &= v.z;
+#else
+  m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+#endif
+}
+
 // Legal-move mask (96 bits in m[0..2], bit id&31 of word id>>5) and the "lines present" flag.
 // LB(idx) must return a pointer to the 3 words of line-breaker mask idx (util.h:85-290 data);
 // idx 102 must return an all-ones mask ("no line in this category").
@@ -116,8 +129,7 @@ CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
       const int t = (int)((any1 >> i4) & 1u) + 2 * (int)((any2 >> i4) & 1u);
       const bool l = (left >> i4) & 1u, r = (right >> i4) & 1u;
       const int cat = (l && r) ? 2 : (l ? 0 : 1);  // RB, RL, RR (util.h:67-69)
-      const uint32_t *lb = LB(has ? cat * 12 + i * 3 + t : 102);
-      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+      lb_and(LB, has ? cat * 12 + i * 3 + t : 102, m0, m1, m2);
       if (has && t == 2 && cat != 2) {  // capital fix-ups (game.cpp:280-309), column `e`
         const int e = l ? 3 : 0;
         const uint32_t colm = 0x111u << e;
@@ -141,8 +153,7 @@ CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
       const int t = (int)((any1 >> i) & 1u) + 2 * (int)((any2 >> i) & 1u);
       const bool u = (upper >> i) & 1u, d = (lower >> i) & 1u;
       const int cat = (u && d) ? 5 : (u ? 3 : 4);  // CB, CU, CD (util.h:70-72)
-      const uint32_t *lb = LB(has ? cat * 12 + i * 3 + t : 102);
-      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+      lb_and(LB, has ? cat * 12 + i * 3 + t : 102, m0, m1, m2);
       if (has && t == 2 && cat != 5) {  // capital fix-ups along row `e`
         const int e = u ? 3 : 0;
         const uint32_t Arow = (A >> (4 * e)) & 0xFu;
@@ -173,8 +184,7 @@ CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
       int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
       bool has = mainl || antil;
       lines |= has;
-      const uint32_t *lb = LB(has ? 72 + D * 3 + t : 102);
-      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+      lb_and(LB, has ? 72 + D * 3 + t : 102, m0, m1, m2);
       // short diagonals (game.cpp:362-391): S0..S3, first found
       const bool s0 = D3 & 0x04u, s1 = D5 & 0x02u, s2 = D3 & 0x80u, s3 = D5 & 0x10u;
       D = s0 ? 6 : (s1 ? 7 : (s2 ? 8 : 9));
@@ -184,8 +194,7 @@ CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
       t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
       has = s0 || s1 || s2 || s3;
       lines |= has;
-      lb = LB(has ? 72 + D * 3 + t : 102);
-      m0 &= lb[0], m1 &= lb[1], m2 &= lb[2];
+      lb_and(LB, has ? 72 + D * 3 + t : 102, m0, m1, m2);
     }
   }
   m[0] = m0, m[1] = m1, m[2] = m2;
