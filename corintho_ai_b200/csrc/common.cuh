@@ -48,6 +48,7 @@ inline Globals &G() {
 // line-breaker masks padded to 4 words so one 128-bit load fetches a mask
 __device__ __align__(16) uint32_t d_line_breakers[103 * 4];  // entry 102 = all ones (no line)
 __device__ float d_gamma[1024];
+__device__ uint32_t d_inv32[128];  // floor(2^32 / d) for d = 1..127 ([0] unused; [1] = 2^32 - 1)
 
 struct DeviceLB {
   __device__ __forceinline__ const uint32_t *operator()(int idx) const {
@@ -67,6 +68,10 @@ inline int ensure_tables() {
   }
   CB_CUDA(cudaMemcpyToSymbol(d_line_breakers, lb, sizeof(lb)));
   CB_CUDA(cudaMemcpyToSymbol(d_gamma, kCGammaBits, sizeof(kCGammaBits)));
+  static uint32_t inv[128];
+  inv[0] = 0, inv[1] = 0xFFFFFFFFu;
+  for (uint32_t d = 2; d < 128; ++d) inv[d] = (uint32_t)(0x100000000ull / d);
+  CB_CUDA(cudaMemcpyToSymbol(d_inv32, inv, sizeof(inv)));
   if (dev < 16) G().tables_ready[dev] = true;
   return CB200_OK;
 }

@@ -31,7 +31,11 @@ __global__ void __launch_bounds__(kStepThreads)
       const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
       const int result = terminal_result(nl, lines);
       // select-only: compute the move for every state, keep it only where one exists
-      const int pick = nth_move(m, (int)(step_rnd(seed, (uint64_t)i) % (uint32_t)max(nl, 1)));
+      // r % nl with nl <= 96: quotient estimate from floor(2^32 / nl) (one below at most), fix-up
+      const uint32_t rnd = step_rnd(seed, (uint64_t)i), dv = (uint32_t)max(nl, 1);
+      uint32_t rem = rnd - __umulhi(rnd, __ldg(d_inv32 + dv)) * dv;
+      rem -= rem >= dv ? dv : 0u;
+      const int pick = nth_move(m, (int)rem);
       const CState moved = do_move(s, pick & 127);
       const int chosen = nl > 0 ? pick : 0x7f;
       CState o;

@@ -215,8 +215,11 @@ CB_HD CState do_move(const CState &st, int move) {
   // place: 48 + piece*16 + square
   const int piece = (move - 48) >> 4;
   // move: dir = id/12 (0 right, 1 down, 2 left, 3 up), r = id%12 (move.cpp:11-42)
-  const int dir = move / 12, r = move - dir * 12;
-  const int r3 = (r / 3) * 4 + r % 3;  // (row, col<3) of a horizontal move
+  // (small unsigned multiply-shift divisions: exact for ids 0..47 / r 0..11)
+  const uint32_t um = (uint32_t)move & 63u;
+  const int dir = (int)((um * 43u) >> 9), r = (int)um - dir * 12;
+  const int rq = (int)(((uint32_t)r * 11u) >> 5);  // r / 3
+  const int r3 = rq * 4 + (r - rq * 3);            // (row, col<3) of a horizontal move
   const int from = dir == 0 ? r3 : (dir == 1 ? r : (dir == 2 ? r3 + 1 : r + 4));
   const int to_m = dir == 0 ? r3 + 1 : (dir == 1 ? r + 4 : (dir == 2 ? r3 : r));
   const int to = is_place ? (move & 15) : to_m;
