@@ -17,10 +17,11 @@ __global__ void __launch_bounds__(kStepThreads)
                 uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next,
                 float *__restrict__ enc) {
   __shared__ ulonglong2 sm_states[kEncode ? kStepThreads : 1];
-  const int64_t stride = (int64_t)gridDim.x * kStepThreads;
+  // 32-bit indices: the launcher refuses more than 2^31 - 2^20 states per call
+  const int stride = (int)gridDim.x * kStepThreads;
   // every warp runs the same number of trips so the cooperative encode stays convergent
-  const int64_t n_round = ((n + 31) / 32) * 32;
-  for (int64_t i = (int64_t)blockIdx.x * kStepThreads + threadIdx.x; i < n_round; i += stride) {
+  const int n_round = (int)(((n + 31) / 32) * 32);
+  for (int i = (int)blockIdx.x * kStepThreads + threadIdx.x; i < n_round; i += stride) {
     const bool live = i < n;
     CState s{0, 0};
     if (live) {
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(kStepThreads)
 inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void *d_mask_flags,
                             void *d_next, void *d_enc) {
   if (n <= 0) return CB200_OK;
+  if (n > (int64_t)0x7FF00000) return set_error(CB200_ERR_ARG, "cb200_game_step: at most 2^31 - 2^20 states per call");
   int rc = ensure_tables();
   if (rc != CB200_OK) return rc;
   int dev = 0, sms = 148;
