@@ -88,6 +88,7 @@ def lib():
         "cb200_trainer_phase_profile": (i32, [vp, i32, vp]),
         "cb200_trainer_set_profiling": (i32, [vp, i32]),
         "cb200_trainer_kernel_times": (i32, [vp, vp, vp]),
+        "cb200_trainer_phase_split": (i32, [vp, vp]),
         "cb200_tourney_create": (vp, [i32, C.c_char_p]),
         "cb200_tourney_destroy": (None, [vp]),
         "cb200_tourney_add_player": (i32, [vp, i32, i32, i32, i32, f32, f32, i32]),
@@ -114,6 +115,30 @@ def _check(rc):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _in_f32(a, min_size, what):
+    """Input buffer of the reference API (typed float memoryview in main.pyx:30-38): converted to
+    a C-contiguous float32 array; fewer than `min_size` elements is an error, never a short read."""
+    if a is None:
+        if min_size > 0:
+            raise Corintho200Error(f"{what}: buffer is None but {min_size} floats are needed")
+        return None
+    b = np.ascontiguousarray(a, np.float32)
+    if b.size < min_size:
+        raise Corintho200Error(f"{what}: {b.size} floats given, {min_size} needed")
+    return b
+
+
+def _out_f32(a, min_size, what):
+    """Output buffer written through a raw pointer: must already be float32, C-contiguous,
+    writable and large enough (the reference's Cython signature rejects anything else)."""
+    if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags.c_contiguous \
+            or not a.flags.writeable:
+        raise Corintho200Error(f"{what}: need a writable C-contiguous float32 numpy array")
+    if a.size < min_size:
+        raise Corintho200Error(f"{what}: {a.size} floats given, {min_size} needed")
+    return a
 
 
 # ---- packed state helpers -----------------------------------------------------------------
@@ -243,19 +268,28 @@ class Trainer:
 
     # ---- reference API ------------------------------------------------------------------
     def doIteration(self, evaluations=None, probabilities=None, to_play=-1):
-        return bool(_check(lib().cb200_trainer_do_iteration(
-            self._h, _ptr(evaluations), _ptr(probabilities), to_play)))
+        # the answers of the requests that are pending for this side (none on the first call)
+        n = self.num_requests(to_play)
+        ev = _in_f32(evaluations, n, "doIteration: evaluations")
+        pr = _in_f32(probabilities, n * NUM_MOVES, "doIteration: probabilities")
+        return bool(_check(lib().cb200_trainer_do_iteration(self._h, _ptr(ev), _ptr(pr), to_play)))
 
     def num_requests(self, to_play=-1):
         return _check(lib().cb200_trainer_num_requests(self._h, to_play))
 
     def writeRequests(self, game_states, to_play=-1):
+        n = self.num_requests(to_play)
+        _out_f32(game_states, n * STATE_SIZE, "writeRequests: game_states")
         _check(lib().cb200_trainer_write_requests(self._h, _ptr(game_states), to_play))
 
     def num_samples(self):
         return _check(lib().cb200_trainer_num_samples(self._h))
 
     def writeSamples(self, game_states, eval_samples, prob_samples):
+        rows = self.num_samples() * NUM_SYMMETRIES
+        _out_f32(game_states, rows * STATE_SIZE, "writeSamples: game_states")
+        _out_f32(eval_samples, rows, "writeSamples: eval_samples")
+        _out_f32(prob_samples, rows * NUM_MOVES, "writeSamples: prob_samples")
         _check(lib().cb200_trainer_write_samples(self._h, _ptr(game_states), _ptr(eval_samples),
                                                  _ptr(prob_samples)))
 
@@ -326,8 +360,15 @@ class Trainer:
         ms = np.zeros(8, np.float64)
         ln = np.zeros(8, np.int64)
         _check(lib().cb200_trainer_kernel_times(self._h, _ptr(ms), _ptr(ln)))
-        names = ["scan", "pack", "network", "game_step", "fused_tail"]
+        names = ["scan", "pack", "network", "game_step", "fused_tail", "fused_tail_wide"]
         return {n: {"ms": float(ms[i]), "launches": int(ln[i])} for i, n in enumerate(names)}
+
+    def phase_split(self):
+        """Simulations / leaf evaluations done by lock-step launches vs in total (profiling on)."""
+        out = np.zeros(4, np.int64)
+        _check(lib().cb200_trainer_phase_split(self._h, _ptr(out)))
+        return {"lockstep_simulations": int(out[0]), "simulations": int(out[1]),
+                "lockstep_leaf_evals": int(out[2]), "leaf_evals": int(out[3])}
 
     def raw_samples(self):
         n = self.num_samples()
@@ -398,6 +439,7 @@ class Tourney:
         return _check(lib().cb200_tourney_num_requests(self._h, int(model_id)))
 
     def writeRequests(self, game_states, model_id):
+        _out_f32(game_states, self.num_requests(model_id) * STATE_SIZE, "writeRequests: game_states")
         _check(lib().cb200_tourney_write_requests(self._h, _ptr(game_states), int(model_id)))
 
     def doIteration(self, evals, probs, model_id):

@@ -33,15 +33,25 @@ inline int set_error(int code, const std::string &msg) {
     }                                                                                       \
   } while (0)
 
+constexpr int kMaxDevices = 16;
 struct Globals {
-  cudaStream_t stream = nullptr;
+  // launch stream per device (cb200_set_stream applies to the device that is current when it is
+  // called); devices past kMaxDevices share the last entry
+  cudaStream_t stream_of[kMaxDevices] = {};
   std::atomic<int64_t> launches{0};
-  bool tables_ready[16] = {false};
+  bool tables_ready[kMaxDevices] = {false};
 };
 inline Globals &G() {
   static Globals g;
   return g;
 }
+inline int cur_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev < kMaxDevices ? dev : kMaxDevices - 1);
+}
+inline cudaStream_t cur_stream() { return G().stream_of[cur_device_slot()]; }
+inline void set_cur_stream(cudaStream_t s) { G().stream_of[cur_device_slot()] = s; }
 #define CB_LAUNCHED() (cb200::G().launches.fetch_add(1, std::memory_order_relaxed))
 
 // ---- device-resident rule data (uploaded once per device by ensure_tables) ------------------

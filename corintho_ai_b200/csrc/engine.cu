@@ -137,9 +137,15 @@ struct cb200_trainer {
   std::vector<cudaEvent_t> ev_pool;
   std::vector<int> ev_class;  // class of the pair starting at ev_pool[2*i]
   size_t ev_used = 0;
+  // profiling: running search / leaf-evaluation counts attributed to the lock-step launches
+  // (the rest of a run belongs to the persistent kernels); marks = values at the last snapshot
+  long long searches_now = 0, searches_mark = 0, evals_mark = 0;
+  long long lockstep_searches = 0, lockstep_evals = 0, total_searches = 0, total_evals = 0;
   double class_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long class_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
+
+extern "C" int cb200_trainer_counters(cb200_trainer *t, int64_t out[4]);
 
 namespace {
 
@@ -206,7 +212,7 @@ struct ProfScope {
   bool on;
   size_t idx = 0;
   cudaStream_t st;
-  ProfScope(cb200_trainer *t_, int cls, cudaStream_t stream = G().stream)
+  ProfScope(cb200_trainer *t_, int cls, cudaStream_t stream = cur_stream())
       : t(t_), on(t_->profiling), st(stream) {
     if (!on) return;
     if (2 * (t->ev_used + 1) > t->ev_pool.size()) {
@@ -226,9 +232,25 @@ struct ProfScope {
   }
 };
 
+// profiling only: attribute the searches / leaf evaluations since the last mark to the lock-step
+// launches (to_lockstep) or to the persistent kernels
+int prof_mark(cb200_trainer *t, bool to_lockstep) {
+  int64_t c4[4];
+  int rc = cb200_trainer_counters(t, c4);
+  if (rc != CB200_OK) return rc;
+  if (to_lockstep) {
+    t->lockstep_searches += t->searches_now - t->searches_mark;
+    t->lockstep_evals += c4[2] - t->evals_mark;
+  }
+  t->total_searches += t->searches_now - t->searches_mark;
+  t->total_evals += c4[2] - t->evals_mark;
+  t->searches_mark = t->searches_now, t->evals_mark = c4[2];
+  return CB200_OK;
+}
+
 int scan(cb200_trainer *t, int to_play) {
   ProfScope ps(t, 0);
-  k_scan_requests<<<1, 1024, 0, G().stream>>>(t->P, to_play, t->d_offs, t->d_summary);
+  k_scan_requests<<<1, 1024, 0, cur_stream()>>>(t->P, to_play, t->d_offs, t->d_summary);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;
@@ -236,8 +258,8 @@ int scan(cb200_trainer *t, int to_play) {
 
 int fetch_summary(cb200_trainer *t) {
   CB_CUDA(cudaMemcpyAsync(t->h_summary, t->d_summary, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost,
-                          G().stream));
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+                          cur_stream()));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   if (t->profiling) {
     int rc = prof_drain(t);
     if (rc != CB200_OK) return rc;
@@ -256,7 +278,7 @@ int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_
   const long prs = probs_move_major ? 1 : CB200_NUM_MOVES;
   const long pcs = probs_move_major ? (long)t->cap : 1;
   ProfScope ps(t, 3);
-  k_iterate<false, 4><<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
+  k_iterate<false, 4><<<grid, kTreeWarps * 32, 0, cur_stream()>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
                                                        to_play, t->iterations_done,
                                                        t->stagger_div);
   CB_LAUNCHED();
@@ -268,7 +290,7 @@ int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_
 int pack(cb200_trainer *t, int to_play, float *d_rows, ulonglong2 *d_packed) {
   const int grid = (t->P.num_games + 7) / 8;
   ProfScope ps(t, 1);
-  k_pack_requests<<<grid, 256, 0, G().stream>>>(t->P, to_play, t->d_offs, d_rows, d_packed);
+  k_pack_requests<<<grid, 256, 0, cur_stream()>>>(t->P, to_play, t->d_offs, d_rows, d_packed);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;
@@ -286,6 +308,7 @@ int run_net(cb200_trainer *t, int model, const ulonglong2 *d_states, const int32
 }
 
 int guard(cb200_trainer *t) {
+  last_error_ref().clear();  // a message always belongs to the call that failed last
   if (!t) return set_error(CB200_ERR_ARG, "null trainer");
   CB_CUDA(cudaSetDevice(t->device));
   return CB200_OK;
@@ -460,6 +483,19 @@ __global__ void k_seed_mt(int n, const uint32_t *__restrict__ seeds, uint32_t *_
   }
 }
 
+// (Re)open log_folder/game_<i>.txt for the logged games of this shard, truncating like the
+// reference's ofstream(..., out) does for every new Trainer (trainer.cpp:243-250); a missing
+// folder silently produces no log.
+static void open_log_files(cb200_trainer *t) {
+  t->log_files.clear();
+  for (int i = 0; i < t->P.n_logged; ++i) {
+    auto f = std::make_unique<std::ofstream>(
+        t->log_folder + "/game_" + std::to_string(t->P.first_game + i) + ".txt", std::ofstream::out);
+    if (!f->is_open()) f.reset();
+    t->log_files.push_back(std::move(f));
+  }
+}
+
 // initialisation: per-game seeds (trainer.cpp:238-256) from the host generator, MT19937 states
 // expanded on the device, control blocks
 static int init_state(cb200_trainer *t) {
@@ -483,7 +519,7 @@ static int init_state(cb200_trainer *t) {
       tw[TW_ROOT_ALLV] = 1;
     }
   }
-  cudaStream_t s = G().stream;
+  cudaStream_t s = cur_stream();
   CB_CUDA(cudaMemcpyAsync(P.ctl, ctl.data(), ctl.size() * 4, cudaMemcpyHostToDevice, s));
   CB_CUDA(cudaMemcpyAsync(P.tree, tree.data(), tree.size() * 4, cudaMemcpyHostToDevice, s));
   // the seeds travel through the (still unused) request-offset buffer
@@ -501,6 +537,7 @@ static int init_state(cb200_trainer *t) {
   if (P.n_logged > 0) {
     CB_CUDA(cudaMemset(P.log_count, 0, (size_t)P.n_logged * sizeof(int32_t)));
     std::fill(t->log_written.begin(), t->log_written.end(), 0);
+    open_log_files(t);  // a run after reset() starts its transcripts afresh
   }
   t->iterations_done = 0;
   t->ps_active = false, t->ps_from_lockstep = false, t->ps_n = 0, t->ps_cur = 0;
@@ -524,7 +561,7 @@ int cb200_set_device(int device) {
 }
 
 int cb200_set_stream(void *cuda_stream) {
-  G().stream = (cudaStream_t)cuda_stream;
+  set_cur_stream((cudaStream_t)cuda_stream);
   return CB200_OK;
 }
 
@@ -550,7 +587,7 @@ int cb200_game_step(int64_t n, const uint64_t *states, uint64_t seed, uint32_t *
       (enc && (e = cudaMalloc(&d_e, n * CB200_STATE_SIZE * sizeof(float))) != cudaSuccess)) {
     rc = set_error(CB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
   }
-  cudaStream_t s = G().stream;
+  cudaStream_t s = cur_stream();
   if (rc == CB200_OK && (e = cudaMemcpyAsync(d_s, states, n * 16, cudaMemcpyHostToDevice, s)) != cudaSuccess)
     rc = set_error(CB200_ERR_CUDA, cudaGetErrorString(e));
   if (rc == CB200_OK) rc = launch_game_step(n, d_s, seed, d_m, d_n, d_e);
@@ -571,6 +608,7 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
                                           const char *log_folder, int seed, int max_searches,
                                           int searches_per_eval, float c_puct, float epsilon,
                                           int num_logged, int testing) {
+  last_error_ref().clear();
   // the reference only assert()s these (trainer.cpp:25-34); here they are hard errors
   if (num_games <= 0 || total_games < num_games || first_game < 0 ||
       first_game + num_games > total_games || max_searches <= 0 || searches_per_eval <= 0 ||
@@ -599,14 +637,15 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     words = atoll(env) * (8 + 4 * 28);
   } else {
     // Larger arenas make in-place re-rooting the common case (compaction only when room runs
-    // out): spend up to half of the free HBM, capped at 16 moves' worth of nodes per arena.
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-      long long budget = (long long)(free_b / 2) / ((long long)num_games * 3 * 4);
-      long long cap = (long long)max_searches * 16 * (8 + 4 * 28);
-      if (budget > cap) budget = cap;
-      if (budget > words) words = budget;
-    }
+    // out). The node arenas of one trainer take at most an explicit budget -- 48 GiB by default,
+    // CB200_ARENA_BUDGET_MB overrides -- capped at 16 moves' worth of nodes per arena and never
+    // below the minimum above; a co-resident trainer keeps the rest of the HBM.
+    long long budget_bytes = 48ll << 30;
+    if (const char *env = getenv("CB200_ARENA_BUDGET_MB")) budget_bytes = atoll(env) << 20;
+    long long budget = budget_bytes / ((long long)num_games * 3 * 4);
+    const long long cap = (long long)max_searches * 16 * (8 + 4 * 28);
+    if (budget > cap) budget = cap;
+    if (budget > words) words = budget;
   }
   words = (words + 3) & ~3ll;
   if (words < 1024) words = 1024;
@@ -658,13 +697,6 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
            dmalloc(&P.log_count, (size_t)P.n_logged) == CB200_OK;
       if (ok) ok = cudaMemset(P.log_count, 0, (size_t)P.n_logged * sizeof(int32_t)) == cudaSuccess;
       t->log_written.assign(P.n_logged, 0);
-      for (int i = 0; i < P.n_logged; ++i) {
-        // like the reference, a missing folder silently produces no log
-        auto f = std::make_unique<std::ofstream>(
-            t->log_folder + "/game_" + std::to_string(first_game + i) + ".txt", std::ofstream::out);
-        if (!f->is_open()) f.reset();
-        t->log_files.push_back(std::move(f));
-      }
     }
   }
   if (!ok) {
@@ -738,7 +770,7 @@ cb200_trainer *cb200_trainer_create(int num_games, const char *log_folder, int s
 int cb200_trainer_phase_profile(cb200_trainer *t, int enable, uint64_t out[16]) {
   int rc = guard(t);
   if (rc) return rc;
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   if (t->P.phase_prof && out) {
     CB_CUDA(cudaMemcpy(out, t->P.phase_prof, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     CB_CUDA(cudaMemset(t->P.phase_prof, 0, 16 * sizeof(uint64_t)));
@@ -763,17 +795,26 @@ int cb200_trainer_reset(cb200_trainer *t, int seed) {
 int cb200_trainer_set_profiling(cb200_trainer *t, int enable) {
   int rc = guard(t);
   if (rc) return rc;
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   if ((rc = prof_drain(t)) != CB200_OK) return rc;
   t->profiling = enable != 0;
   for (int i = 0; i < 8; ++i) t->class_ms[i] = 0, t->class_launches[i] = 0;
+  t->lockstep_searches = t->lockstep_evals = t->total_searches = t->total_evals = 0;
+  return CB200_OK;
+}
+
+int cb200_trainer_phase_split(cb200_trainer *t, int64_t out[4]) {
+  int rc = guard(t);
+  if (rc) return rc;
+  out[0] = t->lockstep_searches, out[1] = t->total_searches;
+  out[2] = t->lockstep_evals, out[3] = t->total_evals;
   return CB200_OK;
 }
 
 int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[8], int64_t out_launches[8]) {
   int rc = guard(t);
   if (rc) return rc;
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   if ((rc = prof_drain(t)) != CB200_OK) return rc;
   for (int i = 0; i < 8; ++i) out_ms[i] = t->class_ms[i], out_launches[i] = t->class_launches[i];
   return CB200_OK;
@@ -823,8 +864,8 @@ int cb200_trainer_write_requests(cb200_trainer *t, float *game_states, int to_pl
   const int n = t->h_summary[0];
   if (n > 0) {
     CB_CUDA(cudaMemcpyAsync(game_states, t->d_rows, (size_t)n * CB200_STATE_SIZE * sizeof(float),
-                            cudaMemcpyDeviceToHost, G().stream));
-    CB_CUDA(cudaStreamSynchronize(G().stream));
+                            cudaMemcpyDeviceToHost, cur_stream()));
+    CB_CUDA(cudaStreamSynchronize(cur_stream()));
   }
   return CB200_OK;
 }
@@ -843,9 +884,9 @@ int cb200_trainer_do_iteration(cb200_trainer *t, const float *eval, const float 
   if (n > 0) {
     if (!eval || !probs) return set_error(CB200_ERR_ARG, "requests pending but eval/probs null");
     CB_CUDA(cudaMemcpyAsync(t->d_eval, eval, (size_t)n * sizeof(float), cudaMemcpyHostToDevice,
-                            G().stream));
+                            cur_stream()));
     CB_CUDA(cudaMemcpyAsync(t->d_probs, probs, (size_t)n * CB200_NUM_MOVES * sizeof(float),
-                            cudaMemcpyHostToDevice, G().stream));
+                            cudaMemcpyHostToDevice, cur_stream()));
   }
   if ((rc = iterate(t, t->d_eval, t->d_probs, to_play)) != CB200_OK) return rc;
   if ((rc = scan(t, to_play)) != CB200_OK) return rc;
@@ -856,7 +897,7 @@ int cb200_trainer_do_iteration(cb200_trainer *t, const float *eval, const float 
 
 static int fetch_ctl(cb200_trainer *t) {
   t->h_ctl.resize((size_t)t->P.num_games * kCtlWords);
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   CB_CUDA(cudaMemcpy(t->h_ctl.data(), t->P.ctl, t->h_ctl.size() * 4, cudaMemcpyDeviceToHost));
   return CB200_OK;
 }
@@ -887,7 +928,6 @@ int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eva
   const size_t rows = (size_t)ns * 8;
   if (rows > t->samp_rows) {  // one cached device buffer: [rows][70] + [rows] + [rows][96]
     cudaFree(t->d_samp);
-  cudaFree(t->d_raw);
     t->d_samp = nullptr, t->samp_rows = 0;
     const size_t want = rows + rows / 4 + 1024;
     rc = dmalloc(&t->d_samp, want * (CB200_STATE_SIZE + 1 + CB200_NUM_MOVES));
@@ -896,7 +936,7 @@ int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eva
   }
   float *d_gs = t->d_samp, *d_ev = d_gs + t->samp_rows * CB200_STATE_SIZE, *d_pr = d_ev + t->samp_rows;
   {
-    cudaStream_t s = G().stream;
+    cudaStream_t s = cur_stream();
     cudaError_t e = cudaMemcpyAsync(t->d_soff, soff.data(), Gn * sizeof(int32_t),
                                     cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
@@ -979,10 +1019,13 @@ int cb200_trainer_counters(cb200_trainer *t, int64_t out[4]) {
   int rc = guard(t);
   if (rc) return rc;
   std::vector<long long> h((size_t)t->P.num_games * 4);
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   CB_CUDA(cudaMemcpy(h.data(), t->P.counters, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
   out[0] = out[1] = out[2] = 0;
-  for (int g = 0; g < t->P.num_games; ++g) out[0] += h[4 * g], out[1] += h[4 * g + 1], out[2] += h[4 * g + 2];
+  long long searches = 0;
+  for (int g = 0; g < t->P.num_games; ++g)
+    out[0] += h[4 * g], out[1] += h[4 * g + 1], out[2] += h[4 * g + 2], searches += h[4 * g + 3];
+  t->searches_now = searches;
   out[3] = t->iterations_done;
   return CB200_OK;
 }
@@ -1047,7 +1090,7 @@ int cb200_trainer_raw_samples_device(cb200_trainer *t, void **rows_device, int *
     if ((rc = dmalloc(&t->d_raw, want * 102)) != CB200_OK) return rc;
     t->raw_rows = want;
   }
-  cudaStream_t s = G().stream;
+  cudaStream_t s = cur_stream();
   CB_CUDA(cudaMemcpyAsync(t->d_soff, soff.data(), Gn * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   if (ns > 0) {
     const long long warps = (long long)Gn * kMaxSamples;
@@ -1093,7 +1136,7 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
     for (int j = 0; j < 6; ++j) w1 |= (uint64_t)(int)(r[64 + j] * 4.0f + 0.5f) << (8 * j);
     hs[i] = make_ulonglong2(w0, w1);
   }
-  cudaStream_t s = G().stream;
+  cudaStream_t s = cur_stream();
   CB_CUDA(cudaMemcpyAsync(t->d_packed, hs.data(), (size_t)n * sizeof(ulonglong2), cudaMemcpyHostToDevice, s));
   if ((rc = run_net(t, model, t->d_packed, nullptr, n, n)) != CB200_OK) return rc;
   CB_CUDA(cudaMemcpyAsync(eval, t->d_eval, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1177,7 +1220,7 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
     CB_CUDA(cudaMemsetAsync(t->d_ps_out, 0, 4 * sizeof(int32_t), st));
     int rc;
     {
-      ProfScope ps(t, 4, st);
+      ProfScope ps(t, wide ? 5 : 4, st);
       if (t->nettc[0].fp16)
         rc = wide ? ps_launch<true, 16>(t, P, rounds, exit_done)
                   : ps_launch<true, 8>(t, P, rounds, exit_done);
@@ -1219,7 +1262,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   const int ng = t->n_groups;
   std::vector<char> active(ng, 1);
   // work queued on the default stream (weights, reset) must be visible to the group streams
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   int done_iters = 0, result = 0;
   long long live_games = t->P.num_games;
   // parking budget (TreeParams::yield_budget): a typical doIteration is ~16 searches x ~3 levels
@@ -1261,6 +1304,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       int rc = ps_list_games(t);
       if (rc != CB200_OK) return rc;
       t->ps_active = true, t->ps_from_lockstep = true;
+      if (t->profiling && (rc = prof_mark(t, true)) != CB200_OK) return rc;
     }
     if (t->ps_active) {
       int rounds = 0;
@@ -1354,7 +1398,16 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
   const int saved_div = t->stagger_div;
   if (!stagger) t->stagger_div = 0;
   if (!testing) {
+    if (t->profiling) {  // counters may have been reset since the last mark
+      int64_t c4[4];
+      if ((rc = cb200_trainer_counters(t, c4)) != CB200_OK) return rc;
+      t->searches_mark = t->searches_now, t->evals_mark = c4[2];
+    }
     rc = run_selfplay_groups(t, max_iterations);
+    if (rc >= 0 && t->profiling) {
+      const int mr = prof_mark(t, !t->ps_active);
+      if (mr != CB200_OK) return mr;
+    }
     t->stagger_div = saved_div;
     if (rc >= 0) {
       const int lr = drain_logs(t);
@@ -1368,7 +1421,7 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
   if ((t->iterations_done == 0 || t->ps_active) && t->precision[0] == 1 && t->precision[1] == 1 &&
       t->nettc[0].fp16 == t->nettc[1].fp16 && t->P.spe <= kPsRowsPerGame &&
       t->P.num_games <= t->ps_ctas * 16 && !getenv("CB200_NO_PERSISTENT")) {
-    CB_CUDA(cudaStreamSynchronize(G().stream));
+    CB_CUDA(cudaStreamSynchronize(cur_stream()));
     if (!t->ps_active) {
       if ((rc = ps_list_games(t)) != CB200_OK) return rc;
       t->ps_active = true, t->ps_from_lockstep = false;
@@ -1416,7 +1469,7 @@ int cb200_trainer_dump_tree(cb200_trainer *t, int game, int player, int64_t out[
   if (rc) return rc;
   if (game < 0 || game >= t->P.num_games || player < 0 || player > 1)
     return set_error(CB200_ERR_ARG, "bad game/player");
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   int32_t tw[kTreeCtlWords], cw[kCtlWords];
   CB_CUDA(cudaMemcpy(tw, t->P.tree + ((size_t)game * 2 + player) * kTreeCtlWords, sizeof(tw), cudaMemcpyDeviceToHost));
   CB_CUDA(cudaMemcpy(cw, t->P.ctl + (size_t)game * kCtlWords, sizeof(cw), cudaMemcpyDeviceToHost));
@@ -1451,38 +1504,9 @@ struct cb200_tourney {
   int32_t *d_pack_offs = nullptr, *d_iter_offs = nullptr;
 };
 
-static int tourney_ready(cb200_tourney *T) {
-  if (!T) return set_error(CB200_ERR_ARG, "null tourney");
-  if (T->t) return CB200_OK;
+static int tourney_ready_build(cb200_tourney *T, cb200_trainer *t, const std::vector<MatchSide> &sides,
+                               int n_log) {
   const int n = (int)T->matches.size();
-  if (n == 0) return set_error(CB200_ERR_STATE, "tourney has no matches");
-  int max_ms = 1, max_spe = 1;
-  std::vector<MatchSide> sides(2 * (size_t)n);
-  int n_log = 0;
-  for (int i = 0; i < n; ++i) {
-    const int pid[2] = {T->matches[i].first, T->matches[i].second};
-    for (int s = 0; s < 2; ++s) {
-      sides[2 * i + s] = T->players[pid[s]];
-      sides[2 * i + s].log_slot = -1;
-      if (sides[2 * i + s].max_searches > max_ms) max_ms = sides[2 * i + s].max_searches;
-      if (sides[2 * i + s].spe > max_spe) max_spe = sides[2 * i + s].spe;
-    }
-    if (T->logging[i]) {  // log_folder/match_<p1>_<p2>_<index>.txt (tourney.cpp:88-93)
-      sides[2 * i].log_slot = n_log++;
-      auto f = std::make_unique<std::ofstream>(T->log_folder + "/match_" + std::to_string(pid[0]) + "_" +
-                                                   std::to_string(pid[1]) + "_" + std::to_string(i) + ".txt",
-                                               std::ofstream::out);
-      if (!f->is_open()) f.reset();
-      T->log_files.push_back(std::move(f));
-    }
-  }
-  T->log_written.assign(n_log, 0);
-  if (max_spe > max_ms) max_ms = max_spe;
-  // match seeds = successive draws of a default-seeded std::mt19937 (tourney.h:42, tourney.cpp:86)
-  T->t = cb200_trainer_create_shard(n, 0, n, T->log_folder.c_str(), 5489, max_ms, max_spe, 1.0f,
-                                    0.25f, 0, 1);
-  if (!T->t) return CB200_ERR_CUDA;
-  cb200_trainer *t = T->t;
   int rc = fetch_ctl(t);
   if (rc != CB200_OK) return rc;
   const CState st = start_state();
@@ -1504,6 +1528,55 @@ static int tourney_ready(cb200_tourney *T) {
       return rc;
     CB_CUDA(cudaMemset(t->P.log_count, 0, (size_t)n_log * sizeof(int32_t)));
   }
+  return CB200_OK;
+}
+
+static int tourney_ready(cb200_tourney *T) {
+  if (!T) return set_error(CB200_ERR_ARG, "null tourney");
+  if (T->t) return CB200_OK;
+  last_error_ref().clear();
+  const int n = (int)T->matches.size();
+  if (n == 0) return set_error(CB200_ERR_STATE, "tourney has no matches");
+  int max_ms = 1, max_spe = 1;
+  std::vector<MatchSide> sides(2 * (size_t)n);
+  int n_log = 0;
+  T->log_files.clear();
+  for (int i = 0; i < n; ++i) {
+    const int pid[2] = {T->matches[i].first, T->matches[i].second};
+    for (int s = 0; s < 2; ++s) {
+      sides[2 * i + s] = T->players[pid[s]];
+      sides[2 * i + s].log_slot = -1;
+      if (sides[2 * i + s].max_searches > max_ms) max_ms = sides[2 * i + s].max_searches;
+      if (sides[2 * i + s].spe > max_spe) max_spe = sides[2 * i + s].spe;
+    }
+    if (T->logging[i]) {  // log_folder/match_<p1>_<p2>_<index>.txt (tourney.cpp:88-93)
+      sides[2 * i].log_slot = n_log++;
+      auto f = std::make_unique<std::ofstream>(T->log_folder + "/match_" + std::to_string(pid[0]) + "_" +
+                                                   std::to_string(pid[1]) + "_" + std::to_string(i) + ".txt",
+                                               std::ofstream::out);
+      if (!f->is_open()) f.reset();
+      T->log_files.push_back(std::move(f));
+    }
+  }
+  T->log_written.assign(n_log, 0);
+  if (max_spe > max_ms) max_ms = max_spe;
+  // match seeds = successive draws of a default-seeded std::mt19937 (tourney.h:42, tourney.cpp:86)
+  cb200_trainer *t = cb200_trainer_create_shard(n, 0, n, T->log_folder.c_str(), 5489, max_ms, max_spe,
+                                                1.0f, 0.25f, 0, 1);
+  if (!t) return CB200_ERR_CUDA;
+  // the tourney becomes usable (T->t set) only when every buffer exists; a failure on the way
+  // releases the partial allocations so that a later call starts over instead of launching
+  // kernels with null side / offset pointers
+  const int rc = tourney_ready_build(T, t, sides, n_log);
+  if (rc != CB200_OK) {
+    const std::string msg = last_error_ref();
+    cudaFree(T->d_sides), cudaFree(T->d_pack_offs), cudaFree(T->d_iter_offs);
+    T->d_sides = nullptr, T->d_pack_offs = nullptr, T->d_iter_offs = nullptr;
+    cb200_trainer_destroy(t);
+    last_error_ref() = msg;
+    return rc;
+  }
+  T->t = t;
   return CB200_OK;
 }
 
@@ -1532,7 +1605,7 @@ static int tourney_drain_logs(cb200_tourney *T) {
 // offsets + summary for one model id; h_summary = {requests, live matches, error, rows read}
 static int tourney_scan(cb200_tourney *T, int id) {
   cb200_trainer *t = T->t;
-  k_match_scan<<<1, 32, 0, G().stream>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs,
+  k_match_scan<<<1, 32, 0, cur_stream()>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs,
                                          t->d_summary);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
@@ -1604,13 +1677,13 @@ int cb200_tourney_write_requests(cb200_tourney *T, float *game_states, int id) {
   cb200_trainer *t = T->t;
   const int n = t->h_summary[0];
   if (n <= 0) return CB200_OK;
-  k_match_pack<<<(t->P.num_games + 7) / 8, 256, 0, G().stream>>>(t->P, T->d_sides, id,
+  k_match_pack<<<(t->P.num_games + 7) / 8, 256, 0, cur_stream()>>>(t->P, T->d_sides, id,
                                                                  T->d_pack_offs, t->d_rows);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemcpyAsync(game_states, t->d_rows, (size_t)n * CB200_STATE_SIZE * sizeof(float),
-                          cudaMemcpyDeviceToHost, G().stream));
-  CB_CUDA(cudaStreamSynchronize(G().stream));
+                          cudaMemcpyDeviceToHost, cur_stream()));
+  CB_CUDA(cudaStreamSynchronize(cur_stream()));
   return CB200_OK;
 }
 
@@ -1627,12 +1700,12 @@ int cb200_tourney_do_iteration(cb200_tourney *T, const float *eval, const float 
       return set_error(CB200_ERR_ARG, "cb200_tourney_do_iteration: the answer offsets of "
                                       "tourney.cpp:54-62 reach past the caller's buffers");
     CB_CUDA(cudaMemcpyAsync(t->d_eval, eval, (size_t)need * sizeof(float), cudaMemcpyHostToDevice,
-                            G().stream));
+                            cur_stream()));
     CB_CUDA(cudaMemcpyAsync(t->d_probs, probs, (size_t)need * CB200_NUM_MOVES * sizeof(float),
-                            cudaMemcpyHostToDevice, G().stream));
+                            cudaMemcpyHostToDevice, cur_stream()));
   }
   const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
-  k_match_iterate<<<grid, kTreeWarps * 32, 0, G().stream>>>(t->P, T->d_sides, t->d_eval, t->d_probs,
+  k_match_iterate<<<grid, kTreeWarps * 32, 0, cur_stream()>>>(t->P, T->d_sides, t->d_eval, t->d_probs,
                                                             T->d_iter_offs, id);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());

@@ -80,11 +80,11 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
   int64_t cap = (int64_t)sms * 8 * 4;
   int grid = (int)(want < cap ? want : cap);
   if (d_enc)
-    k_game_step<true><<<grid, kStepThreads, 0, G().stream>>>(
+    k_game_step<true><<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
         (float *)d_enc);
   else
-    k_game_step<false><<<grid, kStepThreads, 0, G().stream>>>(
+    k_game_step<false><<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
         nullptr);
   CB_LAUNCHED();

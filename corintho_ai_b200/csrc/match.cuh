@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
   c.mate_turn = 0, c.n_samples = 0;
   c.n_pending = ctl[CW_N_PENDING], c.error = ctl[CW_ERROR], c.spare = ctl[CW_SPARE];
   c.mt_idx = ctl[CW_MT_IDX];
-  c.d_sims = 0, c.d_evals = 0, c.d_moves = 0;
+  c.d_sims = 0, c.d_evals = 0, c.d_moves = 0, c.d_searches = 0;
   c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
   c.t_sel = c.t_exp = c.n_lvl = c.n_exp = c.n_exact = 0;
   c.work = 0, c.yielded = 0;

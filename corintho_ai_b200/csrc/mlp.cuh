@@ -174,7 +174,7 @@ inline int launch_mlp_f32(const NetF32 &net, const ulonglong2 *d_states, const i
   if (n_max <= 0) return CB200_OK;
   int tiles = (n_max + kNetTile - 1) / kNetTile;
   int grid = tiles < sms ? tiles : sms;
-  k_mlp_f32<<<grid, kNetThreads, kMlpSmemBytes, use_stream ? stream : G().stream>>>(
+  k_mlp_f32<<<grid, kNetThreads, kMlpSmemBytes, use_stream ? stream : cur_stream()>>>(
       net.w, d_states, d_n, n_static, d_eval, d_probs, zero2);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());

@@ -565,10 +565,10 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
     const int tiles = (n_max + 127) / 128;
     const int g1 = tiles < sms ? tiles : sms;
     if (net.fp16)
-      k_mlp_tc1<true><<<g1, 128, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+      k_mlp_tc1<true><<<g1, 128, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
           (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
     else
-      k_mlp_tc1<false><<<g1, 128, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+      k_mlp_tc1<false><<<g1, 128, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
           (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
     CB_LAUNCHED();
     CB_CUDA(cudaGetLastError());
@@ -577,10 +577,10 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   const int pairs = (n_max + 255) / 256;
   const int grid = pairs < 2 * sms ? pairs : 2 * sms;
   if (net.fp16)
-    k_mlp_tc<true><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+    k_mlp_tc<true><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
         (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
   else
-    k_mlp_tc<false><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : G().stream>>>(
+    k_mlp_tc<false><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
         (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());

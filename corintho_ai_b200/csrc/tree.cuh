@@ -75,7 +75,7 @@ struct TreeParams {
   ulonglong2 *leaf_state;    // [G][spe]
   ulonglong2 *sample_state;  // [G][kMaxSamples]
   float *sample_probs;       // [G][kMaxSamples][96]
-  long long *counters;       // [G][4] simulations, moves, leaf evals, (unused)
+  long long *counters;       // [G][4] simulations, moves, leaf evals, searches so far
   // fused (device-resident) mode: the kernel instance covers games [game_begin, game_end) of one
   // stream group; request rows are handed out with one atomicAdd per game
   int game_begin, game_end;
@@ -165,7 +165,7 @@ struct Ctx {
   // game control (selfplayer.h:88-111)
   int to_play, parity, result, mate_turn, n_samples, n_pending, error, spare, mt_idx;
   long long d_sims, d_evals;
-  int d_moves;
+  int d_moves, d_searches;
   long long t_ingest, t_search, t_move, n_none, n_copy;
   long long t_sel, t_exp, n_lvl, n_exp, n_exact;
   int work, yielded;
@@ -961,11 +961,13 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
   if (!c.has_root) {
     fresh_tree(c, P, start_state(), 0);
     c.searches_done = 1;
+    c.d_searches += 1;
     request_root(c);
     return false;
   }
   if (c.searches_done == 0 && c.root_visits == 1 && c.root_allv) {
     c.searches_done = 1;
+    c.d_searches += 1;
     request_root(c);
     return false;
   }
@@ -973,6 +975,7 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
   if (c.n_pending > 0 && !resume) receive_eval(c, P, sm, eval, probs, prs, pcs);
   long long t1 = CB_CLOCK();
   c.t_ingest += t1 - t0;
+  const int sd0 = c.searches_done;
   while (c.n_pending < P.spe && c.searches_done < P.max_searches && !r_known(c.root_result) &&
          !c.root_allv && !c.error) {
     if (P.yield_budget > 0 && c.work >= P.yield_budget) {
@@ -982,6 +985,7 @@ __device__ __forceinline__ bool tree_do_iteration(Ctx &c, const TreeParams &P, W
     search(c, P, sm);
   }
   c.t_search += CB_CLOCK() - t1;
+  c.d_searches += c.searches_done - sd0;
   if (c.yielded) return false;
   return (c.searches_done == P.max_searches || r_known(c.root_result)) && c.n_pending == 0;
 }
@@ -1131,6 +1135,7 @@ __device__ __forceinline__ bool receive_opponent_move(Ctx &c, const TreeParams &
   fresh_tree(c, P, st, depth);
   request_root(c);
   c.searches_done = 1;
+  c.d_searches += 1;
   return true;
 }
 
@@ -1329,7 +1334,7 @@ __device__ __forceinline__ void run_game(const TreeParams &P, int g, WarpSm &sm,
   c.mate_turn = ctl[CW_MATE_TURN], c.n_samples = ctl[CW_N_SAMPLES];
   c.n_pending = ctl[CW_N_PENDING], c.error = ctl[CW_ERROR], c.spare = ctl[CW_SPARE];
   c.mt_idx = ctl[CW_MT_IDX];
-  c.d_sims = 0, c.d_evals = 0, c.d_moves = 0;
+  c.d_sims = 0, c.d_evals = 0, c.d_moves = 0, c.d_searches = 0;
   c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
   c.t_sel = c.t_exp = c.n_lvl = c.n_exp = c.n_exact = 0;
   c.work = 0, c.yielded = 0;
@@ -1399,6 +1404,9 @@ __device__ __forceinline__ void run_game(const TreeParams &P, int g, WarpSm &sm,
     if (c.d_sims) atomicAdd((unsigned long long *)cnt, (unsigned long long)c.d_sims);
     if (c.d_moves) atomicAdd((unsigned long long *)cnt + 1, (unsigned long long)c.d_moves);
     if (c.d_evals) atomicAdd((unsigned long long *)cnt + 2, (unsigned long long)c.d_evals);
+    // searches performed in this launch: the running form of the simulation count (equal to
+    // cnt[0] once every game is over), which lets the host attribute simulations to launches
+    if (c.d_searches) atomicAdd((unsigned long long *)cnt + 3, (unsigned long long)c.d_searches);
     if (P.phase_prof) {
       atomicMax(P.phase_prof + 0, (unsigned long long)c.t_ingest);
       atomicMax(P.phase_prof + 1, (unsigned long long)c.t_search);

@@ -161,8 +161,14 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
 int cb200_trainer_reset(cb200_trainer *t, int seed);
 /* Per-kernel-class device timing with CUDA events on the launch stream (bench.py roofline):
  * classes 0 request scan, 1 request pack, 2 network, 3 game step (tree), 4 persistent fused
- * tail (network + game step in one kernel); 5-7 unused. */
+ * tail with 8 games per CTA (network + game step in one kernel), 5 the same with 16 games per
+ * CTA; 6-7 unused. */
 int cb200_trainer_set_profiling(cb200_trainer *t, int enable);
+/* Work attribution of fused training-mode runs made while profiling was enabled: out =
+ * {simulations done by lock-step game-step launches, simulations in total, leaf evaluations
+ * ingested by lock-step launches, leaf evaluations in total}; the remainder belongs to the
+ * persistent kernels (classes 4 and 5). Reset by cb200_trainer_set_profiling. */
+int cb200_trainer_phase_split(cb200_trainer *t, int64_t out[4]);
 int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[8], int64_t out_launches[8]);
 
 /* Debug: per-warp phase cycle maxima/sums of the game-step kernel since the last call:

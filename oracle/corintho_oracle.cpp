@@ -1061,9 +1061,22 @@ void orc_game_step_batch(int64_t n, const uint64_t *states, const uint32_t *rnd,
 }
 
 // ---- Trainer (trainer.cpp:18-256) --------------------------------------------------------
+// Shard of a larger run (the engine's multi-GPU partitioning, not in the reference): global games
+// [first_game, first_game + num_games) of the seed stream of mt19937(seed), parity = global index
+// % 2 (trainer.cpp:238-256 applied to the global index). The staggered start uses local indices;
+// it only moves games between iterations and does not change any per-game result.
+void *orc_trainer_create_shard(int first_game, int num_games, const char *log_folder, int seed,
+                               int max_searches, int searches_per_eval, float c_puct, float epsilon,
+                               int num_logged, int num_threads, int testing);
 void *orc_trainer_create(int num_games, const char *log_folder, int seed, int max_searches,
                          int searches_per_eval, float c_puct, float epsilon, int num_logged,
                          int num_threads, int testing) {
+  return orc_trainer_create_shard(0, num_games, log_folder, seed, max_searches, searches_per_eval,
+                                  c_puct, epsilon, num_logged, num_threads, testing);
+}
+void *orc_trainer_create_shard(int first_game, int num_games, const char *log_folder, int seed,
+                               int max_searches, int searches_per_eval, float c_puct, float epsilon,
+                               int num_logged, int num_threads, int testing) {
   (void)log_folder;
   (void)num_logged;
   Engine *E = new Engine();
@@ -1076,10 +1089,11 @@ void *orc_trainer_create(int num_games, const char *log_folder, int seed, int ma
   E->done.assign(num_games, 0);
   MT gen;
   gen.seed((uint32_t)seed);
+  for (int i = 0; i < first_game; ++i) gen.next();
   for (int i = 0; i < num_games; ++i) {
     GameRec &g = E->games[i];
     g.rng.seed(gen.next());
-    g.parity = i % 2;
+    g.parity = (first_game + i) % 2;
     for (int a = 0; a < 3; ++a) g.arena[a].assign(E->p.arena_words, 0);
     g.tree[0].arena = 0;
     g.tree[1].arena = 1;
@@ -1187,8 +1201,11 @@ void orc_trainer_write_samples(void *h, float *game_states, float *eval_samples,
 float orc_trainer_score(void *h) {  // trainer.cpp:59-68
   Engine *E = static_cast<Engine *>(h);
   float score = 0;
-  for (size_t i = 0; i < E->games.size(); i += 2) score += game_score(E->games[i]);
-  for (size_t i = 1; i < E->games.size(); i += 2) score += 1.0 - game_score(E->games[i]);
+  // even (global) indices first, then odd ones; g.parity == i % 2 unless this is a shard
+  for (size_t i = 0; i < E->games.size(); ++i)
+    if (E->games[i].parity == 0) score += game_score(E->games[i]);
+  for (size_t i = 0; i < E->games.size(); ++i)
+    if (E->games[i].parity == 1) score += 1.0 - game_score(E->games[i]);
   return score / E->games.size();
 }
 
@@ -1198,6 +1215,11 @@ float orc_trainer_avg_mate_length(void *h) {  // trainer.cpp:70-77, selfplayer.c
   for (auto &g : E->games)
     total += g.mate_turn == 0 ? 0 : (int)g.samples.size() - g.mate_turn + 1;
   return static_cast<float>(total) / E->games.size();
+}
+
+void orc_trainer_game_results(void *h, int32_t *results) {  // per game: util.h:58-61 result code
+  Engine *E = static_cast<Engine *>(h);
+  for (size_t i = 0; i < E->games.size(); ++i) results[i] = E->games[i].result;
 }
 
 void orc_trainer_counters(void *h, int64_t out[3]) {

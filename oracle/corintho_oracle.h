@@ -39,6 +39,10 @@ void orc_game_step_batch(int64_t n, const uint64_t *states, const uint32_t *rnd,
 void *orc_trainer_create(int num_games, const char *log_folder, int seed, int max_searches,
                          int searches_per_eval, float c_puct, float epsilon, int num_logged,
                          int num_threads, int testing);
+/* shard [first_game, first_game+num_games) of the same seed stream (engine multi-GPU sharding) */
+void *orc_trainer_create_shard(int first_game, int num_games, const char *log_folder, int seed,
+                               int max_searches, int searches_per_eval, float c_puct, float epsilon,
+                               int num_logged, int num_threads, int testing);
 void orc_trainer_destroy(void *h);
 int orc_trainer_do_iteration(void *h, const float *eval, const float *probs, int to_play);
 int orc_trainer_num_requests(void *h, int to_play);
@@ -51,6 +55,8 @@ float orc_trainer_avg_mate_length(void *h);
 /* exact counters for the metric: simulations = sum over moves of the mover's
  * searches_done_ at chooseMove time; moves = chooseMove calls; leaf_evals = requests served */
 void orc_trainer_counters(void *h, int64_t out[3]);
+/* per game: 0 unfinished, 1 first player lost, 2 draw, 3 first player won (util.h:58-61) */
+void orc_trainer_game_results(void *h, int32_t *results);
 /* white-box dump of one tree for engine-vs-oracle debugging:
  * out = {has_root, used_words, root_visits, root_result, root_all_visited, searches_done,
  *        root_eval_bits}; returns used_words and copies min(cap,used) arena words */

@@ -123,10 +123,18 @@ class _Trainer:
 
     def __init__(self, L, num_games, log_folder="", seed=0, max_searches=1600,
                  searches_per_eval=16, c_puct=1.0, epsilon=0.25, num_logged=0, num_threads=1,
-                 testing=False):
+                 testing=False, first_game=0):
         self.L = L
         self.num_games = num_games
         self.spe = searches_per_eval
+        if first_game:  # oracle only: a shard of a larger run (the engine's multi-GPU partitioning)
+            f = getattr(L.lib, L.prefix + "trainer_create_shard")
+            f.restype = C.c_void_p
+            f.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                          C.c_float, C.c_int, C.c_int, C.c_int]
+            self.h = f(first_game, num_games, log_folder.encode(), seed, max_searches,
+                       searches_per_eval, c_puct, epsilon, num_logged, num_threads, int(testing))
+            return
         self.h = L._t_create(num_games, log_folder.encode(), seed, max_searches,
                              searches_per_eval, c_puct, epsilon, num_logged, num_threads,
                              int(testing))
@@ -271,6 +279,13 @@ class OracleLib(_Lib):
         f.restype = None
         f.argtypes = [C.c_void_p, _i64p]
         self._counters = f
+
+    def game_results(self, trainer):
+        f = self.lib.orc_trainer_game_results
+        f.restype, f.argtypes = None, [C.c_void_p, _i32p]
+        out = np.zeros(trainer.num_games, np.int32)
+        f(trainer.h, out)
+        return out
 
     def counters(self, trainer):
         out = np.zeros(3, np.int64)

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, call A: full GPU test-suite incl. the benchmark-configuration parity tests, then a bench line
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total --format=csv > gpurun_out/r2a_gpu.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2a_tests.log
+tail -15 gpurun_out/r2a_tests.log
+timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/r2a_bench.json 2> gpurun_out/r2a_bench.err
+echo "bench rc=$?"
+tail -c 600 gpurun_out/r2a_bench.json
