@@ -110,6 +110,11 @@ struct cb200_trainer {
   int seed = 0;
   // fused mode: games are split into independent stream groups (no lock-step across groups)
   int n_groups = 1;
+  int lanes = kGameLanes;     // lanes per game in the lock-step kernels (CB200_LANES overrides)
+  int ps_lanes = 32;          // ... and in the persistent kernels (CB200_PS_LANES)
+  int min_blocks = 4;         // resident CTAs per SM the fused game step is compiled for (CB200_MINBLOCKS)
+  int32_t *d_live_list = nullptr;   // [num_games] live games per stream group (TreeParams::live_list)
+  int32_t *d_live_count = nullptr;  // [n_groups]
   std::vector<cudaStream_t> g_stream;
   std::vector<int> g_begin, g_end;
   int32_t *d_gctr = nullptr;  // [n_groups][8] device counters (TreeParams::group_ctr)
@@ -274,13 +279,19 @@ int fetch_summary(cb200_trainer *t) {
 // probs_move_major: answers were written by the tensor-core network as [96][cap]
 int iterate(cb200_trainer *t, const float *d_eval, const float *d_probs, int to_play,
             bool probs_move_major = false) {
-  const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
   const long prs = probs_move_major ? 1 : CB200_NUM_MOVES;
   const long pcs = probs_move_major ? (long)t->cap : 1;
   ProfScope ps(t, 3);
-  k_iterate<false, 4><<<grid, kTreeWarps * 32, 0, cur_stream()>>>(t->P, d_eval, d_probs, prs, pcs, t->d_offs,
-                                                       to_play, t->iterations_done,
-                                                       t->stagger_div);
+  // lanes per game: 16 (two games per warp; the default) or 32 (CB200_LANES=32, for comparison)
+  if (t->lanes == 32) {
+    const int per_cta = kTreeWarps;
+    k_iterate<false, 32, 4><<<(t->P.num_games + per_cta - 1) / per_cta, kTreeWarps * 32, 0, cur_stream()>>>(
+        t->P, d_eval, d_probs, prs, pcs, t->d_offs, to_play, t->iterations_done, t->stagger_div);
+  } else {
+    const int per_cta = kTreeWarps * 2;
+    k_iterate<false, 16, 4><<<(t->P.num_games + per_cta - 1) / per_cta, kTreeWarps * 32, 0, cur_stream()>>>(
+        t->P, d_eval, d_probs, prs, pcs, t->d_offs, to_play, t->iterations_done, t->stagger_div);
+  }
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   if (to_play != 0 && to_play != 1) ++t->iterations_done;
@@ -712,7 +723,11 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
   if (ng < 1) ng = 1;
   while (ng > 1 && num_games / ng < 64) ng /= 2;
   t->n_groups = ng;
-  int per = ((num_games + ng - 1) / ng + kTreeWarps - 1) / kTreeWarps * kTreeWarps;
+  if (const char *env = getenv("CB200_LANES")) t->lanes = atoi(env) == 32 ? 32 : 16;
+  if (const char *env = getenv("CB200_MINBLOCKS")) t->min_blocks = atoi(env);
+  if (const char *env = getenv("CB200_PS_LANES")) t->ps_lanes = atoi(env) == 16 ? 16 : 32;
+  const int per_cta = kTreeWarps * (32 / t->lanes);  // games per CTA of the lock-step kernel
+  int per = ((num_games + ng - 1) / ng + per_cta - 1) / per_cta * per_cta;
   for (int g = 0; g < ng; ++g) {
     int b = g * per, e = b + per < num_games ? b + per : num_games;
     if (b >= num_games) {
@@ -735,6 +750,7 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
   t->ps_ld = t->ps_ctas * 16 * kPsRowsPerGame * 2;  // x2: two row regions in two-model runs
   const size_t ps_rows = (size_t)t->ps_ld;
   if (dmalloc(&t->d_gctr, (size_t)t->n_groups * 8) != CB200_OK ||
+      dmalloc(&t->d_live_list, Gn) != CB200_OK || dmalloc(&t->d_live_count, (size_t)t->n_groups) != CB200_OK ||
       dmalloc(&t->d_ps_list, Gn) != CB200_OK || dmalloc(&t->d_ps_out, 8) != CB200_OK ||
       dmalloc(&t->d_ps_eval[0], ps_rows) != CB200_OK ||
       dmalloc(&t->d_ps_eval[1], ps_rows) != CB200_OK ||
@@ -748,6 +764,7 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
     return nullptr;
   }
   P.game_begin = 0, P.game_end = num_games, P.group_row0 = 0, P.group_ctr = nullptr;
+  P.live_list = nullptr, P.live_count = nullptr;
   P.packed = t->d_packed;
   P.phase_prof = nullptr;
   t->seed = seed;
@@ -837,7 +854,7 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(t->d_raw);
   if (t->h_summary) cudaFreeHost(t->h_summary);
   if (t->h_gctr) cudaFreeHost(t->h_gctr);
-  cudaFree(t->d_gctr);
+  cudaFree(t->d_gctr), cudaFree(t->d_live_list), cudaFree(t->d_live_count);
   for (cudaStream_t st : t->g_stream) cudaStreamDestroy(st);
   for (int m = 0; m < 2; ++m) {
     cudaFree(t->net32[m].w);
@@ -1171,11 +1188,11 @@ static int ps_list_games(cb200_trainer *t) {
 }
 
 extern "C++" {
-template <bool kFp16, int kGames>
+template <bool kFp16, int kGames, int kL>
 static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit_done) {
   static bool attr_set[16] = {false};
   if (t->device < 16 && !attr_set[t->device]) {
-    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<kFp16, kGames>,
+    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<kFp16, kGames, kL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)ps_smem_bytes<kGames>()));
     attr_set[t->device] = true;
@@ -1188,7 +1205,7 @@ static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit
   const int grid = t->ps_n < t->ps_ctas ? t->ps_n : t->ps_ctas;
   // two-model (gating match) runs: model 1 answers the other side's requests
   const uint8_t *w1 = P.testing ? (const uint8_t *)t->nettc[1].w : nullptr;
-  k_selfplay_persistent<kFp16, kGames><<<grid, kGames * 32, ps_smem_bytes<kGames>(), t->g_stream[0]>>>(
+  k_selfplay_persistent<kFp16, kGames, kL><<<grid, kGames * kL, ps_smem_bytes<kGames>(), t->g_stream[0]>>>(
       P, (const uint8_t *)t->nettc[0].w, w1, t->d_ps_list, t->ps_n, ev0, pr0, pcs0, t->d_ps_eval[nxt],
       t->d_ps_probs[nxt], t->ps_ld, t->d_ps_packed, rounds, exit_done, t->iterations_done,
       t->d_ps_out);
@@ -1221,12 +1238,19 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
     int rc;
     {
       ProfScope ps(t, wide ? 5 : 4, st);
+      // lanes per game: one warp (the default: the tail is bound by the serial chain of a game,
+      // which is shortest with 32 lanes) or 16 (CB200_PS_LANES=16)
+      const bool half = t->ps_lanes == 16;
       if (t->nettc[0].fp16)
-        rc = wide ? ps_launch<true, 16>(t, P, rounds, exit_done)
-                  : ps_launch<true, 8>(t, P, rounds, exit_done);
+        rc = wide ? (half ? ps_launch<true, 16, 16>(t, P, rounds, exit_done)
+                          : ps_launch<true, 16, 32>(t, P, rounds, exit_done))
+                  : (half ? ps_launch<true, 8, 16>(t, P, rounds, exit_done)
+                          : ps_launch<true, 8, 32>(t, P, rounds, exit_done));
       else
-        rc = wide ? ps_launch<false, 16>(t, P, rounds, exit_done)
-                  : ps_launch<false, 8>(t, P, rounds, exit_done);
+        rc = wide ? (half ? ps_launch<false, 16, 16>(t, P, rounds, exit_done)
+                          : ps_launch<false, 16, 32>(t, P, rounds, exit_done))
+                  : (half ? ps_launch<false, 8, 16>(t, P, rounds, exit_done)
+                          : ps_launch<false, 8, 32>(t, P, rounds, exit_done));
     }
     if (rc != CB200_OK) return rc;
     CB_CUDA(cudaMemcpyAsync(t->h_ps_out, t->d_ps_out, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1284,6 +1308,8 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   // 16 K registers per SM) and the network in single-tile CTAs of 128 threads that fit beside
   // them, so that one group's network overlaps the other groups' tree work (2-3 % per run).
   const bool overlap = tc && ng > 1 && getenv("CB200_NO_OVERLAP") == nullptr;
+  const bool use_lists = getenv("CB200_NO_LIVE_LIST") == nullptr;
+  std::vector<int> group_live(ng, -1);  // live games per group at the last host sync (-1 = unknown)
   while (max_iterations <= 0 || done_iters < max_iterations) {
     if (!t->ps_active && ps_ok && live_games <= ps_capacity && t->iterations_done > stagger_span) {
       // evaluate the requests queued by the last lock-step game step, then list the live games
@@ -1319,6 +1345,17 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
     const int yb = live_games >= yield_min_live ? yield_budget : 0;
     int batch = 32;
     if (max_iterations > 0 && max_iterations - done_iters < batch) batch = max_iterations - done_iters;
+    // the games of each group that are still live (finished games would leave idle lane groups
+    // behind): rebuilt once per batch on the group's own stream
+    const int per_cta = kTreeWarps * (32 / t->lanes);
+    for (int g = 0; g < ng && use_lists; ++g) {
+      if (!active[g]) continue;
+      TreeParams P = t->P;
+      P.game_begin = t->g_begin[g], P.game_end = t->g_end[g];
+      k_group_live_list<<<1, 32, 0, t->g_stream[g]>>>(P, t->d_live_list, t->d_live_count + g);
+      CB_LAUNCHED();
+      CB_CUDA(cudaGetLastError());
+    }
     for (int i = 0; i < batch; ++i) {
       const int it = t->iterations_done;
       for (int g = 0; g < ng; ++g) {
@@ -1341,18 +1378,29 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
         TreeParams P = t->P;
         P.game_begin = gb, P.game_end = ge, P.group_row0 = row0, P.group_ctr = ctr;
         P.yield_budget = yb;
+        int width = ge - gb;  // lane groups to launch: the group's games, or its live games
+        if (use_lists) {
+          P.live_list = t->d_live_list, P.live_count = t->d_live_count + g;
+          if (group_live[g] >= 0 && group_live[g] < width) width = group_live[g];
+        }
         {
           ProfScope ps(t, 3, st);
-          const dim3 grid((ge - gb + kTreeWarps - 1) / kTreeWarps), block(kTreeWarps * 32);
-#define CB_ITER(MB) \
-  k_iterate<true, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, \
-                                              t->stagger_div)
-          // register budget of the game step (measured over whole runs): 128
-          // registers without spills, or 96 when network CTAs are to share the SM
-          if (overlap) CB_ITER(5);
-          else CB_ITER(4);
+          const dim3 grid((width + per_cta - 1) / per_cta), block(kTreeWarps * 32);
+          if (grid.x > 0) {
+#define CB_ITER(L, MB) \
+  k_iterate<true, L, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, t->stagger_div)
+            // lanes per game x resident CTAs per SM (register budget 65536 / (128 * MB))
+            if (t->lanes == 32) {
+              if (t->min_blocks >= 6) CB_ITER(32, 6);
+              else if (t->min_blocks == 5) CB_ITER(32, 5);
+              else CB_ITER(32, 4);
+            } else {
+              if (t->min_blocks <= 3) CB_ITER(16, 3);
+              else CB_ITER(16, 4);
+            }
 #undef CB_ITER
-          CB_LAUNCHED();
+            CB_LAUNCHED();
+          }
         }
         CB_CUDA(cudaGetLastError());
       }
@@ -1378,6 +1426,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
         return set_error(c[4], "a game overflowed its node arena / path / sample buffer (raise "
                                "CB200_ARENA_NODES) or reached an impossible state");
       if (c[2 + par] == 0 && c[par] == 0) active[g] = 0;
+      group_live[g] = c[2 + par];
       live += c[2 + par];
     }
     live_games = live;

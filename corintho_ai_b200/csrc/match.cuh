@@ -67,14 +67,14 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
   if (!match_selected(ctl, sides, model_id)) return;
   WarpSm &sm = sm_all[warp];
   Ctx c;
-  c.lane = threadIdx.x & 31;
+  c.bind_lanes();
   c.to_play = ctl[CW_TO_PLAY], c.parity = 0, c.result = ctl[CW_RESULT];
   c.mate_turn = 0, c.n_samples = 0;
   c.n_pending = ctl[CW_N_PENDING], c.error = ctl[CW_ERROR], c.spare = ctl[CW_SPARE];
   c.mt_idx = ctl[CW_MT_IDX];
   c.d_sims = 0, c.d_evals = 0, c.d_moves = 0, c.d_searches = 0;
-  c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
-  c.t_sel = c.t_exp = c.n_lvl = c.n_exp = c.n_exact = 0;
+  CB_PROF(c.t_ingest = c.t_search = c.t_move = c.n_none = c.n_copy = 0;
+          c.t_sel = c.t_exp = c.n_lvl = c.n_exp = c.n_exact = 0;)
   c.work = 0, c.yielded = 0;
   c.arenas = P.arenas + (size_t)g * 3 * P.arena_words;
   c.mt = P.mt + (size_t)g * 624;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
         if (!is_random)
           log_pre_move(c.base, c.root_off, c.to_play, c.root_visits, c.root_eval, c.root_result, lrec);
       }
-      __syncwarp();
+      g_sync(c);
     }
     int choice;
     if (is_random) {
@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
     } else {
       c.d_sims += c.searches_done;
       c.d_moves += 1;
-      choice = choose_move(c, Pm, sm, nullptr);
+      choice = choose_move(c, Pm, sm, (float *)nullptr);
       if (c.error) break;
-      __syncwarp();
+      g_sync(c);
     }
     root = do_move(root, choice);
     depth += 1;
