@@ -32,8 +32,10 @@ ALGO_BYTES_PER_SIM = 1670.0      # algorithmic bytes per simulat
 FLOP_PER_EVAL = 253400.0         # unpadded dense FLOPs per leaf evaluation
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_iterate launch with all 4096 games live
 # (65 536 simulations = 109.4 MB algorithmic), from the `ncu --set full` capture summarised in
-# profiles/r01_ncu_k_iterate_k_mlp_tc_v3.txt; the same capture gives 1.36 MB for k_mlp_tc
-NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 146.107136e6 + 54.567680e6, "network": 1.356800e6 + 0.008960e6}
+# profiles/r02_ncu_k_iterate_lanes16_vs_32.txt; profiles/r01_ncu_k_iterate_k_mlp_tc_v3.txt gives
+# 1.36 MB for k_mlp_tc
+NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 146.333184e6 + 52.767232e6, "network": 1.356800e6 + 0.008960e6}
+NCU_SOURCE = "profiles/r02_ncu_k_iterate_lanes16_vs_32.txt, k_iterate<1, 32>"
 
 
 def peaks():
@@ -135,10 +137,17 @@ def cpu_mlp(flat):
     return f
 
 
+_EXACT_SIMS = {}
+
+
 def time_cpu_reference(args, flat, games, budget_s=None):
     """Time the reference's own CPU implementation of the path (oracle/_ref when it was built
     from /root/reference, else the oracle port) on `games` games of the engine's workload.
     Returns dict(value sims/s, moves/s, cores, kind, sample, seconds, play_s, predict_s)."""
+    # the tree (OpenMP in the compiled reference) and the network (torch's own thread pool) take
+    # turns on the same cores: idle workers of either pool must sleep, not spin
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+    os.environ.setdefault("GOMP_SPINCOUNT", "0")
     from oracle.pyoracle import OracleLib, RefLib, have_ref
     kind = "reference" if have_ref() else "port"
     L = RefLib() if kind == "reference" else OracleLib()
@@ -177,14 +186,17 @@ def time_cpu_reference(args, flat, games, budget_s=None):
     # search), measured outside the timed region when the run completed.
     sims = served
     sims_exact = False
-    if complete and games <= 64:
-        O = OracleLib()
-        o = O.trainer(**cfg)
-        from oracle.pyoracle import play_out
-        play_out(o, evaluator=ev_fn)
-        c = O.counters(o)
-        if c["leaf_evals"] == served:
-            sims, sims_exact = c["simulations"], True
+    if complete and games <= 512:
+        key = (games, args.sims, args.spe, args.c_puct, args.epsilon)
+        if key not in _EXACT_SIMS:  # same seed every time: replay once, outside the timed region
+            O = OracleLib()
+            o = O.trainer(**cfg)
+            from oracle.pyoracle import play_out
+            play_out(o, evaluator=ev_fn)
+            c = O.counters(o)
+            _EXACT_SIMS[key] = (c["simulations"], c["leaf_evals"])
+        if _EXACT_SIMS[key][1] == served:
+            sims, sims_exact = _EXACT_SIMS[key][0], True
     return {"value": sims / secs, "unit": "sims/s", "moves_per_sec": moves / secs, "cores": cores,
             "kind": kind, "seconds": secs, "play_seconds": play_s, "predict_seconds": pred_s,
             "simulations": int(sims), "simulations_exact": sims_exact, "leaf_evals": int(served),
@@ -250,11 +262,24 @@ def run_reference_arm(args, rank, world):
         "moves_per_sec": moves / secs,
         "config": dict(workload_desc(args, args.gpus), reference_sample_games=args.ref_games),
         "cpu_baseline": {"value": value, "unit": "sims/s", "cores": last["cores"], "kind": last["kind"],
-                         "sample": last["sample"]},
+                         "sample": last["sample"], "play_seconds": last["play_seconds"],
+                         "predict_seconds": last["predict_seconds"],
+                         "evaluator_free_sims_per_sec": last["simulations"] / max(1e-9, last["play_seconds"])},
         "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def samples_digest(tr):
+    """sha256 over the un-augmented samples of a finished run (game order): packed states, move
+    probabilities, value labels, game indices."""
+    import hashlib
+    st, pr, lb, go = tr.raw_samples()
+    h = hashlib.sha256()
+    for a in (st, pr, lb, go):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
 
 
 def run_engine_arm(args, rank, world, local_rank):
@@ -289,14 +314,36 @@ def run_engine_arm(args, rank, world, local_rank):
     G = args.games_per_gpu
     flat = cb.fold_batchnorm(cb.random_weights(0))
     pinned_w = torch.from_numpy(flat).pin_memory()
-    tr = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
-                    total_games=G * world, first_game=rank * G)
-    tr.set_weights(flat, 0, args.precision)
+
+    def make_trainer():
+        t = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
+                       total_games=G * world, first_game=rank * G)
+        t.set_weights(flat, 0, args.precision)
+        return t
+
+    tr = make_trainer()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed_steps(t):
+        """K steps of the workload: game state re-initialised (untimed), inputs resident in HBM,
+        CUDA events around the run, barrier + synchronize on both sides."""
+        ms, sims, moves, evals, iters = 0.0, 0, 0, 0, 0
+        for k in range(args.steps):
+            t.reset(2000 + k)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            t.run_selfplay(0, stagger=False)
+            e1.record()
+            barrier()
+            ms += e0.elapsed_time(e1)
+            c = t.counters()
+            sims += c["simulations"]; moves += c["moves"]; evals += c["leaf_evals"]; iters += c["iterations"]
+        return ms, sims, moves, evals, iters
 
     # ---- warm-up (untimed)
     for w in range(args.warmup):
@@ -304,120 +351,71 @@ def run_engine_arm(args, rank, world, local_rank):
         tr.run_selfplay(0, stagger=False)
     barrier()
 
-    # ---- device-timed steps: game state re-initialised (untimed), inputs resident in HBM
+    # ---- (1) device-timed steps: `value`
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = L.cb200_launch_count()
-    dev_ms, sims, moves, evals, iters = 0.0, 0, 0, 0, 0
-    for k in range(args.steps):
-        tr.reset(2000 + k)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        tr.run_selfplay(0, stagger=False)
-        e1.record()
-        barrier()
-        dev_ms += e0.elapsed_time(e1)
-        c = tr.counters()
-        sims += c["simulations"]; moves += c["moves"]; evals += c["leaf_evals"]; iters += c["iterations"]
+    dev_ms, sims, moves, evals, iters = timed_steps(tr)
     launches = L.cb200_launch_count() - launches0
-    # ---- same steps again with a CUDA-event pair around every kernel launch for the per-kernel
-    # durations of the roofline. The timed pass above runs several stream groups whose kernels
-    # overlap; a launch duration is only the kernel's own when nothing else runs beside it, so
-    # this pass uses a second trainer with ONE stream group (same games, seeds and results).
-    # The event records cost host time: `value` comes from the pass above, this one is reported
-    # as ms_per_step_profiled.
-    sims_check = tr.counters()["simulations"]
-    del tr
-    gc.collect()
-    saved_groups = os.environ.get("CB200_GROUPS")
-    os.environ["CB200_GROUPS"] = "1"
-    os.environ["CB200_NO_PERSISTENT"] = "1"  # time k_iterate / k_mlp_tc launches over the whole run
-    tr = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
-                    total_games=G * world, first_game=rank * G)
-    if saved_groups is None:
-        del os.environ["CB200_GROUPS"]
-    else:
-        os.environ["CB200_GROUPS"] = saved_groups
-    tr.set_weights(flat, 0, args.precision)
+    digest_timed = samples_digest(tr)
+
+    # ---- (2) the SAME steps on the SAME schedule (stream groups, parking, persistent tail) with a
+    # CUDA-event pair around every kernel launch, recorded on the stream the kernel is launched on:
+    # per-kernel-class durations for the roofline. Kernels of different stream groups overlap, so
+    # the class times add up to more than the step (the overlap factor is reported); the event
+    # records cost host time, so `value` comes from pass (1) and this pass reports
+    # ms_per_step_profiled.
     tr.set_profiling(True)
-    prof_ms, prof_sims, prof_evals = 0.0, 0, 0
-    for k in range(args.steps):
-        tr.reset(2000 + k)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        tr.run_selfplay(0, stagger=False)
-        e1.record()
-        barrier()
-        prof_ms += e0.elapsed_time(e1)
-        c = tr.counters()
-        prof_sims += c["simulations"]; prof_evals += c["leaf_evals"]
-    if c["simulations"] != sims_check:
-        raise SystemExit("bench.py: the single-group pass played different games than the timed pass")
+    prof_ms, prof_sims, _, prof_evals, _ = timed_steps(tr)
     kt = tr.kernel_times()
-    kt.pop("fused_tail", None)
+    split = tr.phase_split()
     tr.set_profiling(False)
-    del os.environ["CB200_NO_PERSISTENT"]
+    digest_prof = samples_digest(tr)
+    if digest_prof != digest_timed:
+        raise SystemExit("bench.py: the profiled pass produced different samples than the timed pass")
+
+    # ---- (3) reference execution of the same steps: ONE stream group, lock-step all the way (no
+    # parking, no persistent kernel). Its kernels run alone, back to back, so its per-launch times
+    # are the kernels' own; and its samples must hash equal to the timed schedule's.
     del tr
     gc.collect()
-    tr = cb.Trainer(G, "", 12345, args.sims, args.spe, args.c_puct, args.epsilon, 0, 1, False,
-                    total_games=G * world, first_game=rank * G)
-    tr.set_weights(flat, 0, args.precision)
-    tr.reset(2000)
-    tr.run_selfplay(0, stagger=False)  # untimed: sizes the pinned sample buffers below
+    saved = {k: os.environ.get(k) for k in ("CB200_GROUPS", "CB200_NO_PERSISTENT", "CB200_YIELD")}
+    os.environ.update(CB200_GROUPS="1", CB200_NO_PERSISTENT="1", CB200_YIELD="0")
+    tr = make_trainer()
+    tr.set_profiling(True)
+    iso_ms, iso_sims, _, iso_evals, _ = timed_steps(tr)
+    kt_iso = tr.kernel_times()
+    tr.set_profiling(False)
+    digest_iso = samples_digest(tr)
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+    if digest_iso != digest_timed:
+        raise SystemExit("bench.py: the single-group lock-step pass produced different samples than the timed pass")
+    del tr
+    gc.collect()
+    tr = make_trainer()
     clocks = sampler.stop() if rank == 0 else None
     game_logic = measure_game_logic(torch, cb, dev) if rank == 0 else None
 
-    # ---- end-to-end steps through the public API with host buffers:
-    # pinned weights -> device, seeds/control blocks -> device, self-play, samples (8 symmetries) -> host
-    e2e_s, e2e_sims, h2d, d2h, gather_s = 0.0, 0, 0, 0, 0.0
-    # pinned host buffers for the samples (8 symmetries), sized from the last timed step
-    cap_rows = int(tr.num_samples() * 8 * 1.25) + 1024
-    pin_gs = torch.empty((cap_rows, 70), dtype=torch.float32).pin_memory()
-    pin_ev = torch.empty((cap_rows,), dtype=torch.float32).pin_memory()
-    pin_pr = torch.empty((cap_rows, 96), dtype=torch.float32).pin_memory()
-    # one untimed end-to-end warm-up (first use allocates the device-side sample buffer)
-    n_w = tr.num_samples()
-    tr.writeSamples(pin_gs.numpy()[:n_w * 8], pin_ev.numpy()[:n_w * 8], pin_pr.numpy()[:n_w * 8])
-    if dist is not None:  # ... and sizes NCCL's buffers / the allocator's blocks for the gather
-        from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
-        ptr, n_rows = tr.raw_samples_device()
-        all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
-        torch.cuda.synchronize()
-    for k in range(args.steps):
-        barrier()
-        t0 = time.perf_counter()
-        tr.set_weights(pinned_w.numpy(), 0, args.precision)
-        tr.reset(3000 + k)
-        tr.run_selfplay(0, stagger=False)
-        n_s = tr.num_samples()
-        if n_s * 8 > cap_rows:
-            raise SystemExit("bench.py: pinned sample buffers too small")
-        gs, ev, pr = pin_gs.numpy()[:n_s * 8], pin_ev.numpy()[:n_s * 8], pin_pr.numpy()[:n_s * 8]
-        tr.writeSamples(gs, ev, pr)
-        if dist is not None:  # all-gather the finished (un-augmented) samples over NCCL
-            from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
-            g0 = time.perf_counter()
-            ptr, n_rows = tr.raw_samples_device()
-            allrows, _ = all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
-            torch.cuda.synchronize()
-            gather_s += time.perf_counter() - g0
-        torch.cuda.synchronize()
-        e2e_s += time.perf_counter() - t0
-        e2e_sims += tr.counters()["simulations"]
-        h2d += flat.nbytes + G * (20 + 24 + 1) * 4  # weights + control blocks, tree headers, seeds
-        d2h += gs.nbytes + ev.nbytes + pr.nbytes
+    # ---- (4) end-to-end steps through the public API with host buffers: pinned weights -> device,
+    # seeds/control blocks -> device, self-play, samples (8 symmetries) -> pinned host memory
+    e2e = run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier)
+    digest_e2e = samples_digest(tr)
+    if digest_e2e != digest_timed:
+        raise SystemExit("bench.py: the end-to-end pass produced different samples than the timed pass")
 
     # ---- aggregate over ranks: max time, summed work
     if dist is not None:
-        tt = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        tt = torch.tensor([dev_ms, e2e["seconds"]], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(tt[0]), float(tt[1])
-        ww = torch.tensor([sims, moves, evals, e2e_sims, launches], device=dev, dtype=torch.int64)
+        dev_ms, e2e["seconds"] = float(tt[0]), float(tt[1])
+        ww = torch.tensor([sims, moves, evals, e2e["sims"], launches], device=dev, dtype=torch.int64)
         dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        sims, moves, evals, e2e_sims, launches = (int(x) for x in ww)
+        sims, moves, evals, e2e["sims"], launches = (int(x) for x in ww)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -425,45 +423,83 @@ def run_engine_arm(args, rank, world, local_rank):
 
     pk = peaks()
     value = sims / (dev_ms * 1e-3)
-    # dominant kernel = the class with the largest summed device time
-    dom = max(kt, key=lambda k: kt[k]["ms"])
-    share = {k: kt[k]["ms"] / max(1e-9, sum(v["ms"] for v in kt.values())) for k in kt}
+    # work per kernel class of the profiled pass: lock-step launches vs persistent kernels
+    ls_sims, ls_evals = split["lockstep_simulations"], split["lockstep_leaf_evals"]
+    tail_sims, tail_evals = split["simulations"] - ls_sims, split["leaf_evals"] - ls_evals
+    tail_ms = kt["fused_tail"]["ms"] + kt["fused_tail_wide"]["ms"]
+    tail_launches = kt["fused_tail"]["launches"] + kt["fused_tail_wide"]["launches"]
+    classes = {
+        "game_step": {"kernel": "k_iterate (tree search game step, lock-step phase)", "ms": kt["game_step"]["ms"],
+                      "launches": kt["game_step"]["launches"], "simulations": ls_sims},
+        "network": {"kernel": "k_mlp_tc (policy/value network, lock-step phase)", "ms": kt["network"]["ms"],
+                    "launches": kt["network"]["launches"], "leaf_evals": ls_evals},
+        "fused_tail": {"kernel": "k_selfplay_persistent (game step + network per CTA, tail phase)", "ms": tail_ms,
+                       "launches": tail_launches, "simulations": tail_sims, "leaf_evals": tail_evals},
+    }
+    total_class_ms = sum(c["ms"] for c in classes.values())
+    dom = max(classes, key=lambda k: classes[k]["ms"])
+    share = {k: classes[k]["ms"] / max(1e-9, total_class_ms) for k in classes}
+
+    def hbm_roof(cls, traffic):
+        c = classes[cls]
+        per_launch_bytes = ALGO_BYTES_PER_SIM * c["simulations"] / max(1, c["launches"])
+        ach = per_launch_bytes / (c["ms"] / max(1, c["launches"]) * 1e-3) / 1e9
+        return {"kernel": c["kernel"], "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic,
+                "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_us": 1e3 * c["ms"] / max(1, c["launches"])}
+
     if dom == "network":
-        per_launch_flop = FLOP_PER_EVAL * prof_evals / max(1, kt["network"]["launches"])
-        ach = per_launch_flop / (kt["network"]["ms"] / kt["network"]["launches"] * 1e-3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        roof = {"kernel": "k_mlp (policy/value network)", "bound": "tensor", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_DENSE_LAUNCH["network"]}
+        c = classes["network"]
+        per_launch_flop = FLOP_PER_EVAL * c["leaf_evals"] / max(1, c["launches"])
+        ach = per_launch_flop / (c["ms"] / max(1, c["launches"]) * 1e-3) / 1e12
+        roof = {"kernel": c["kernel"], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
+                "traffic": NCU_DRAM_BYTES_PER_DENSE_LAUNCH["network"]}
+    elif dom == "fused_tail":
+        roof = hbm_roof("fused_tail", None)
     else:
-        per_launch_bytes = ALGO_BYTES_PER_SIM * prof_sims / max(1, kt["game_step"]["launches"])
-        ach = per_launch_bytes / (kt["game_step"]["ms"] / kt["game_step"]["launches"] * 1e-3) / 1e9
-        peak = pk["hbm_gbs"]
-        roof = {"kernel": "k_iterate (tree search game step)", "bound": "hbm", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": NCU_DRAM_BYTES_PER_DENSE_LAUNCH["game_step"]}
-    roof["traffic_note"] = ("bytes of one launch with every game live (ncu --set full, profiles/"
-                            "r01_ncu_k_iterate_k_mlp_tc_v3.txt): 200.7 MB DRAM for 109.4 MB algorithmic; "
-                            "`achieved` averages over all launches of the run, most of which carry fewer games")
+        roof = hbm_roof("game_step", NCU_DRAM_BYTES_PER_DENSE_LAUNCH["game_step"])
+    roof["traffic_note"] = ("dram__bytes of ONE game-step launch with every game live (ncu --set full, " + NCU_SOURCE +
+                            "): 199.1 MB for 109.4 MB algorithmic; `achieved` averages over all lock-step "
+                            "launches of the run, most of which carry fewer games")
     roof["peak_source"] = pk["source"]
+    roof["measured_on"] = ("the timed schedule itself: %d stream groups, parking, persistent tail; CUDA-event pair per "
+                           "launch on the launching stream (pass 2)" % int(os.environ.get(
+                               "CB200_GROUPS", 6 if G >= 2048 else (2 if G >= 512 else 1))))
     roof["kernel_time_share"] = share
-    roof["kernel_ms"] = {k: kt[k]["ms"] for k in kt}
-    roof["kernel_launches"] = {k: kt[k]["launches"] for k in kt}
-    roof["note"] = ("per-launch durations from CUDA events recorded on the launching stream during a second "
-                    "pass of the same K steps with a single stream group (kernels run alone, back to back). "
-                    "Whole-step algorithmic rates of the timed pass: %.1f GB/s tree traffic, %.2f TFLOP/s network"
-                    % (ALGO_BYTES_PER_SIM * sims / (dev_ms * 1e-3) / 1e9,
-                       FLOP_PER_EVAL * evals / (dev_ms * 1e-3) / 1e12))
-    # secondary roofline of the other heavy kernel, for the record
-    if kt["network"]["launches"]:
-        roof["network_tflops"] = (FLOP_PER_EVAL * prof_evals / (kt["network"]["ms"] * 1e-3)) / 1e12
-    if kt["game_step"]["launches"]:
-        roof["game_step_gbs"] = (ALGO_BYTES_PER_SIM * prof_sims / (kt["game_step"]["ms"] * 1e-3)) / 1e9
+    roof["kernel_ms_per_step"] = {k: classes[k]["ms"] / args.steps for k in classes}
+    roof["kernel_launches_per_step"] = {k: classes[k]["launches"] / args.steps for k in classes}
+    roof["stream_overlap_factor"] = total_class_ms / max(1e-9, prof_ms)
+    roof["note"] = ("sum of kernel-class times per step = %.1f ms = %.2f x the profiled step (%.1f ms): kernels of "
+                    "different stream groups overlap. Whole-step algorithmic rates of the timed pass: %.1f GB/s tree "
+                    "traffic, %.2f TFLOP/s network"
+                    % (total_class_ms / args.steps, total_class_ms / max(1e-9, prof_ms), prof_ms / args.steps,
+                       ALGO_BYTES_PER_SIM * sims / (dev_ms * 1e-3) / 1e9, FLOP_PER_EVAL * evals / (dev_ms * 1e-3) / 1e12))
+    # the other classes, same arithmetic, for the record
+    roof["other"] = {}
+    if classes["game_step"]["launches"] and dom != "game_step":
+        roof["other"]["game_step"] = hbm_roof("game_step", NCU_DRAM_BYTES_PER_DENSE_LAUNCH["game_step"])
+    if tail_launches and dom != "fused_tail":
+        roof["other"]["fused_tail"] = hbm_roof("fused_tail", None)
+    if classes["network"]["launches"]:
+        roof["other"]["network_tflops"] = FLOP_PER_EVAL * ls_evals / (classes["network"]["ms"] * 1e-3) / 1e12
+    # kernels alone (pass 3: one stream group, lock-step all the way)
+    roof["isolated"] = {
+        "ms_per_step": iso_ms / args.steps,
+        "game_step_avg_launch_us": 1e3 * kt_iso["game_step"]["ms"] / max(1, kt_iso["game_step"]["launches"]),
+        "network_avg_launch_us": 1e3 * kt_iso["network"]["ms"] / max(1, kt_iso["network"]["launches"]),
+        "game_step_gbs": ALGO_BYTES_PER_SIM * iso_sims / max(1e-9, kt_iso["game_step"]["ms"] * 1e-3) / 1e9,
+        "network_tflops": FLOP_PER_EVAL * iso_evals / max(1e-9, kt_iso["network"]["ms"] * 1e-3) / 1e12,
+        "game_step_share": kt_iso["game_step"]["ms"] / max(1e-9, kt_iso["game_step"]["ms"] + kt_iso["network"]["ms"]),
+    }
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         r = time_cpu_reference(args, flat, args.ref_games)
         cpu = {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                "moves_per_sec": r["moves_per_sec"], "play_seconds": r["play_seconds"],
-               "predict_seconds": r["predict_seconds"], "simulations_exact": r["simulations_exact"]}
+               "predict_seconds": r["predict_seconds"], "simulations_exact": r["simulations_exact"],
+               "evaluator_free_sims_per_sec": r["simulations"] / max(1e-9, r["play_seconds"])}
 
     line = {
         "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world,
@@ -473,11 +509,14 @@ def run_engine_arm(args, rank, world, local_rank):
         "config": workload_desc(args, world),
         "moves_per_sec": moves / (dev_ms * 1e-3), "leaf_evals_per_sec": evals / (dev_ms * 1e-3),
         "simulations_per_step": sims / args.steps, "iterations_per_step": iters / args.steps,
-        "ms_per_step_profiled": prof_ms / args.steps, "stream_groups": int(os.environ.get("CB200_GROUPS", 6 if G >= 2048 else (2 if G >= 512 else 1))),
+        "ms_per_step_profiled": prof_ms / args.steps,
+        "samples_sha256": digest_timed,
+        "samples_check": "timed pass == profiled pass == single-group lock-step pass == end-to-end pass",
         "game_logic": game_logic,
-        "e2e": {"value": e2e_sims / e2e_s, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps,
-                "d2h_bytes_per_step": d2h // args.steps, "seconds_per_step": e2e_s / args.steps,
-                "nccl_gather_seconds_per_step": gather_s / args.steps if world > 1 else 0.0},
+        "e2e": {"value": e2e["sims"] / e2e["seconds"], "unit": "sims/s", "h2d_bytes_per_step": e2e["h2d"] // args.steps,
+                "d2h_bytes_per_step": e2e["d2h"] // args.steps, "seconds_per_step": e2e["seconds"] / args.steps,
+                "nccl_gather_seconds_per_step": e2e["gather_s"] / args.steps if world > 1 else 0.0,
+                "path": e2e["path"]},
         "gpu_launches": int(launches),
         "roofline": roof,
         "cpu_baseline": cpu,
@@ -486,6 +525,57 @@ def run_engine_arm(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
+    """End-to-end steps through the public API: host weights in, host samples out (all 8
+    symmetries of every move, 668 B per row). The samples of finished games are streamed to
+    the trainer's pinned host buffers during the run (Trainer.stream_samples), so the 370 MB
+    device->host transfer overlaps the self-play instead of following it; the timed region ends
+    when the last row is in host memory. Rows come in game completion order with a game index
+    per sample (see include/corintho_b200.h)."""
+    tr.stream_samples(-1)
+    tr.reset(2000)
+    tr.run_selfplay(0, stagger=False)  # untimed warm-up of the streaming path
+    tr.streamed_samples()
+    if dist is not None:  # ... and of NCCL's buffers / the allocator's blocks for the gather
+        from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
+        ptr, n_rows = tr.raw_samples_device()
+        all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
+        torch.cuda.synchronize()
+    out = {"seconds": 0.0, "sims": 0, "h2d": 0, "d2h": 0, "gather_s": 0.0,
+           "path": "set_weights(pinned host) + reset + run_selfplay with streamed samples (8 symmetries, "
+                   "completion order + game index) + streamed_samples() = all rows in pinned host memory"}
+    for k in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        tr.set_weights(pinned_w.numpy(), 0, args.precision)
+        tr.reset(2000 + k)
+        tr.run_selfplay(0, stagger=False)
+        gs, ev, pr, game_of = tr.streamed_samples()
+        if dist is not None:  # all-gather the finished (un-augmented) samples over NCCL
+            from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
+            g0 = time.perf_counter()
+            ptr, n_rows = tr.raw_samples_device()
+            all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
+            torch.cuda.synchronize()
+            out["gather_s"] += time.perf_counter() - g0
+        torch.cuda.synchronize()
+        out["seconds"] += time.perf_counter() - t0
+        if game_of.shape[0] != tr.num_samples():
+            raise SystemExit("bench.py: the streamed samples are incomplete")
+        out["sims"] += tr.counters()["simulations"]
+        out["h2d"] += flat.nbytes + G * (20 + 24 + 1) * 4  # weights + control blocks, tree headers, seeds
+        out["d2h"] += gs.nbytes + ev.nbytes + pr.nbytes + game_of.nbytes
+    # the streamed rows of the last step, brought into game order, must be writeSamples' rows
+    order = np.argsort(game_of, kind="stable")
+    rows = (order[:, None] * 8 + np.arange(8)[None, :]).ravel()
+    g2, e2, p2 = tr.write_samples()
+    if not (np.array_equal(gs[rows].view(np.uint32), g2.view(np.uint32)) and
+            np.array_equal(ev[rows].view(np.uint32), e2.view(np.uint32)) and
+            np.array_equal(pr[rows].view(np.uint32), p2.view(np.uint32))):
+        raise SystemExit("bench.py: streamed samples differ from Trainer::writeSamples")
+    return out
 
 
 def main():
@@ -500,7 +590,7 @@ def main():
     ap.add_argument("--c-puct", type=float, default=1.0)
     ap.add_argument("--epsilon", type=float, default=0.25)
     ap.add_argument("--precision", default=os.environ.get("CB200_PRECISION", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--ref-games", type=int, default=32, help="games in one CPU-reference sample")
+    ap.add_argument("--ref-games", type=int, default=256, help="games in one CPU-reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -80,6 +80,8 @@ def lib():
         "cb200_trainer_write_raw_samples": (i32, [vp, vp, vp, vp, vp]),
         "cb200_trainer_game_results": (i32, [vp, vp]),
         "cb200_trainer_raw_samples_device": (i32, [vp, vp, vp]),
+        "cb200_trainer_stream_samples": (i32, [vp, i64]),
+        "cb200_trainer_streamed_samples": (i32, [vp, vp, vp, vp, vp, vp]),
         "cb200_trainer_set_weights": (i32, [vp, i32, vp, C.c_size_t, i32]),
         "cb200_trainer_evaluate": (i32, [vp, i32, i32, vp, vp, vp]),
         "cb200_trainer_run_selfplay": (i32, [vp, i32, i32]),
@@ -385,6 +387,30 @@ class Trainer:
         n = C.c_int()
         _check(lib().cb200_trainer_raw_samples_device(self._h, C.byref(ptr), C.byref(n)))
         return ptr.value or 0, n.value
+
+    def stream_samples(self, max_samples=-1):
+        """Enable (or with 0 disable) streaming of finished games' samples to pinned host memory
+        during run_selfplay (see cb200_trainer_stream_samples in the C header)."""
+        _check(lib().cb200_trainer_stream_samples(self._h, int(max_samples)))
+
+    def streamed_samples(self):
+        """(game_states[n*8,70], eval_samples[n*8], prob_samples[n*8,96], game_of[n]) as numpy views
+        of the trainer's pinned host buffers (valid until the next reset / run); rows in game
+        completion order, 8 consecutive rows per sample."""
+        gs, ev, pr, go = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_int()
+        _check(lib().cb200_trainer_streamed_samples(self._h, C.byref(gs), C.byref(ev), C.byref(pr),
+                                                    C.byref(go), C.byref(n)))
+        n = n.value
+        if n == 0:
+            return (np.zeros((0, STATE_SIZE), np.float32), np.zeros(0, np.float32),
+                    np.zeros((0, NUM_MOVES), np.float32), np.zeros(0, np.int32))
+
+        def view(ptr, ctype, shape):
+            count = int(np.prod(shape))
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).reshape(shape)
+        return (view(gs, C.c_float, (n * 8, STATE_SIZE)), view(ev, C.c_float, (n * 8,)),
+                view(pr, C.c_float, (n * 8, NUM_MOVES)), view(go, C.c_int32, (n,)))
 
     def game_results(self):
         out = np.zeros(self.num_games, np.int32)

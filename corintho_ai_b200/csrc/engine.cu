@@ -31,17 +31,22 @@ __device__ uint8_t d_space_sym[8 * 16];
 __device__ uint8_t d_move_sym[8 * 96];
 
 // SelfPlayer::writeSamples (selfplayer.cpp:79-113): 8 symmetries per stored sample.
-// One warp per (game, sample); soff[g] = index of game g's first sample row.
+// One warp per (game, sample); soff[g] = index of game g's first sample row. Streaming form
+// (emitted != nullptr): only the games stamped `stamp` by k_emit_assign take part, and game_of
+// receives the global game index of every (un-augmented) sample.
 __global__ void __launch_bounds__(256)
     k_write_samples(TreeParams P, const int32_t *__restrict__ soff, float *__restrict__ gs_out,
-                    float *__restrict__ ev_out, float *__restrict__ pr_out) {
+                    float *__restrict__ ev_out, float *__restrict__ pr_out,
+                    const int32_t *__restrict__ emitted, int stamp, int32_t *__restrict__ game_of) {
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int g = w / kMaxSamples, i = w - g * kMaxSamples;
   if (g >= P.num_games) return;
+  if (emitted != nullptr && emitted[g] != stamp) return;
   const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
   const int ns = ctl[CW_N_SAMPLES];
   if (i >= ns) return;
+  if (game_of != nullptr && lane == 0) game_of[soff[g] + i] = P.first_game + g;
   const ulonglong2 sv = P.sample_state[(size_t)g * kMaxSamples + i];
   const CState st{sv.x, sv.y};
   const float *pr = P.sample_probs + ((size_t)g * kMaxSamples + i) * CB200_NUM_MOVES;
@@ -58,6 +63,27 @@ __global__ void __launch_bounds__(256)
     float *po = pr_out + (row + k) * CB200_NUM_MOVES;
     for (int j = lane; j < CB200_NUM_MOVES; j += 32) po[j] = pr[d_move_sym[k * 96 + j]];
   }
+}
+
+// Streaming sample output: finished games that have not been emitted yet get their block of
+// sample rows (one atomicAdd per game: completion order, not game order) and the stamp of this
+// emission round. ctr[0] = samples handed out so far, ctr[1] = 1 if a game did not fit.
+__global__ void k_emit_assign(TreeParams P, int32_t *__restrict__ emitted, int32_t *__restrict__ ctr,
+                              int cap_samples, int32_t *__restrict__ soff, int stamp) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.num_games) return;
+  const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
+  if (!*(volatile const int32_t *)(ctl + CW_DONE) || emitted[g] != 0) return;
+  __threadfence();  // pairs with the fence before the game's CW_DONE store
+  const int ns = *(volatile const int32_t *)(ctl + CW_N_SAMPLES);
+  const int base = atomicAdd(ctr, ns);
+  if (base + ns > cap_samples) {
+    atomicSub(ctr, ns);
+    ctr[1] = 1;
+    return;
+  }
+  soff[g] = base;
+  emitted[g] = stamp;
 }
 
 // Un-augmented samples as 102-float rows for the NCCL gather: 4 words of cstate (bit-cast),
@@ -137,6 +163,22 @@ struct cb200_trainer {
   int ps_cur = 0;                  // buffer holding the answers of the queued requests
   bool ps_active = false;          // the games now live in the persistent loop's rows
   bool ps_from_lockstep = false;   // ... except that the next launch reads d_eval/d_probs first
+  // streaming sample output (cb200_trainer_stream_samples): finished games' samples, all 8
+  // symmetries, go to pinned host memory while the run continues
+  bool stream_on = false;
+  size_t st_cap = 0;               // allocated capacity in (un-augmented) samples
+  size_t st_limit = 0;             // capacity requested by the caller (<= st_cap)
+  float *d_st = nullptr;           // device staging [cap*8][70] | [cap*8] | [cap*8][96]
+  float *h_st = nullptr;           // pinned host mirror, same layout
+  int32_t *d_st_game = nullptr, *h_st_game = nullptr;  // [cap] global game index per sample
+  int32_t *d_st_ctr = nullptr, *h_st_ctr = nullptr;    // [2] samples handed out, overflow flag
+  int32_t *d_emitted = nullptr;    // [num_games] emission round of a game's samples (0 = not yet)
+  int32_t *d_st_soff = nullptr;    // [num_games] first sample row of an emitted game
+  cudaStream_t st_stream = nullptr;
+  cudaEvent_t st_ev = nullptr;
+  bool st_pending = false;         // st_ev marks a counter read-back that has not been consumed
+  size_t st_copied = 0;            // samples whose device->host copy has been queued
+  int st_round = 0;
   // per-kernel-class CUDA-event timing (bench.py roofline): 0 scan, 1 pack, 2 network, 3 iterate
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -552,6 +594,13 @@ static int init_state(cb200_trainer *t) {
   }
   t->iterations_done = 0;
   t->ps_active = false, t->ps_from_lockstep = false, t->ps_n = 0, t->ps_cur = 0;
+  if (t->stream_on) {
+    CB_CUDA(cudaStreamSynchronize(t->st_stream));
+    CB_CUDA(cudaMemset(t->d_emitted, 0, Gn * sizeof(int32_t)));
+    CB_CUDA(cudaMemset(t->d_st_ctr, 0, 2 * sizeof(int32_t)));
+    t->st_pending = false, t->st_copied = 0, t->st_round = 0;
+    t->h_st_ctr[0] = t->h_st_ctr[1] = 0;
+  }
   return CB200_OK;
 }
 
@@ -852,6 +901,12 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
   cudaFree(t->d_samp);
   cudaFree(t->d_raw);
+  cudaFree(t->d_st), cudaFree(t->d_st_game), cudaFree(t->d_st_ctr), cudaFree(t->d_emitted), cudaFree(t->d_st_soff);
+  if (t->h_st) cudaFreeHost(t->h_st);
+  if (t->h_st_game) cudaFreeHost(t->h_st_game);
+  if (t->h_st_ctr) cudaFreeHost(t->h_st_ctr);
+  if (t->st_ev) cudaEventDestroy(t->st_ev);
+  if (t->st_stream) cudaStreamDestroy(t->st_stream);
   if (t->h_summary) cudaFreeHost(t->h_summary);
   if (t->h_gctr) cudaFreeHost(t->h_gctr);
   cudaFree(t->d_gctr), cudaFree(t->d_live_list), cudaFree(t->d_live_count);
@@ -958,7 +1013,7 @@ int cb200_trainer_write_samples(cb200_trainer *t, float *game_states, float *eva
                                     cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
       const long long warps = (long long)Gn * kMaxSamples;
-      k_write_samples<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(t->P, t->d_soff, d_gs, d_ev, d_pr);
+      k_write_samples<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(t->P, t->d_soff, d_gs, d_ev, d_pr, nullptr, 0, nullptr);
       CB_LAUNCHED();
       e = cudaGetLastError();
     }
@@ -1121,6 +1176,70 @@ int cb200_trainer_raw_samples_device(cb200_trainer *t, void **rows_device, int *
   return CB200_OK;
 }
 
+static int emit_finished(cb200_trainer *t, bool final);
+
+int cb200_trainer_stream_samples(cb200_trainer *t, int64_t max_samples) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (t->P.testing) return set_error(CB200_ERR_STATE, "testing-mode trainers produce no samples");
+  if (max_samples == 0) {
+    t->stream_on = false;
+    return CB200_OK;
+  }
+  if (max_samples < 0) max_samples = (int64_t)t->P.num_games * 32;  // ~20 moves per game on average
+  if (max_samples > (int64_t)t->P.num_games * kMaxSamples) max_samples = (int64_t)t->P.num_games * kMaxSamples;
+  if (max_samples * 8 >= (1ll << 31)) return set_error(CB200_ERR_ARG, "max_samples too large");
+  if ((size_t)max_samples > t->st_cap) {
+    cudaFree(t->d_st), cudaFree(t->d_st_game);
+    if (t->h_st) cudaFreeHost(t->h_st);
+    if (t->h_st_game) cudaFreeHost(t->h_st_game);
+    t->d_st = nullptr, t->d_st_game = nullptr, t->h_st = nullptr, t->h_st_game = nullptr, t->st_cap = 0;
+    const size_t floats = (size_t)max_samples * 8 * (CB200_STATE_SIZE + 1 + CB200_NUM_MOVES);
+    if ((rc = dmalloc(&t->d_st, floats)) != CB200_OK || (rc = dmalloc(&t->d_st_game, (size_t)max_samples)) != CB200_OK)
+      return rc;
+    CB_CUDA(cudaMallocHost((void **)&t->h_st, floats * sizeof(float)));
+    CB_CUDA(cudaMallocHost((void **)&t->h_st_game, (size_t)max_samples * sizeof(int32_t)));
+    t->st_cap = (size_t)max_samples;
+  }
+  if (!t->d_emitted) {
+    const size_t Gn = (size_t)t->P.num_games;
+    if ((rc = dmalloc(&t->d_emitted, Gn)) != CB200_OK || (rc = dmalloc(&t->d_st_soff, Gn)) != CB200_OK ||
+        (rc = dmalloc(&t->d_st_ctr, 2)) != CB200_OK)
+      return rc;
+    CB_CUDA(cudaMallocHost((void **)&t->h_st_ctr, 2 * sizeof(int32_t)));
+    CB_CUDA(cudaStreamCreateWithFlags(&t->st_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreateWithFlags(&t->st_ev, cudaEventDisableTiming));
+  }
+  CB_CUDA(cudaStreamSynchronize(t->st_stream));
+  CB_CUDA(cudaMemset(t->d_emitted, 0, (size_t)t->P.num_games * sizeof(int32_t)));
+  CB_CUDA(cudaMemset(t->d_st_ctr, 0, 2 * sizeof(int32_t)));
+  t->st_pending = false, t->st_copied = 0, t->st_round = 0;
+  t->h_st_ctr[0] = t->h_st_ctr[1] = 0;
+  t->st_limit = (size_t)max_samples;
+  t->stream_on = true;
+  return CB200_OK;
+}
+
+int cb200_trainer_streamed_samples(cb200_trainer *t, const float **game_states, const float **eval_samples,
+                                   const float **prob_samples, const int32_t **game_of, int *n_samples) {
+  int rc = guard(t);
+  if (rc) return rc;
+  if (!t->stream_on) return set_error(CB200_ERR_STATE, "cb200_trainer_stream_samples was not enabled");
+  if (!game_states || !eval_samples || !prob_samples || !game_of || !n_samples)
+    return set_error(CB200_ERR_ARG, "null output");
+  // work queued on the self-play streams is complete when run_selfplay has returned
+  if ((rc = emit_finished(t, true)) != CB200_OK) return rc;
+  if (t->h_st_ctr[1] != 0)
+    return set_error(CB200_ERR_OVERFLOW, "the sample staging buffer is too small for this run: enable streaming "
+                                         "with a larger max_samples (or use cb200_trainer_write_samples)");
+  const size_t R = t->st_cap * 8;
+  *game_states = t->h_st, *eval_samples = t->h_st + R * CB200_STATE_SIZE;
+  *prob_samples = t->h_st + R * CB200_STATE_SIZE + R;
+  *game_of = t->h_st_game;
+  *n_samples = (int)t->st_copied;
+  return CB200_OK;
+}
+
 int cb200_trainer_set_weights(cb200_trainer *t, int model, const float *weights, size_t n_floats,
                               int precision) {
   int rc = guard(t);
@@ -1215,6 +1334,52 @@ static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit
 }
 }  // extern "C++"
 
+// Streaming sample output. Called whenever the host has control during a fused run (every batch
+// of lock-step iterations, between persistent launches) and once at the end (final): queues the
+// device->host copy of the rows the PREVIOUS round produced (their count has reached the host by
+// now), then stamps the games that finished since and expands their samples into the staging
+// buffer. Everything runs on its own stream, beside the self-play kernels.
+static int emit_finished(cb200_trainer *t, bool final) {
+  if (!t->stream_on) return CB200_OK;
+  cudaStream_t st = t->st_stream;
+  const size_t R = t->st_cap * 8;
+  float *d_gs = t->d_st, *d_ev = d_gs + R * CB200_STATE_SIZE, *d_pr = d_ev + R;
+  float *h_gs = t->h_st, *h_ev = h_gs + R * CB200_STATE_SIZE, *h_pr = h_ev + R;
+  for (int pass = 0; pass < (final ? 2 : 1); ++pass) {
+    if (t->st_pending) {
+      CB_CUDA(cudaEventSynchronize(t->st_ev));
+      t->st_pending = false;
+      const size_t total = (size_t)t->h_st_ctr[0], a = t->st_copied;
+      if (total > a) {
+        const size_t n = total - a;
+        CB_CUDA(cudaMemcpyAsync(h_gs + a * 8 * CB200_STATE_SIZE, d_gs + a * 8 * CB200_STATE_SIZE,
+                                n * 8 * CB200_STATE_SIZE * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaMemcpyAsync(h_ev + a * 8, d_ev + a * 8, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaMemcpyAsync(h_pr + a * 8 * CB200_NUM_MOVES, d_pr + a * 8 * CB200_NUM_MOVES,
+                                n * 8 * CB200_NUM_MOVES * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaMemcpyAsync(t->h_st_game + a, t->d_st_game + a, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        t->st_copied = total;
+      }
+    }
+    if (pass == 1) break;
+    const int Gn = t->P.num_games;
+    ++t->st_round;
+    k_emit_assign<<<(Gn + 255) / 256, 256, 0, st>>>(t->P, t->d_emitted, t->d_st_ctr, (int)t->st_limit, t->d_st_soff,
+                                                     t->st_round);
+    CB_LAUNCHED();
+    const long long warps = (long long)Gn * kMaxSamples;
+    k_write_samples<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(t->P, t->d_st_soff, d_gs, d_ev, d_pr, t->d_emitted,
+                                                                 t->st_round, t->d_st_game);
+    CB_LAUNCHED();
+    CB_CUDA(cudaGetLastError());
+    CB_CUDA(cudaMemcpyAsync(t->h_st_ctr, t->d_st_ctr, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaEventRecord(t->st_ev, st));
+    t->st_pending = true;
+  }
+  if (final) CB_CUDA(cudaStreamSynchronize(st));
+  return CB200_OK;
+}
+
 static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bool *all_done) {
   cudaStream_t st = t->g_stream[0];
   *rounds_done = 0, *all_done = false;
@@ -1272,6 +1437,7 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
       break;
     }
     if ((rc = ps_list_games(t)) != CB200_OK) return rc;
+    if ((rc = emit_finished(t, false)) != CB200_OK) return rc;
   }
   return CB200_OK;
 }
@@ -1434,6 +1600,8 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       result = 1;
       break;
     }
+    const int er = emit_finished(t, false);
+    if (er != CB200_OK) return er;
   }
   return result;
 }

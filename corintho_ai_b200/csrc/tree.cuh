@@ -1512,7 +1512,12 @@ __device__ __forceinline__ void run_game(const TreeParams &P, int g, WarpSm &sm,
     ctl[CW_TO_PLAY] = c.to_play, ctl[CW_RESULT] = c.result, ctl[CW_MATE_TURN] = c.mate_turn;
     ctl[CW_N_SAMPLES] = c.n_samples, ctl[CW_N_PENDING] = c.n_pending, ctl[CW_ERROR] = c.error;
     ctl[CW_SPARE] = c.spare, ctl[CW_MT_IDX] = c.mt_idx;
-    if (done) ctl[CW_DONE] = 1;
+    if (done) {
+      // a finished game's samples may be picked up by the streaming emit kernel on another
+      // stream: everything the game wrote must be visible before the flag is
+      __threadfence();
+      ctl[CW_DONE] = 1;
+    }
     long long *cnt = P.counters + (size_t)g * 4;
     // reductions without a return value: nothing waits for the old counter values
     if (c.d_sims) atomicAdd((unsigned long long *)cnt, (unsigned long long)c.d_sims);

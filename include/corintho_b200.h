@@ -133,6 +133,22 @@ int cb200_trainer_write_raw_samples(cb200_trainer *t, uint64_t *states, float *p
  * {cstate as 4 bit-cast words, probs[96], label, global game index bit-cast}; the buffer is owned
  * by the trainer and valid until the next call. */
 int cb200_trainer_raw_samples_device(cb200_trainer *t, void **rows_device, int *n_rows);
+/* Streaming sample output for fused runs. Once enabled, cb200_trainer_run_selfplay expands the
+ * samples of every FINISHED game (all 8 symmetries: exactly the rows Trainer::writeSamples
+ * produces for that game, selfplayer.cpp:79-113) on the device and copies them to pinned host
+ * memory owned by the trainer while the remaining games keep playing, so that the device->host
+ * transfer overlaps the run instead of following it. Rows arrive in game COMPLETION order:
+ * game_of[i] is the global game index of sample i, whose rows are 8*i .. 8*i+7 (a stable sort by
+ * game_of restores writeSamples' order; a trainer that shuffles its samples need not bother).
+ * max_samples: capacity in un-augmented samples (< 0: num_games * 32; 0: switch streaming off).
+ * cb200_trainer_streamed_samples waits for the outstanding copies and returns host pointers that
+ * stay valid until the next reset / run; CB200_ERR_OVERFLOW if the capacity was too small (the
+ * run itself is unaffected and cb200_trainer_write_samples still works). */
+int cb200_trainer_stream_samples(cb200_trainer *t, int64_t max_samples);
+int cb200_trainer_streamed_samples(cb200_trainer *t, const float **game_states /* [n*8][70] */,
+                                   const float **eval_samples /* [n*8] */,
+                                   const float **prob_samples /* [n*8][96] */,
+                                   const int32_t **game_of /* [n] */, int *n_samples);
 /* per game: result (util.h:58-61: 1 first player lost, 2 draw, 3 first player won) */
 int cb200_trainer_game_results(cb200_trainer *t, int32_t *results /* [num_games] */);
 

@@ -115,3 +115,82 @@ def test_raw_samples_device_rows_match_host_rows():
     rows = device_rows_as_tensor(ptr, n, 102, torch.device("cuda", 0)).cpu().numpy()
     assert n == st.shape[0]
     assert rows.tobytes() == pack_raw_samples(st, pr, lb, go, first_game=0).tobytes()
+
+
+def test_streamed_samples_equal_write_samples():
+    """Streaming sample output (finished games' rows copied to pinned host memory during the
+    run, completion order) holds exactly Trainer::writeSamples' rows: a stable sort by game
+    index restores trainer.cpp:103-113's order byte for byte. Also across reset()."""
+    flat = cb.fold_batchnorm(cb.random_weights(4))
+    t = cb.Trainer(300, "", 3, 48, 16, 1.0, 0.25)
+    t.set_weights(flat, 0, "bf16")
+    t.stream_samples()
+    for seed in (3, 11):
+        t.reset(seed)
+        assert t.run_selfplay(0, stagger=False)
+        gs, ev, pr, game_of = t.streamed_samples()
+        assert game_of.shape[0] == t.num_samples()
+        assert len(np.unique(game_of)) == 300
+        order = np.argsort(game_of, kind="stable")
+        rows = (order[:, None] * 8 + np.arange(8)[None, :]).ravel()
+        g2, e2, p2 = t.write_samples()
+        assert gs[rows].tobytes() == g2.tobytes()
+        assert ev[rows].tobytes() == e2.tobytes()
+        assert pr[rows].tobytes() == p2.tobytes()
+    # a capacity that is too small is reported, and the classic path still works
+    t.stream_samples(100)
+    t.reset(3)
+    assert t.run_selfplay(0, stagger=False)
+    with pytest.raises(cb.Corintho200Error):
+        t.streamed_samples()
+    assert t.write_samples()[0].shape[0] == t.num_samples() * 8
+
+
+def test_sample_folder_written_from_the_engine(tmp_path, oracle):
+    """SURVEY 8f-2 end to end: the CUDA Trainer's samples go through save_samples into the
+    reference's on-disk layout (main.pyx:189-204) and equal the oracle's for the same run."""
+    from corintho_ai_b200.samples import load_samples, save_samples
+    cfg = (6, 21, 64, 16, 1.0, 0.25, False)
+    eng = make_engine(cfg)
+    run_trainer(eng, synth_eval)
+    rows = save_samples(eng, str(tmp_path / "samples" / "gen_3"))
+    assert rows == eng.num_samples() * 8 and rows > 0
+    for name in ("game_states", "evaluation_labels", "probability_labels"):
+        z = np.load(tmp_path / "samples" / "gen_3" / (name + ".npz"))
+        assert z.files == ["arr_0"] and z["arr_0"].dtype == np.float32
+    gs, ev, pr = load_samples(str(tmp_path / "samples" / "gen_3"))
+    o = oracle.trainer(num_games=6, seed=21, max_searches=64, searches_per_eval=16, c_puct=1.0, epsilon=0.25)
+    r = run_trainer(o, synth_eval)
+    assert gs.tobytes() == r["samples"][0].tobytes()
+    assert ev.tobytes() == r["samples"][1].tobytes()
+    assert pr.tobytes() == r["samples"][2].tobytes()
+
+
+def test_raw_sample_buffer_survives_growth_of_the_augmented_buffer():
+    """Regression (advisor, round 1): write_samples used to free the raw-sample device buffer
+    when its own buffer grew; the next raw_samples_device then wrote into (or freed again) memory
+    it no longer owned. Sequence: few samples -> both buffers sized small -> many samples -> the
+    augmented buffer grows -> raw rows again."""
+    import torch
+    from corintho_ai_b200.dist import device_rows_as_tensor
+    flat = cb.fold_batchnorm(cb.random_weights(2))
+    t = cb.Trainer(96, "", 5, 48, 16, 1.0, 0.25)
+    t.set_weights(flat, 0, "fp32")
+    assert not t.run_selfplay(12, stagger=False)  # a few moves per game only
+    few = t.num_samples()
+    assert few > 0
+    t.write_samples()
+    ptr0, n0 = t.raw_samples_device()
+    assert n0 == few
+    done = t.run_selfplay(0, stagger=False)
+    assert done and t.num_samples() * 8 > (few * 8) * 5 // 4 + 1024  # the cached buffer must grow
+    t.write_samples()
+    ptr1, n1 = t.raw_samples_device()
+    st, pr, lb, go = t.raw_samples()
+    assert n1 == t.num_samples()
+    dev_rows = device_rows_as_tensor(ptr1, n1, 102, torch.device("cuda", 0)).cpu().numpy()
+    assert np.array_equal(np.ascontiguousarray(dev_rows[:, 4:100]), pr)
+    assert np.array_equal(dev_rows[:, 100], lb)
+    # and once more after the buffers are warm
+    ptr2, n2 = t.raw_samples_device()
+    assert (ptr2, n2) == (ptr1, n1)
