@@ -333,7 +333,7 @@ class Trainer:
 
     def set_weights(self, flat_weights, model=0, precision="fp32"):
         w = np.ascontiguousarray(flat_weights, np.float32)
-        prec = {"fp32": 0, "bf16": 1, "fp16": 2}[precision]
+        prec = {"fp32": 0, "bf16": 1, "fp16": 2, "bf16x3": 3}[precision]
         _check(lib().cb200_trainer_set_weights(self._h, model, _ptr(w), w.size, prec))
 
     def evaluate(self, game_states, model=0):

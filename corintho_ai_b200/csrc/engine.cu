@@ -1245,11 +1245,12 @@ int cb200_trainer_set_weights(cb200_trainer *t, int model, const float *weights,
   int rc = guard(t);
   if (rc) return rc;
   if (model < 0 || model > 1 || !weights || n_floats != kNetWeightFloats ||
-      (precision < 0 || precision > 2))
-    return set_error(CB200_ERR_ARG, "cb200_trainer_set_weights: bad arguments (127997 floats, precision 0|1|2)");
+      (precision < 0 || precision > 3))
+    return set_error(CB200_ERR_ARG, "cb200_trainer_set_weights: bad arguments (127997 floats, precision 0|1|2|3)");
+  // tensor-core operand modes: precision 1 -> bf16, 2 -> fp16, 3 -> bf16x3 (hi + lo operands)
   rc = precision == 0 ? net_f32_upload(t->net32[model], weights)
-                      : net_tc_upload(t->nettc[model], weights, precision == 2);
-  // precisions 1 (bf16) and 2 (fp16) share the tensor-core kernel and the move-major output
+                      : net_tc_upload(t->nettc[model], weights, precision == 1 ? 0 : (precision == 2 ? 1 : 2));
+  // precisions 1-3 share the tensor-core kernel and the move-major output
   if (rc == CB200_OK) t->precision[model] = precision == 0 ? 0 : 1;
   return rc;
 }
@@ -1464,7 +1465,8 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   if (const char *e = getenv("CB200_YIELD_MIN_LIVE")) yield_min_live = atoi(e);
   // Persistent tail: once every live game fits on the device at 16 games per SM (and all games
   // have started), the rest of the run happens inside persistent kernels (persistent.cuh).
-  const bool ps_ok = tc && t->P.spe <= kPsRowsPerGame && !getenv("CB200_NO_PERSISTENT");
+  // (bf16x3 networks need 210 KB of shared memory: they stay in the lock-step loop)
+  const bool ps_ok = tc && t->nettc[model].mode != 2 && t->P.spe <= kPsRowsPerGame && !getenv("CB200_NO_PERSISTENT");
   long long ps_capacity = (long long)t->ps_ctas * 16;
   if (const char *e = getenv("CB200_PS_CAPACITY")) ps_capacity = atoll(e);
   if (ps_capacity > (long long)t->ps_ctas * 16) ps_capacity = (long long)t->ps_ctas * 16;
@@ -1473,7 +1475,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   // With several stream groups the game step runs in its 96-register build (four CTAs leave
   // 16 K registers per SM) and the network in single-tile CTAs of 128 threads that fit beside
   // them, so that one group's network overlaps the other groups' tree work (2-3 % per run).
-  const bool overlap = tc && ng > 1 && getenv("CB200_NO_OVERLAP") == nullptr;
+  const bool overlap = tc && t->nettc[model].mode != 2 && ng > 1 && getenv("CB200_NO_OVERLAP") == nullptr;
   const bool use_lists = getenv("CB200_NO_LIVE_LIST") == nullptr;
   std::vector<int> group_live(ng, -1);  // live games per group at the last host sync (-1 = unknown)
   while (max_iterations <= 0 || done_iters < max_iterations) {
@@ -1636,7 +1638,7 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
   // and every game resident at <= 16 per SM, the whole match runs in the persistent kernel
   // (persistent.cuh; each game's requests go to the row region of the model that owns its side).
   if ((t->iterations_done == 0 || t->ps_active) && t->precision[0] == 1 && t->precision[1] == 1 &&
-      t->nettc[0].fp16 == t->nettc[1].fp16 && t->P.spe <= kPsRowsPerGame &&
+      t->nettc[0].mode == t->nettc[1].mode && t->nettc[0].mode != 2 && t->P.spe <= kPsRowsPerGame &&
       t->P.num_games <= t->ps_ctas * 16 && !getenv("CB200_NO_PERSISTENT")) {
     CB_CUDA(cudaStreamSynchronize(cur_stream()));
     if (!t->ps_active) {

@@ -21,6 +21,13 @@
 // the layers by unit weights), and weight rows 100/101 hold the bias split into bf16 hi + lo
 // parts (~16 significant bits), so the hidden epilogue is just ReLU + bf16 packing
 // (cvt.rn.relu.bf16x2.f32) on batched TMEM loads.
+//
+// Operand modes (template parameter kMode): 0 = bf16, 1 = fp16, 2 = "bf16x3": activations and
+// weights are both carried as a bf16 hi + lo pair (16 significant bits) and every k-step issues
+// three MMAs into the same accumulator (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi; the lo*lo term is
+// below fp32 round-off). Trained checkpoints need it: their folded BatchNorm scales make the
+// outputs so sensitive to operand rounding that single bf16 / fp16 operands miss the 2e-2 bar
+// (value error up to 0.24 / 0.033), while bf16x3 stays below 1e-3 (tests/test_gpu_net.py).
 #ifndef CORINTHO_B200_MLP_TC_CUH
 #define CORINTHO_B200_MLP_TC_CUH
 
@@ -43,6 +50,8 @@ constexpr int kTcOnes = 100;                             // activation columns 1
 constexpr int kTcThreads = 256;
 constexpr int kTcTmemCols = 256;                         // 2 tiles x 128 columns
 constexpr size_t kTcSmemBytes = 2 * kTcABytes + 2 * kTcLayerBytes + 64;
+// bf16x3: hi and lo copies of both activation tiles and of both weight buffers
+constexpr size_t kTcSmemBytesX3 = 2 * (2 * kTcABytes + 2 * kTcLayerBytes) + 64;
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 (bits 4-5 = 1),
 // A=B=BF16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
@@ -52,9 +61,11 @@ constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(k
 constexpr uint32_t kTcIdescF16 = (1u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 struct NetTC {
-  void *w = nullptr;  // device: kTcLayers images of kTcLayerBytes
+  void *w = nullptr;  // device: kTcLayers images of kTcLayerBytes (mode 2: hi image + lo image each)
   bool ready = false;
   bool fp16 = false;  // operand format of the images: false = bf16, true = fp16
+  int mode = 0;       // 0 bf16, 1 fp16, 2 bf16x3 (hi + lo operands, three MMAs per k-step)
+  size_t w_bytes = 0;
 };
 
 // ---- raw PTX helpers -------------------------------------------------------------------------
@@ -151,6 +162,16 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t v[16])
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// tcgen05.wait::ld that also "touches" the 16 destination registers of the load it completes, so
+// that the compiler cannot move their first use above the wait
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t v[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                 "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]),
+                 "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t v[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -210,18 +231,21 @@ struct TcState {
   uint8_t *sA, *sW;
   uint32_t wbar0, mbar0, tmem_base;
   int nthreads;        // threads running the network: 256 (two tiles) or 128 (one tile)
+  int parts;           // operand copies in shared memory: 1, or 2 (hi + lo) in bf16x3 mode
   uint32_t tmem_cols;  // 128 TMEM columns per tile
   uint32_t wcount[2];  // completed waits per weight buffer
   uint32_t mcount;     // completed waits on this warpgroup's MMA barrier
 };
 constexpr size_t kTcStateSmemBytes = kTcSmemBytes;  // sA[2] | sW[2] | 4 mbarriers | tmem slot
 
-__device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem, int nthreads = kTcThreads) {
+__device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem, int nthreads = kTcThreads,
+                                         int parts = 1) {
   S.nthreads = nthreads;
+  S.parts = parts;
   S.tmem_cols = nthreads == kTcThreads ? kTcTmemCols : kTcTmemCols / 2;
-  S.sA = smem;                                 // 2 x kTcABytes
-  S.sW = smem + 2 * kTcABytes;                 // 2 x kTcLayerBytes
-  uint64_t *bars = reinterpret_cast<uint64_t *>(S.sW + 2 * kTcLayerBytes);  // wbar[2], mbar[2]
+  S.sA = smem;                                 // 2 tiles x parts x kTcABytes
+  S.sW = smem + 2 * parts * kTcABytes;         // 2 buffers x parts x kTcLayerBytes
+  uint64_t *bars = reinterpret_cast<uint64_t *>(S.sW + 2 * parts * kTcLayerBytes);  // wbar[2], mbar[2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
   const int t = threadIdx.x, warp = t >> 5;
   S.wbar0 = smem_u32(bars), S.mbar0 = smem_u32(bars + 2);
@@ -257,11 +281,16 @@ __device__ __forceinline__ void tc_teardown(TcState &S) {
 
 // One pair of 128-position tiles (positions [pair * 256, pair * 256 + 256) of `states`, n valid
 // positions in total) through all 13 layers. Called by all 256 threads of the CTA.
-template <bool kFp16>
+// kMode: 0 bf16, 1 fp16, 2 bf16x3 operands (see the file header).
+template <int kMode>
 __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict__ W,
                                            const ulonglong2 *__restrict__ states, int n, int pair,
                                            float *__restrict__ eval, float *__restrict__ probs,
                                            int probs_ld) {
+  constexpr bool kFp16 = kMode == 1;
+  constexpr int kParts = kMode == 2 ? 2 : 1;              // operand copies (hi, lo)
+  constexpr int kBufBytes = kParts * kTcLayerBytes;       // one layer's weights in shared / global memory
+  constexpr int kTileBytes = kParts * kTcABytes;          // one tile's activations
   const int t = threadIdx.x, warp = t >> 5;
   const int wg = t >> 7;    // warpgroup = tile within the CTA
   const int row = t & 127;  // row of the tile owned by this thread
@@ -269,15 +298,14 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
   const uint32_t wbar0 = S.wbar0, mbar0 = S.mbar0;
   const uint32_t tmem_tile = S.tmem_base + (uint32_t)wg * 128u;                  // column offset
   const uint32_t tmem_row = tmem_tile + ((uint32_t)((warp & 3) * 32) << 16);     // lane offset
-  uint8_t *myA = S.sA + wg * kTcABytes;
+  uint8_t *myA = S.sA + wg * kTileBytes;  // hi copy; the lo copy (bf16x3) follows at + kTcABytes
   const uint32_t aaddr = smem_u32(myA);
   uint32_t wcount[2] = {S.wcount[0], S.wcount[1]};
   uint32_t mcount = S.mcount;
   if (t == 0) {  // both weight buffers are free here: fetch layers 0 and 1
     for (int b = 0; b < 2; ++b) {
-      mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
-      bulk_g2s(smem_u32(sW + b * kTcLayerBytes), W + (size_t)b * kTcLayerBytes, kTcLayerBytes,
-               wbar0 + 8 * b);
+      mbar_expect_tx(wbar0 + 8 * b, kBufBytes);
+      bulk_g2s(smem_u32(sW + b * kBufBytes), W + (size_t)b * kBufBytes, kBufBytes, wbar0 + 8 * b);
     }
   }
   // ---- input encoding straight from the packed state into the A operand (bf16 exact)
@@ -303,6 +331,8 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
       }
       *reinterpret_cast<uint4 *>(myA + c * kTcAChunkBytes + row * 16) =
           make_uint4(q[0], q[1], q[2], q[3]);
+      if (kParts == 2)  // the encoding (0, 1/4, ..., 1) is exact in bf16: no lo part
+        *reinterpret_cast<uint4 *>(myA + kTcABytes + c * kTcAChunkBytes + row * 16) = make_uint4(0, 0, 0, 0);
     }
   }
   // make this thread's generic-proxy writes of A visible to the tensor core, then sync
@@ -312,17 +342,24 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
   tc_fence_after();
   for (int layer = 0; layer < kTcLayers; ++layer) {
     const int b = layer & 1;
-    uint8_t *wbuf = sW + b * kTcLayerBytes;
+    uint8_t *wbuf = sW + b * kBufBytes;
     mbar_wait(wbar0 + 8 * b, wcount[b] & 1);
     wcount[b] += 1;
     if (tile_live) {
-    if (row == 0) {  // one thread per warpgroup issues the 7 MMAs of its tile
+    if (row == 0) {  // one thread per warpgroup issues the MMAs of its tile
       const uint32_t waddr = smem_u32(wbuf);
+      const uint32_t idesc = kFp16 ? kTcIdescF16 : kTcIdesc;
 #pragma unroll
       for (int kk = 0; kk < kTcChunks / 2; ++kk) {
         const uint64_t ad = umma_desc(aaddr + kk * 2 * kTcAChunkBytes, kTcAChunkBytes, 128);
         const uint64_t bd = umma_desc(waddr + kk * 2 * kTcWChunkBytes, kTcWChunkBytes, 128);
-        umma_bf16(tmem_tile, ad, bd, kFp16 ? kTcIdescF16 : kTcIdesc, kk > 0 ? 1u : 0u);
+        umma_bf16(tmem_tile, ad, bd, idesc, kk > 0 ? 1u : 0u);
+        if (kParts == 2) {  // + a_hi * w_lo + a_lo * w_hi
+          const uint64_t adl = umma_desc(aaddr + kTcABytes + kk * 2 * kTcAChunkBytes, kTcAChunkBytes, 128);
+          const uint64_t bdl = umma_desc(waddr + kTcLayerBytes + kk * 2 * kTcWChunkBytes, kTcWChunkBytes, 128);
+          umma_bf16(tmem_tile, ad, bdl, idesc, 1u);
+          umma_bf16(tmem_tile, adl, bd, idesc, 1u);
+        }
       }
       umma_commit(mbar0 + 8 * wg);
     }
@@ -330,32 +367,35 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
     mcount += 1;
     tc_fence_after();
     if (layer < kTcLayers - 1) {
-      // ---- hidden-layer epilogue: ReLU + bf16 (bias already in the accumulator), the result
-      // becomes the next A operand. TMEM loads are batched: 64 columns, then 48.
-      {
-        uint32_t v[64];
-        tmem_ld32_nowait(tmem_row, v);
-        tmem_ld32_nowait(tmem_row + 32, v + 32);
-        tmem_wait_ld();
+      // ---- hidden-layer epilogue: ReLU + 16-bit pack (bias already in the accumulator), the
+      // result becomes the next A operand. Seven 16-column TMEM loads, software-pipelined over two
+      // register buffers: the next load is in flight while the current columns are converted
+      // (32 registers of accumulator data at a time -- no local-memory spills).
+      uint32_t va[16], vb[16];
+      tmem_ld16_nowait(tmem_row, va);
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const uint32_t *x = v + 8 * c8;
-          *reinterpret_cast<uint4 *>(myA + c8 * kTcAChunkBytes + row * 16) =
-              make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
-                         relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
-        }
-      }
-      {
-        uint32_t v[48];
-        tmem_ld32_nowait(tmem_row + 64, v);
-        tmem_ld16_nowait(tmem_row + 96, v + 32);
-        tmem_wait_ld();
+      for (int c = 0; c < kTcN / 16; ++c) {
+        uint32_t *cur = (c & 1) ? vb : va;
+        tmem_wait_ld16(cur);
+        if (c + 1 < kTcN / 16) tmem_ld16_nowait(tmem_row + 16 * (c + 1), (c & 1) ? va : vb);
 #pragma unroll
-        for (int c8 = 0; c8 < 6; ++c8) {
-          const uint32_t *x = v + 8 * c8;
-          *reinterpret_cast<uint4 *>(myA + (8 + c8) * kTcAChunkBytes + row * 16) =
-              make_uint4(relu_pack16<kFp16>(x[0], x[1]), relu_pack16<kFp16>(x[2], x[3]),
-                         relu_pack16<kFp16>(x[4], x[5]), relu_pack16<kFp16>(x[6], x[7]));
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const uint32_t *x = cur + 8 * h8;
+          uint32_t hi[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) hi[q] = relu_pack16<kFp16>(x[2 * q], x[2 * q + 1]);
+          uint8_t *dst = myA + (2 * c + h8) * kTcAChunkBytes + row * 16;
+          *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (kParts == 2) {  // lo = bf16(relu(x) - hi)
+            uint32_t lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float r0 = fmaxf(__uint_as_float(x[2 * q]), 0.0f) - __uint_as_float(hi[q] << 16);
+              const float r1 = fmaxf(__uint_as_float(x[2 * q + 1]), 0.0f) - __uint_as_float(hi[q] & 0xffff0000u);
+              lo[q] = pack16<false>(r0, r1);
+            }
+            *reinterpret_cast<uint4 *>(dst + kTcABytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       }
     } else {
@@ -437,17 +477,16 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
     tc_sync(S.nthreads);
     tc_fence_after();
     if (t == 0 && layer + 2 < kTcLayers) {
-      mbar_expect_tx(wbar0 + 8 * b, kTcLayerBytes);
-      bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kTcLayerBytes, kTcLayerBytes,
-               wbar0 + 8 * b);
+      mbar_expect_tx(wbar0 + 8 * b, kBufBytes);
+      bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kBufBytes, kBufBytes, wbar0 + 8 * b);
     }
   }
   S.wcount[0] = wcount[0], S.wcount[1] = wcount[1];
   S.mcount = mcount;
 }
 
-template <bool kFp16>
-__global__ void __launch_bounds__(kTcThreads, 2)
+template <int kMode>
+__global__ void __launch_bounds__(kTcThreads, kMode == 2 ? 1 : 2)
     k_mlp_tc(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
              const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
              float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
@@ -455,10 +494,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   const int n = n_ptr ? *n_ptr : n_static;
   if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;  // next parity's counters
   TcState S;
-  tc_setup(S, smem);
+  tc_setup(S, smem, kTcThreads, kMode == 2 ? 2 : 1);
   const int n_pairs = (n + 255) / 256;
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
-    tc_forward<kFp16>(S, W, states, n, pair, eval, probs, probs_ld);
+    tc_forward<kMode>(S, W, states, n, pair, eval, probs, probs_ld);
   tc_teardown(S);
 }
 
@@ -476,36 +515,34 @@ __global__ void __launch_bounds__(128, 4)
   tc_setup(S, smem, 128);
   for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
     const int rows = n - tile * 128 < 128 ? n - tile * 128 : 128;
-    tc_forward<kFp16>(S, W, states + tile * 128, rows, 0, eval + tile * 128, probs + tile * 128,
-                      probs_ld);
+    tc_forward<kFp16 ? 1 : 0>(S, W, states + tile * 128, rows, 0, eval + tile * 128, probs + tile * 128,
+                              probs_ld);
   }
   tc_teardown(S);
 }
 
-// Re-layout the C-ABI weight vector into per-layer UMMA images (bf16, zero padded) and upload.
-inline int net_tc_upload(NetTC &net, const float *weights, bool fp16 = false) {
+// Re-layout the C-ABI weight vector into per-layer UMMA images (16-bit operands, zero padded) and
+// upload. mode 0 bf16, 1 fp16, 2 bf16x3: every layer is a hi image followed by a lo image
+// (w = hi + lo to 16 significant bits; the bias rows carry a third part in the lo image).
+inline int net_tc_upload(NetTC &net, const float *weights, int mode) {
+  const bool fp16 = mode == 1;
+  const int parts = mode == 2 ? 2 : 1;
   net.fp16 = fp16;
-  std::vector<uint8_t> host((size_t)kTcLayers * kTcLayerBytes, 0);
+  net.mode = mode;
+  const size_t layer_bytes = (size_t)parts * kTcLayerBytes;
+  std::vector<uint8_t> host((size_t)kTcLayers * layer_bytes, 0);
+  auto rnd = [&](float v) -> float {  // value of the 16-bit operand nearest to v
+    return fp16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+  };
   const float *src = weights;
   for (int l = 0; l < kTcLayers; ++l) {
     const int K = l == 0 ? CB200_STATE_SIZE : 100;
     const int N = l == kTcLayers - 1 ? 97 : 100;
-    uint8_t *img = host.data() + (size_t)l * kTcLayerBytes;
-    for (int k = 0; k < K; ++k)
-      for (int o = 0; o < N; ++o) {
-        // B operand is [N][K] K-major: chunk k/8, row o, element k%8
-        uint8_t *dst = img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2;
-        if (fp16) {
-          const __half h = __float2half_rn(src[(size_t)k * N + o]);
-          memcpy(dst, &h, 2);
-        } else {
-          const __nv_bfloat16 h = __float2bfloat16_rn(src[(size_t)k * N + o]);
-          memcpy(dst, &h, 2);
-        }
-      }
-    src += (size_t)K * N;
-    auto put = [&](int k, int o, float v) {
-      uint8_t *dst = img + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 + (k & 7) * 2;
+    uint8_t *img = host.data() + (size_t)l * layer_bytes;
+    // B operand is [N][K] K-major: chunk k/8, row o, element k%8; part 0 = hi image, 1 = lo image
+    auto put = [&](int part, int k, int o, float v) {
+      uint8_t *dst = img + (size_t)part * kTcLayerBytes + (size_t)(k >> 3) * kTcWChunkBytes + (size_t)o * 16 +
+                     (k & 7) * 2;
       if (fp16) {
         const __half h = __float2half_rn(v);
         memcpy(dst, &h, 2);
@@ -514,19 +551,32 @@ inline int net_tc_upload(NetTC &net, const float *weights, bool fp16 = false) {
         memcpy(dst, &h, 2);
       }
     };
-    for (int o = 0; o < N; ++o) {  // bias = hi + lo, multiplied by the two ones columns
+    for (int k = 0; k < K; ++k)
+      for (int o = 0; o < N; ++o) {
+        const float w = src[(size_t)k * N + o];
+        put(0, k, o, w);
+        if (parts == 2) put(1, k, o, w - rnd(w));
+      }
+    src += (size_t)K * N;
+    for (int o = 0; o < N; ++o) {  // bias = hi + lo (+ lo2), multiplied by the constant-one columns
       const float b = src[o];
-      const float hi = fp16 ? __half2float(__float2half_rn(b)) : __bfloat162float(__float2bfloat16_rn(b));
-      put(kTcOnes, o, hi);
-      put(kTcOnes + 1, o, b - hi);
+      const float hi = rnd(b), lo = rnd(b - hi);
+      put(0, kTcOnes, o, hi);
+      put(0, kTcOnes + 1, o, lo);
+      if (parts == 2) put(1, kTcOnes, o, b - hi - lo);
     }
     if (l < kTcLayers - 1) {  // keep the ones columns alive: out[:,100] = out[:,101] = 1
-      put(kTcOnes, kTcOnes, 1.0f);
-      put(kTcOnes, kTcOnes + 1, 1.0f);
+      put(0, kTcOnes, kTcOnes, 1.0f);
+      put(0, kTcOnes, kTcOnes + 1, 1.0f);
     }
     src += N;
   }
+  if (net.w && net.w_bytes != host.size()) {
+    cudaFree(net.w);
+    net.w = nullptr;
+  }
   if (!net.w) CB_CUDA(cudaMalloc(&net.w, host.size()));
+  net.w_bytes = host.size();
   CB_CUDA(cudaMemcpy(net.w, host.data(), host.size(), cudaMemcpyHostToDevice));
   net.ready = true;
   return CB200_OK;
@@ -546,13 +596,24 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 16 && !attr_set[dev]) {
-    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTcSmemBytes));
-    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)kTcSmemBytes));
+    CB_CUDA(cudaFuncSetAttribute(k_mlp_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kTcSmemBytesX3));
     attr_set[dev] = true;
   }
   if (n_max <= 0) return CB200_OK;
+  cudaStream_t st = use_stream ? stream : cur_stream();
+  if (net.mode == 2) {  // bf16x3: 210 KB of shared memory, one CTA per SM
+    const int pairs = (n_max + 255) / 256;
+    k_mlp_tc<2><<<pairs < sms ? pairs : sms, kTcThreads, kTcSmemBytesX3, st>>>(
+        (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
+    CB_LAUNCHED();
+    CB_CUDA(cudaGetLastError());
+    return CB200_OK;
+  }
   if (single_tile) {
     static bool attr1[16] = {false};
     if (dev < 16 && !attr1[dev]) {
@@ -565,10 +626,10 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
     const int tiles = (n_max + 127) / 128;
     const int g1 = tiles < sms ? tiles : sms;
     if (net.fp16)
-      k_mlp_tc1<true><<<g1, 128, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
+      k_mlp_tc1<true><<<g1, 128, kTcSmemBytes, st>>>(
           (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
     else
-      k_mlp_tc1<false><<<g1, 128, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
+      k_mlp_tc1<false><<<g1, 128, kTcSmemBytes, st>>>(
           (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
     CB_LAUNCHED();
     CB_CUDA(cudaGetLastError());
@@ -577,10 +638,10 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   const int pairs = (n_max + 255) / 256;
   const int grid = pairs < 2 * sms ? pairs : 2 * sms;
   if (net.fp16)
-    k_mlp_tc<true><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
+    k_mlp_tc<1><<<grid, kTcThreads, kTcSmemBytes, st>>>(
         (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
   else
-    k_mlp_tc<false><<<grid, kTcThreads, kTcSmemBytes, use_stream ? stream : cur_stream()>>>(
+    k_mlp_tc<0><<<grid, kTcThreads, kTcSmemBytes, st>>>(
         (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());

@@ -97,9 +97,9 @@ __global__ void __launch_bounds__(kGames * kL, 1)
     // every round ends with the network, so the answers of all queued requests are in the
     // CTA's rows whenever the kernel stops (a later launch continues from there)
     if (net_thread && n > 0)
-      tc_forward<kFp16>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
+      tc_forward<kFp16 ? 1 : 0>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
     if (net_thread && n1 > 0)
-      tc_forward<kFp16>(S, W1, packed + row0 + kRows, n1, 0, eval + row0 + kRows,
+      tc_forward<kFp16 ? 1 : 0>(S, W1, packed + row0 + kRows, n1, 0, eval + row0 + kRows,
                         probs + row0 + kRows, ld);
     __syncthreads();  // answers visible to every warp; counters read before they are cleared
     if (live == 0 || s_ctr[3]) {

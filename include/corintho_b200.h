@@ -159,8 +159,10 @@ int cb200_trainer_game_results(cb200_trainer *t, int32_t *results /* [num_games]
  * row-major [in][out] like Keras Dense kernels; head column 0 = value (tanh), 1..96 = policy
  * logits (softmax). n_floats must be 127997. precision: 0 = fp32 SIMT kernel (parity mode,
  * 1e-5), 1 = bf16 tcgen05 tensor-core kernel with fp32 accumulation (2e-2 on random-init
- * networks), 2 = the same kernel with fp16 operands (for trained checkpoints, whose folded
- * BatchNorm scales make bf16 operand rounding too coarse; activations must stay below 65504). */
+ * networks), 2 = the same kernel with fp16 operands (activations must stay below 65504),
+ * 3 = "bf16x3": the same kernel with every operand carried as a bf16 hi + lo pair and three MMAs
+ * per k-step (16 significant bits; < 1e-3 on the reference's trained checkpoints, whose folded
+ * BatchNorm scales make single bf16 / fp16 operands miss the 2e-2 bar; ~2x the network time). */
 int cb200_trainer_set_weights(cb200_trainer *t, int model, const float *weights, size_t n_floats,
                               int precision);
 /* Evaluate positions with the resident network (the engine's replacement for the Keras
