@@ -534,7 +534,8 @@ def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
     device->host transfer overlaps the self-play instead of following it; the timed region ends
     when the last row is in host memory. Rows come in game completion order with a game index
     per sample (see include/corintho_b200.h)."""
-    tr.stream_samples(-1)
+    # staging capacity in samples: a game lasts ~19 moves on average (33 at most observed)
+    tr.stream_samples(G * 32 if G <= 8192 else G * 24)
     tr.reset(2000)
     tr.run_selfplay(0, stagger=False)  # untimed warm-up of the streaming path
     tr.streamed_samples()
