@@ -101,6 +101,8 @@ def lib():
         "cb200_tourney_do_iteration": (i32, [vp, vp, vp, i32, i32]),
         "cb200_tourney_write_scores": (i32, [vp, C.c_char_p]),
         "cb200_tourney_counters": (i32, [vp, vp]),
+        "cb200_tourney_set_weights": (i32, [vp, i32, vp, C.c_size_t, i32]),
+        "cb200_tourney_run": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -482,6 +484,16 @@ class Tourney:
         _check(lib().cb200_tourney_counters(self._h, _ptr(out)))
         return {"simulations": int(out[0]), "moves": int(out[1]), "leaf_evals": int(out[2]),
                 "iterations": int(out[3])}
+
+    # ---- engine-only: fused tourney (device-resident networks per model id) -------------------
+    def set_weights(self, model_id, flat_weights, precision="fp32"):
+        w = np.ascontiguousarray(flat_weights, np.float32)
+        prec = {"fp32": 0, "bf16": 1, "fp16": 2, "bf16x3": 3}[precision]
+        _check(lib().cb200_tourney_set_weights(self._h, int(model_id), _ptr(w), w.size, prec))
+
+    def run(self, max_rounds=0):
+        """Play rounds of rating/tourney.pyx:112-173 on the device; True when every match is over."""
+        return bool(_check(lib().cb200_tourney_run(self._h, int(max_rounds))))
 
     # snake_case conveniences shared with the test drivers
     add_player = addPlayer

@@ -196,6 +196,8 @@ extern "C" int cb200_trainer_counters(cb200_trainer *t, int64_t out[4]);
 
 namespace {
 
+constexpr size_t kAnswerSlack = 128;  // spare rows behind the answer buffers
+
 uint32_t mt_seed_word(uint32_t prev, int i) { return 1812433253u * (prev ^ (prev >> 30)) + i; }
 
 struct HostMT {
@@ -728,8 +730,11 @@ cb200_trainer *cb200_trainer_create_shard(int total_games, int first_game, int n
             dmalloc(&P.leaf_state, t->cap) == CB200_OK &&
             dmalloc(&P.sample_state, Gn * kMaxSamples) == CB200_OK &&
             dmalloc(&P.sample_probs, Gn * kMaxSamples * CB200_NUM_MOVES) == CB200_OK &&
-            dmalloc(&P.counters, Gn * 4) == CB200_OK && dmalloc(&t->d_eval, t->cap) == CB200_OK &&
-            dmalloc(&t->d_probs, t->cap * CB200_NUM_MOVES) == CB200_OK &&
+            dmalloc(&P.counters, Gn * 4) == CB200_OK &&
+            // (+ kAnswerSlack rows: a fused tourney reads its answers at the reference's own offsets,
+            // tourney.cpp:54-62, which may run a few rows past the requests of the call)
+            dmalloc(&t->d_eval, t->cap + kAnswerSlack) == CB200_OK &&
+            dmalloc(&t->d_probs, (t->cap + kAnswerSlack) * CB200_NUM_MOVES) == CB200_OK &&
             dmalloc(&t->d_rows, t->cap * CB200_STATE_SIZE) == CB200_OK &&
             dmalloc(&t->d_packed, t->cap) == CB200_OK && dmalloc(&t->d_offs, Gn) == CB200_OK &&
             dmalloc(&t->d_soff, Gn) == CB200_OK && dmalloc(&t->d_summary, 4) == CB200_OK &&
@@ -1721,6 +1726,17 @@ struct cb200_tourney {
   cb200_trainer *t = nullptr;
   MatchSide *d_sides = nullptr;
   int32_t *d_pack_offs = nullptr, *d_iter_offs = nullptr;
+  // fused mode (cb200_tourney_set_weights / cb200_tourney_run): one device-resident network per
+  // model id, evaluated in the first-seen order of the ids like rating/tourney.pyx:112-173
+  std::vector<int> model_order;
+  struct Net {
+    std::vector<float> host;  // kept until the device exists
+    int precision = -1;
+    bool uploaded = false;
+    NetF32 f32;
+    NetTC tc;
+  };
+  std::map<int, Net> nets;
 };
 
 static int tourney_ready_build(cb200_tourney *T, cb200_trainer *t, const std::vector<MatchSide> &sides,
@@ -1845,6 +1861,10 @@ cb200_tourney *cb200_tourney_create(int num_threads, const char *log_folder) {
 void cb200_tourney_destroy(cb200_tourney *T) {
   if (!T) return;
   cudaFree(T->d_sides), cudaFree(T->d_pack_offs), cudaFree(T->d_iter_offs);
+  for (auto &kv : T->nets) {
+    cudaFree(kv.second.f32.w);
+    net_tc_free(kv.second.tc);
+  }
   if (T->t) cb200_trainer_destroy(T->t);
   delete T;
 }
@@ -1861,6 +1881,8 @@ int cb200_tourney_add_player(cb200_tourney *T, int player_id, int model_id, int 
   s.spe = searches_per_eval > 0 ? searches_per_eval : 1, s.random = random ? 1 : 0;
   s.c_puct = c_puct, s.epsilon = epsilon, s.player_id = player_id, s.log_slot = -1;
   T->players[player_id] = s;
+  if (std::find(T->model_order.begin(), T->model_order.end(), model_id) == T->model_order.end())
+    T->model_order.push_back(model_id);
   return CB200_OK;
 }
 
@@ -1897,7 +1919,7 @@ int cb200_tourney_write_requests(cb200_tourney *T, float *game_states, int id) {
   const int n = t->h_summary[0];
   if (n <= 0) return CB200_OK;
   k_match_pack<<<(t->P.num_games + 7) / 8, 256, 0, cur_stream()>>>(t->P, T->d_sides, id,
-                                                                 T->d_pack_offs, t->d_rows);
+                                                                 T->d_pack_offs, t->d_rows, nullptr);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   CB_CUDA(cudaMemcpyAsync(game_states, t->d_rows, (size_t)n * CB200_STATE_SIZE * sizeof(float),
@@ -1925,7 +1947,7 @@ int cb200_tourney_do_iteration(cb200_tourney *T, const float *eval, const float 
   }
   const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
   k_match_iterate<<<grid, kTreeWarps * 32, 0, cur_stream()>>>(t->P, T->d_sides, t->d_eval, t->d_probs,
-                                                            T->d_iter_offs, id);
+                                                            T->d_iter_offs, id, CB200_NUM_MOVES, 1);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   if ((rc = tourney_scan(T, id)) != CB200_OK) return rc;
@@ -1934,6 +1956,85 @@ int cb200_tourney_do_iteration(cb200_tourney *T, const float *eval, const float 
                                       "CB200_ARENA_NODES) or reached an impossible state");
   ++t->iterations_done;
   return tourney_drain_logs(T);
+}
+
+// ---- fused tourney: the per-model evaluation of rating/tourney.pyx:139-155 on the device ------
+int cb200_tourney_set_weights(cb200_tourney *T, int model_id, const float *weights, size_t n_floats,
+                              int precision) {
+  last_error_ref().clear();
+  if (!T) return set_error(CB200_ERR_ARG, "null tourney");
+  if (model_id < 0 || !weights || n_floats != kNetWeightFloats || precision < 0 || precision > 3)
+    return set_error(CB200_ERR_ARG, "cb200_tourney_set_weights: bad arguments (model id >= 0, 127997 floats, "
+                                    "precision 0|1|2|3)");
+  cb200_tourney::Net &n = T->nets[model_id];
+  n.host.assign(weights, weights + n_floats);
+  n.precision = precision;
+  n.uploaded = false;
+  return CB200_OK;
+}
+
+int cb200_tourney_run(cb200_tourney *T, int max_rounds) {
+  int rc = tourney_ready(T);
+  if (rc) return rc;
+  cb200_trainer *t = T->t;
+  if ((rc = guard(t)) != CB200_OK) return rc;
+  for (int id : T->model_order) {
+    if (id < 0) continue;  // random players: no network (tourney.pyx feeds them no evaluation)
+    auto it = T->nets.find(id);
+    if (it == T->nets.end() || it->second.precision < 0)
+      return set_error(CB200_ERR_STATE, "cb200_tourney_run: no weights set for model " + std::to_string(id));
+    cb200_tourney::Net &n = it->second;
+    if (!n.uploaded) {
+      rc = n.precision == 0 ? net_f32_upload(n.f32, n.host.data())
+                            : net_tc_upload(n.tc, n.host.data(), n.precision == 1 ? 0 : (n.precision == 2 ? 1 : 2));
+      if (rc != CB200_OK) return rc;
+      n.uploaded = true;
+    }
+  }
+  cudaStream_t st = cur_stream();
+  const int grid = (t->P.num_games + kTreeWarps - 1) / kTreeWarps;
+  int rounds = 0;
+  for (;;) {
+    // all_done() check (tourney.pyx:118) every few rounds: one small read-back
+    k_match_scan<<<1, 32, 0, st>>>(t->P, T->d_sides, 0x7fffffff, T->d_pack_offs, T->d_iter_offs, t->d_summary);
+    CB_LAUNCHED();
+    CB_CUDA(cudaGetLastError());
+    if ((rc = fetch_summary(t)) != CB200_OK) return rc;
+    if (t->h_summary[1] == 0) return tourney_drain_logs(T) != CB200_OK ? CB200_ERR_CUDA : 1;
+    if (max_rounds > 0 && rounds >= max_rounds) break;
+    int batch = 8;
+    if (max_rounds > 0 && max_rounds - rounds < batch) batch = max_rounds - rounds;
+    for (int r = 0; r < batch; ++r) {
+      for (int id : T->model_order) {
+        // offsets of both kinds + request count of this model (summary[0], read by the network)
+        k_match_scan<<<1, 32, 0, st>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs, t->d_summary);
+        CB_LAUNCHED();
+        long prs = CB200_NUM_MOVES, pcs = 1;
+        if (id >= 0) {
+          cb200_tourney::Net &n = T->nets[id];
+          k_match_pack<<<(t->P.num_games + 7) / 8, 256, 0, st>>>(t->P, T->d_sides, id, T->d_pack_offs, nullptr,
+                                                                 t->d_packed);
+          CB_LAUNCHED();
+          if (n.precision == 0) {
+            rc = launch_mlp_f32(n.f32, t->d_packed, t->d_summary, 0, (int)t->cap, t->d_eval, t->d_probs);
+          } else {
+            rc = launch_mlp_tc(n.tc, t->d_packed, t->d_summary, 0, (int)t->cap, t->d_eval, t->d_probs,
+                               (int)(t->cap + kAnswerSlack));
+            prs = 1, pcs = (long)(t->cap + kAnswerSlack);
+          }
+          if (rc != CB200_OK) return rc;
+        }
+        k_match_iterate<<<grid, kTreeWarps * 32, 0, st>>>(t->P, T->d_sides, t->d_eval, t->d_probs, T->d_iter_offs,
+                                                          id, prs, pcs);
+        CB_LAUNCHED();
+        CB_CUDA(cudaGetLastError());
+      }
+      ++t->iterations_done;
+    }
+    rounds += batch;
+  }
+  rc = tourney_drain_logs(T);
+  return rc != CB200_OK ? rc : 0;
 }
 
 // Tourney::writeScores (tourney.cpp:34-42): "<player1> <player2> <score>" per finished match

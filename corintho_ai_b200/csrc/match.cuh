@@ -57,7 +57,7 @@ __device__ __forceinline__ int match_requests(const int32_t *ctl, const MatchSid
 __global__ void __launch_bounds__(kTreeWarps * 32, 4)
     k_match_iterate(TreeParams P, const MatchSide *__restrict__ sides_all,
                     const float *__restrict__ eval, const float *__restrict__ probs,
-                    const int32_t *__restrict__ offs, int model_id) {
+                    const int32_t *__restrict__ offs, int model_id, long prs, long pcs) {
   __shared__ WarpSm sm_all[kTreeWarps];
   const int warp = threadIdx.x >> 5;
   const int g = blockIdx.x * kTreeWarps + warp;
@@ -92,7 +92,9 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
   apply_side(Pm, sides[c.to_play]);
   if (!is_random) load_tree(c, Pm, c.to_play);
   const long off = offs[g];
-  const float *ev_p = eval + off, *pr_p = probs + off * CB200_NUM_MOVES;
+  // probs element (row k, move m) = probs[k * prs + m * pcs] (row-major from the host API and the
+  // fp32 network, move-major from the tensor-core network; see receive_eval)
+  const float *ev_p = eval + off, *pr_p = probs + off * prs;
   // per-match text log (Match::writePreMoveLogs / writeMoveChoice / endGame, match.cpp:79-180):
   // same records as self-play (tree.cuh, log_pre_move); [13] = 1 when a random player moved
   const int log_slot = P.log_buf != nullptr ? sides[0].log_slot : -1;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
   for (;;) {
     // Match::doIteration: a random player moves at once, a searching player iterates first
     bool turn_done = true;
-    if (!is_random) turn_done = tree_do_iteration(c, Pm, sm, ev_p, pr_p, CB200_NUM_MOVES, 1);
+    if (!is_random) turn_done = tree_do_iteration(c, Pm, sm, ev_p, pr_p, prs, pcs);
     if (c.error || !turn_done) break;
     // one pass of Match::chooseMoveAndContinue's loop
     uint32_t *lrec = nullptr;
@@ -222,7 +224,8 @@ __global__ void k_match_scan(TreeParams P, const MatchSide *__restrict__ sides_a
 // Tourney::writeRequests (tourney.cpp:44-52): 70-float rows of the selected matches
 __global__ void __launch_bounds__(256)
     k_match_pack(TreeParams P, const MatchSide *__restrict__ sides_all, int model_id,
-                 const int32_t *__restrict__ pack_offs, float *__restrict__ rows) {
+                 const int32_t *__restrict__ pack_offs, float *__restrict__ rows,
+                 ulonglong2 *__restrict__ packed) {
   const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (g >= P.num_games) return;
@@ -231,6 +234,9 @@ __global__ void __launch_bounds__(256)
   if (!match_selected(ctl, sides, model_id)) return;
   const int np = match_requests(ctl, sides);
   const ulonglong2 *ls = P.leaf_state + (size_t)g * P.spe;
+  if (packed)  // fused tourney: leaf cstates in request order for the device-resident network
+    for (int k = lane; k < np; k += 32) packed[(size_t)pack_offs[g] + k] = ls[k];
+  if (!rows) return;
   float *out = rows + (size_t)pack_offs[g] * CB200_STATE_SIZE;
   for (int f = lane; f < np * CB200_STATE_SIZE; f += 32) {
     const int k = f / CB200_STATE_SIZE, j = f - k * CB200_STATE_SIZE;

@@ -223,6 +223,18 @@ int cb200_tourney_write_requests(cb200_tourney *t, float *game_states, int model
 int cb200_tourney_do_iteration(cb200_tourney *t, const float *eval, const float *probs, int rows,
                                int model_id);
 int cb200_tourney_write_scores(cb200_tourney *t, const char *file);
+/* Fused tourney: the loop of rating/tourney.pyx:112-173 entirely on the device. Every model id
+ * >= 0 that a player uses gets a device-resident network (same weight layout and precision codes
+ * as cb200_trainer_set_weights); cb200_tourney_run then plays rounds -- for every model id in
+ * first-seen order: request offsets, request packing, that model's network, Match::doIteration
+ * with the reference's answer-offset rule (tourney.cpp:54-62) -- until every match is over or
+ * max_rounds (<= 0: unlimited) rounds were played. Returns 1 when all matches are done, 0 when
+ * stopped by max_rounds, < 0 on error. Note: a model whose tensor-core answers are read with
+ * row-major evaluators cannot share answer rows across models within one round; like the
+ * reference loop, the answer buffers persist between calls. */
+int cb200_tourney_set_weights(cb200_tourney *t, int model_id, const float *weights, size_t n_floats,
+                              int precision);
+int cb200_tourney_run(cb200_tourney *t, int max_rounds);
 /* out = {simulations, moves, leaf evaluations, do_iteration calls} over all matches */
 int cb200_tourney_counters(cb200_tourney *t, int64_t out[4]);
 

@@ -73,3 +73,45 @@ def test_tourney_protocol_and_errors(tmp_path):
     t.writeScores(str(f))
     rows = f.read_text().split("\n")
     assert rows[0].split()[:2] == ["0", "1"] and rows[1].split()[:2] == ["1", "0"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["two_models", "with_random", "deeper"])
+def test_fused_tourney_equals_oracle_driven_by_the_same_networks(oracle, name, precision):
+    """Fused tourney (cb200_tourney_set_weights / cb200_tourney_run): every model id has a
+    device-resident network and the whole loop of rating/tourney.pyx:112-173 runs on the GPU.
+    The oracle's Tourney, driven through that loop with the same networks (the engine's own
+    kernels as evaluators, so the numbers are bit-identical), must end with the same scores."""
+    players, matches = TOURNEY_CASES[name]
+    model_ids = sorted({p[1] for p in players if p[1] >= 0})
+    weights = {m: cb.fold_batchnorm(cb.random_weights(100 + m)) for m in model_ids}
+    eng = make_tourney(_Engine(), name)
+    for m in model_ids:
+        eng.set_weights(m, weights[m], precision)
+    assert eng.run(0)
+    assert eng.all_done()
+    helpers = {}
+    for m in model_ids:
+        h = cb.Trainer(64, "", 1, 64, 16)
+        h.set_weights(weights[m], 0, precision)
+        helpers[m] = h
+    ref = run_tourney(make_tourney(oracle, name), {m: (lambda req, h=helpers[m]: h.evaluate(req)) for m in model_ids})
+    got = np.array(eng.scores(), np.float64).reshape(-1, 3)
+    assert (got == ref["scores"]).all()
+    c = eng.counters()
+    assert c["leaf_evals"] == int(ref["counts"].sum()) and c["simulations"] > 0
+
+
+def test_fused_tourney_bounded_rounds_and_errors():
+    players, matches = TOURNEY_CASES["two_models"]
+    t = make_tourney(_Engine(), "two_models")
+    with pytest.raises(cb.Corintho200Error):
+        t.run(0)  # no weights yet
+    for m in (0, 1):
+        t.set_weights(m, cb.fold_batchnorm(cb.random_weights(7 + m)), "bf16")
+    done, calls = False, 0
+    while not done:
+        done = t.run(5)
+        calls += 1
+        assert calls < 1000
+    assert calls > 1 and len(t.scores()) == len(matches)

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2k_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r2k_tests.log
+tail -25 gpurun_out/r2k_tests.log
