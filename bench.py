@@ -14,6 +14,7 @@ no collective on the hot path) and the finished samples are all-gathered over NC
 Under torchrun (N > 1) every rank runs; rank 0 prints the single JSON line.
 """
 import argparse
+from ctypes import c_void_p as C_void_p
 import gc
 import json
 import os
@@ -539,11 +540,12 @@ def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
     tr.reset(2000)
     tr.run_selfplay(0, stagger=False)  # untimed warm-up of the streaming path
     tr.streamed_samples()
-    if dist is not None:  # ... and of NCCL's buffers / the allocator's blocks for the gather
-        from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
-        ptr, n_rows = tr.raw_samples_device()
-        all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
-        torch.cuda.synchronize()
+    comm, world = None, 1
+    if dist is not None:  # the engine's own NCCL communicator (C ABI), warmed up once
+        import corintho_ai_b200 as cb
+        world = dist.get_world_size()
+        comm = cb.nccl_comm_from_torch(dist, dist.get_rank(), world, dev)
+        tr.allgather_samples(comm, world)
     out = {"seconds": 0.0, "sims": 0, "h2d": 0, "d2h": 0, "gather_s": 0.0,
            "path": "set_weights(pinned host) + reset + run_selfplay with streamed samples (8 symmetries, "
                    "completion order + game index) + streamed_samples() = all rows in pinned host memory"}
@@ -554,15 +556,14 @@ def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
         tr.reset(2000 + k)
         tr.run_selfplay(0, stagger=False)
         gs, ev, pr, game_of = tr.streamed_samples()
-        if dist is not None:  # all-gather the finished (un-augmented) samples over NCCL
-            from corintho_ai_b200.dist import all_gather_rows_device, device_rows_as_tensor
+        if comm is not None:  # all-gather the finished (un-augmented) samples over NCCL (C ABI)
             g0 = time.perf_counter()
-            ptr, n_rows = tr.raw_samples_device()
-            all_gather_rows_device(dist, device_rows_as_tensor(ptr, n_rows, 102, dev), dev)
-            torch.cuda.synchronize()
+            _, n_all, per_rank = tr.allgather_samples(comm, world)
             out["gather_s"] += time.perf_counter() - g0
         torch.cuda.synchronize()
         out["seconds"] += time.perf_counter() - t0
+        if comm is not None and (n_all != int(per_rank.sum()) or int(per_rank[dist.get_rank()]) != tr.num_samples()):
+            raise SystemExit("bench.py: the NCCL sample gather is inconsistent")
         if game_of.shape[0] != tr.num_samples():
             raise SystemExit("bench.py: the streamed samples are incomplete")
         out["sims"] += tr.counters()["simulations"]
@@ -576,6 +577,9 @@ def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
             np.array_equal(ev[rows].view(np.uint32), e2.view(np.uint32)) and
             np.array_equal(pr[rows].view(np.uint32), p2.view(np.uint32))):
         raise SystemExit("bench.py: streamed samples differ from Trainer::writeSamples")
+    if comm is not None:
+        import corintho_ai_b200 as cb
+        cb.lib().cb200_nccl_comm_destroy(C_void_p(comm))
     return out
 
 

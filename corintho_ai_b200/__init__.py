@@ -82,6 +82,10 @@ def lib():
         "cb200_trainer_raw_samples_device": (i32, [vp, vp, vp]),
         "cb200_trainer_stream_samples": (i32, [vp, i64]),
         "cb200_trainer_streamed_samples": (i32, [vp, vp, vp, vp, vp, vp]),
+        "cb200_nccl_unique_id": (i32, [vp]),
+        "cb200_nccl_comm_create": (vp, [i32, i32, vp]),
+        "cb200_nccl_comm_destroy": (None, [vp]),
+        "cb200_trainer_allgather_samples": (i32, [vp, vp, vp, vp, vp]),
         "cb200_trainer_set_weights": (i32, [vp, i32, vp, C.c_size_t, i32]),
         "cb200_trainer_evaluate": (i32, [vp, i32, i32, vp, vp, vp]),
         "cb200_trainer_run_selfplay": (i32, [vp, i32, i32]),
@@ -109,6 +113,22 @@ def lib():
         f.restype, f.argtypes = res, args
     _lib = L
     return L
+
+
+def nccl_comm_from_torch(dist, rank, world, device):
+    """An NCCL communicator owned by this library for the ranks of a torch.distributed job: rank 0
+    draws the ncclUniqueId, torch.distributed (any backend) carries its 128 bytes to the others."""
+    import torch
+    idbuf = np.zeros(128, np.uint8)
+    if rank == 0:
+        _check(lib().cb200_nccl_unique_id(_ptr(idbuf)))
+    t = torch.from_numpy(idbuf).to(device)
+    dist.broadcast(t, src=0)
+    idbuf = np.ascontiguousarray(t.cpu().numpy())
+    comm = lib().cb200_nccl_comm_create(rank, world, _ptr(idbuf))
+    if not comm:
+        raise Corintho200Error("cb200_nccl_comm_create: " + lib().cb200_last_error().decode())
+    return comm
 
 
 def _check(rc):
@@ -413,6 +433,15 @@ class Trainer:
             return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(count,)).reshape(shape)
         return (view(gs, C.c_float, (n * 8, STATE_SIZE)), view(ev, C.c_float, (n * 8,)),
                 view(pr, C.c_float, (n * 8, NUM_MOVES)), view(go, C.c_int32, (n,)))
+
+    def allgather_samples(self, nccl_comm, world):
+        """NCCL all-gather of every rank's un-augmented samples (collective). Returns (device
+        pointer, total rows, rows per rank); rows are [n][102] floats in global game order."""
+        ptr, n = C.c_void_p(), C.c_int()
+        counts = np.zeros(world, np.int32)
+        _check(lib().cb200_trainer_allgather_samples(self._h, C.c_void_p(nccl_comm), C.byref(ptr),
+                                                     C.byref(n), _ptr(counts)))
+        return ptr.value or 0, n.value, counts
 
     def game_results(self):
         out = np.zeros(self.num_games, np.int32)

@@ -22,6 +22,7 @@
 #include "tree.cuh"
 #include "persistent.cuh"
 #include "match.cuh"
+#include "gather.cuh"
 
 using namespace cb200;
 
@@ -128,6 +129,9 @@ struct cb200_trainer {
   size_t samp_rows = 0;
   float *d_raw = nullptr;   // cached [rows][102] buffer of raw_samples_device
   size_t raw_rows = 0;
+  float *d_gath = nullptr;  // all-gather: [world][max rows][102] padded blocks, then the result
+  size_t gath_floats = 0;
+  int32_t *d_gcounts = nullptr, *h_gcounts = nullptr;  // [world + 1] rows per rank (+ own count)
   int32_t *h_summary = nullptr;  // pinned
   NetF32 net32[2];
   NetTC nettc[2];
@@ -906,6 +910,8 @@ void cb200_trainer_destroy(cb200_trainer *t) {
   cudaFree(t->d_offs), cudaFree(t->d_soff), cudaFree(t->d_summary), cudaFree(P.phase_prof);
   cudaFree(t->d_samp);
   cudaFree(t->d_raw);
+  cudaFree(t->d_gath), cudaFree(t->d_gcounts);
+  if (t->h_gcounts) cudaFreeHost(t->h_gcounts);
   cudaFree(t->d_st), cudaFree(t->d_st_game), cudaFree(t->d_st_ctr), cudaFree(t->d_emitted), cudaFree(t->d_st_soff);
   if (t->h_st) cudaFreeHost(t->h_st);
   if (t->h_st_game) cudaFreeHost(t->h_st_game);
@@ -1182,6 +1188,93 @@ int cb200_trainer_raw_samples_device(cb200_trainer *t, void **rows_device, int *
 }
 
 static int emit_finished(cb200_trainer *t, bool final);
+
+// ---- NCCL all-gather of the finished samples ---------------------------------------
+int cb200_nccl_unique_id(void *id_out) {
+  last_error_ref().clear();
+  NcclApi &N = nccl_api();
+  if (!N.ok) return set_error(CB200_ERR_STATE, "libnccl.so.2 is not available in this process");
+  if (!id_out) return set_error(CB200_ERR_ARG, "null id");
+  CB_NCCL(N.GetUniqueId((NcclUniqueId *)id_out));
+  return CB200_OK;
+}
+
+void *cb200_nccl_comm_create(int rank, int world, const void *unique_id) {
+  last_error_ref().clear();
+  NcclApi &N = nccl_api();
+  if (!N.ok || !unique_id || world <= 0 || rank < 0 || rank >= world) {
+    set_error(CB200_ERR_ARG, "cb200_nccl_comm_create: NCCL unavailable or bad arguments");
+    return nullptr;
+  }
+  NcclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  void *comm = nullptr;
+  const int r = N.CommInitRank(&comm, world, id, rank);
+  if (r != 0) {
+    set_error(CB200_ERR_CUDA, std::string("ncclCommInitRank: ") + N.GetErrorString(r));
+    return nullptr;
+  }
+  return comm;
+}
+
+void cb200_nccl_comm_destroy(void *nccl_comm) {
+  NcclApi &N = nccl_api();
+  if (N.ok && nccl_comm) N.CommDestroy(nccl_comm);
+}
+
+int cb200_trainer_allgather_samples(cb200_trainer *t, void *nccl_comm, void **rows_device, int *n_rows,
+                                    int32_t *rows_per_rank) {
+  int rc = guard(t);
+  if (rc) return rc;
+  NcclApi &N = nccl_api();
+  if (!N.ok) return set_error(CB200_ERR_STATE, "libnccl.so.2 is not available in this process");
+  if (!nccl_comm || !rows_device || !n_rows) return set_error(CB200_ERR_ARG, "null argument");
+  int world = 0, rank = 0;
+  CB_NCCL(N.CommCount(nccl_comm, &world));
+  CB_NCCL(N.CommUserRank(nccl_comm, &rank));
+  void *mine = nullptr;
+  int n_mine = 0;
+  if ((rc = cb200_trainer_raw_samples_device(t, &mine, &n_mine)) != CB200_OK) return rc;
+  cudaStream_t st = cur_stream();
+  if (!t->d_gcounts) {
+    if ((rc = dmalloc(&t->d_gcounts, (size_t)world + 1)) != CB200_OK) return rc;
+    CB_CUDA(cudaMallocHost((void **)&t->h_gcounts, ((size_t)world + 1) * sizeof(int32_t)));
+  }
+  // 1. row counts of every rank
+  t->h_gcounts[world] = n_mine;
+  CB_CUDA(cudaMemcpyAsync(t->d_gcounts + world, t->h_gcounts + world, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CB_NCCL(N.AllGather(t->d_gcounts + world, t->d_gcounts, 1, kNcclInt32, nccl_comm, st));
+  CB_CUDA(cudaMemcpyAsync(t->h_gcounts, t->d_gcounts, (size_t)world * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  long long total = 0;
+  int max_rows = 1;
+  for (int r = 0; r < world; ++r) {
+    total += t->h_gcounts[r];
+    if (t->h_gcounts[r] > max_rows) max_rows = t->h_gcounts[r];
+    if (rows_per_rank) rows_per_rank[r] = t->h_gcounts[r];
+  }
+  // 2. padded all-gather straight from / to device memory, then compaction in rank order
+  const size_t padded = (size_t)world * max_rows * 102, need = padded + (size_t)max_rows * 102 + (size_t)total * 102;
+  if (need > t->gath_floats) {
+    cudaFree(t->d_gath);
+    t->d_gath = nullptr, t->gath_floats = 0;
+    if ((rc = dmalloc(&t->d_gath, need + need / 4)) != CB200_OK) return rc;
+    t->gath_floats = need + need / 4;
+  }
+  float *d_pad = t->d_gath, *d_send = d_pad + padded, *d_out = d_send + (size_t)max_rows * 102;
+  if (n_mine > 0)
+    CB_CUDA(cudaMemcpyAsync(d_send, mine, (size_t)n_mine * 102 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CB_NCCL(N.AllGather(d_send, d_pad, (size_t)max_rows * 102, kNcclFloat32, nccl_comm, st));
+  if (total > 0) {
+    k_compact_gathered<<<dim3(64, world), 256, 0, st>>>(d_pad, d_out, t->d_gcounts, world, max_rows, 102);
+    CB_LAUNCHED();
+    CB_CUDA(cudaGetLastError());
+  }
+  CB_CUDA(cudaStreamSynchronize(st));
+  *rows_device = d_out;
+  *n_rows = (int)total;
+  return CB200_OK;
+}
 
 int cb200_trainer_stream_samples(cb200_trainer *t, int64_t max_samples) {
   int rc = guard(t);

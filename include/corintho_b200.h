@@ -149,6 +149,21 @@ int cb200_trainer_streamed_samples(cb200_trainer *t, const float **game_states /
                                    const float **eval_samples /* [n*8] */,
                                    const float **prob_samples /* [n*8][96] */,
                                    const int32_t **game_of /* [n] */, int *n_samples);
+/* Multi-GPU (one trainer per GPU, contiguous game shards: cb200_trainer_create_shard): the one
+ * collective of the path -- an all-gather of the finished un-augmented samples over NCCL, straight
+ * from and to device memory. `nccl_comm` is an ncclComm_t of the caller's (any NCCL 2.x loaded in
+ * the process; the library resolves the NCCL entry points at run time and links nothing), or one
+ * made by cb200_nccl_comm_create from an ncclUniqueId (128 bytes) that rank 0 obtained with
+ * cb200_nccl_unique_id and distributed by any means. On return *rows_device -> float
+ * [*n_rows][102] rows of ALL ranks in rank (= global game) order, layout as in
+ * cb200_trainer_raw_samples_device, owned by the trainer and valid until its next call;
+ * rows_per_rank[world] (may be NULL) receives the per-rank counts. Collective: every rank of
+ * the communicator must call it. */
+int cb200_nccl_unique_id(void *id_out /* 128 bytes */);
+void *cb200_nccl_comm_create(int rank, int world, const void *unique_id /* 128 bytes */);
+void cb200_nccl_comm_destroy(void *nccl_comm);
+int cb200_trainer_allgather_samples(cb200_trainer *t, void *nccl_comm, void **rows_device, int *n_rows,
+                                    int32_t *rows_per_rank);
 /* per game: result (util.h:58-61: 1 first player lost, 2 draw, 3 first player won) */
 int cb200_trainer_game_results(cb200_trainer *t, int32_t *results /* [num_games] */);
 

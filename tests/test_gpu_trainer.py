@@ -194,3 +194,26 @@ def test_raw_sample_buffer_survives_growth_of_the_augmented_buffer():
     # and once more after the buffers are warm
     ptr2, n2 = t.raw_samples_device()
     assert (ptr2, n2) == (ptr1, n1)
+
+
+def test_nccl_allgather_single_rank_returns_own_rows():
+    """cb200_trainer_allgather_samples with a one-rank NCCL communicator made through the C ABI
+    (unique id -> comm): the result is the rank's own raw rows, in order."""
+    import torch
+    from corintho_ai_b200.dist import device_rows_as_tensor
+    idbuf = np.zeros(128, np.uint8)
+    L = cb.lib()
+    assert L.cb200_nccl_unique_id(idbuf.ctypes.data) == 0
+    comm = L.cb200_nccl_comm_create(0, 1, idbuf.ctypes.data)
+    assert comm
+    t = cb.Trainer(32, "", 9, 32, 8, 1.0, 0.25)
+    t.set_weights(cb.fold_batchnorm(cb.random_weights(1)), 0, "fp32")
+    assert t.run_selfplay(0)
+    ptr, n, counts = t.allgather_samples(comm, 1)
+    st, pr, lb, go = t.raw_samples()
+    assert n == t.num_samples() and counts.tolist() == [n]
+    rows = device_rows_as_tensor(ptr, n, 102, torch.device("cuda", 0)).cpu().numpy()
+    assert np.array_equal(np.ascontiguousarray(rows[:, 4:100]), pr) and np.array_equal(rows[:, 100], lb)
+    assert np.array_equal(np.ascontiguousarray(rows[:, 101]).view(np.int32), go)
+    import ctypes
+    L.cb200_nccl_comm_destroy(ctypes.c_void_p(comm))
