@@ -1657,7 +1657,9 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   k_iterate<true, L, MB><<<grid, block, 0, st>>>(P, t->d_eval, t->d_probs, prs, pcs, nullptr, -1, it, t->stagger_div)
             // lanes per game x resident CTAs per SM (register budget 65536 / (128 * MB))
             if (t->lanes == 32) {
-              if (t->min_blocks >= 6) CB_ITER(32, 6);
+              if (t->min_blocks >= 8) CB_ITER(32, 8);
+              else if (t->min_blocks == 7) CB_ITER(32, 7);
+              else if (t->min_blocks == 6) CB_ITER(32, 6);
               else if (t->min_blocks == 5) CB_ITER(32, 5);
               else CB_ITER(32, 4);
             } else {

@@ -66,6 +66,83 @@ __global__ void __launch_bounds__(kStepThreads)
   }
 }
 
+// K1, split form (no encoding requested). 85 % of reachable positions contain no line, and for
+// them the legal mask is the basic-rule mask; the line rules (category search, four table masks,
+// capital fix-ups) are ~60 % of the select-only instruction stream above. A CTA therefore runs
+//   phase A  every thread: basic mask + "any line?" test; positions without a line are finished
+//            at once, the others are queued in shared memory (state + index);
+//   phase B  whenever 256 positions are queued, every thread takes one and runs the full
+//            legal_moves_t on it -- dense warps on the expensive path instead of 5 live lanes.
+// Same outputs as k_game_step<false> (tests compare both with the oracle); stores of queued
+// positions are scattered 16-byte writes (15 % of the states).
+__device__ __forceinline__ void game_step_finish(int i, const CState &s, const uint32_t m[3], bool lines,
+                                                 uint64_t seed, uint4 *__restrict__ mask_flags,
+                                                 ulonglong2 *__restrict__ next) {
+  const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
+  const int result = terminal_result(nl, lines);
+  const uint32_t rnd = step_rnd(seed, (uint64_t)i), dv = (uint32_t)max(nl, 1);
+  uint32_t rem = rnd - __umulhi(rnd, __ldg(d_inv32 + dv)) * dv;
+  rem -= rem >= dv ? dv : 0u;
+  const int pick = nth_move(m, (int)rem);
+  const CState moved = do_move(s, pick & 127);
+  const int chosen = nl > 0 ? pick : 0x7f;
+  CState o;
+  o.w0 = nl > 0 ? moved.w0 : s.w0, o.w1 = nl > 0 ? moved.w1 : s.w1;
+  mask_flags[i] = make_uint4(m[0], m[1], m[2],
+                             (uint32_t)result | (lines ? 4u : 0u) | ((uint32_t)nl << 8) | ((uint32_t)chosen << 16));
+  next[i] = make_ulonglong2(o.w0, o.w1);
+}
+
+__global__ void __launch_bounds__(kStepThreads)
+    k_game_step_split(int64_t n, const ulonglong2 *__restrict__ states, uint64_t seed,
+                      uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next) {
+  constexpr int kQueue = 2 * kStepThreads;  // fewer than 256 entries before a trip, at most 256 more
+  __shared__ ulonglong2 q_state[kQueue];
+  __shared__ int q_idx[kQueue];
+  __shared__ int q_n;
+  const int tid = threadIdx.x;
+  if (tid == 0) q_n = 0;
+  __syncthreads();
+  const int stride = (int)gridDim.x * kStepThreads;
+  const int n_round = (int)(((n + kStepThreads - 1) / kStepThreads) * kStepThreads);  // uniform trip count per CTA
+  for (int base = (int)blockIdx.x * kStepThreads; base < n_round; base += stride) {
+    const int i = base + tid;
+    if (i < n) {
+      const ulonglong2 v = __ldg(states + i);
+      const CState s{v.x, v.y};
+      uint32_t m[3];
+      if (!basic_moves(s, m)) {
+        game_step_finish(i, s, m, false, seed, mask_flags, next);
+      } else {
+        // (a warp-aggregated append -- ballot + one atomic per warp -- measured 4 % slower: the
+        // ballot makes the whole warp wait for its slowest lane before the next trip's load)
+        const int slot = atomicAdd(&q_n, 1);
+        q_state[slot] = v, q_idx[slot] = i;
+      }
+    }
+    __syncthreads();
+    const int qn = q_n;
+    if (qn >= kStepThreads) {  // CTA-uniform: one queued position per thread
+      const int e = qn - kStepThreads + tid;
+      const ulonglong2 v = q_state[e];
+      const CState s{v.x, v.y};
+      uint32_t m[3];
+      const bool lines = legal_moves_t<false>(s, m, DeviceLB());
+      game_step_finish(q_idx[e], s, m, lines, seed, mask_flags, next);
+      __syncthreads();
+      if (tid == 0) q_n = qn - kStepThreads;
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < q_n; e += kStepThreads) {  // drain
+    const ulonglong2 v = q_state[e];
+    const CState s{v.x, v.y};
+    uint32_t m[3];
+    const bool lines = legal_moves_t<false>(s, m, DeviceLB());
+    game_step_finish(q_idx[e], s, m, lines, seed, mask_flags, next);
+  }
+}
+
 inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void *d_mask_flags,
                             void *d_next, void *d_enc) {
   if (n <= 0) return CB200_OK;
@@ -83,10 +160,13 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
     k_game_step<true><<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
         (float *)d_enc);
-  else
+  else if (getenv("CB200_K1_SELECT_ONLY"))  // the round-1 kernel, kept for comparison
     k_game_step<false><<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
         nullptr);
+  else
+    k_game_step_split<<<grid, kStepThreads, 0, cur_stream()>>>(
+        n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;

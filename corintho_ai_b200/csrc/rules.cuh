@@ -200,6 +200,48 @@ CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
   m[0] = m0, m[1] = m1, m[2] = m2;
   return lines;
 }
+// First half of legal_moves_t for callers that treat positions with a line separately (K1): the
+// basic-rule mask (canPlace / canMove only) and whether ANY line exists on the board -- the
+// union of the four `has` conditions above. Without a line the basic mask IS the legal mask.
+CB_HD bool basic_moves(const CState &st, uint32_t m[3]) {
+  const uint32_t lo = (uint32_t)st.w0, hi = (uint32_t)(st.w0 >> 32);
+  const uint32_t B = lo & 0xFFFFu, C = lo >> 16, A = hi & 0xFFFFu, F = hi >> 16;
+  const uint32_t O = B | C | A;
+  const uint32_t E = ~O & 0xFFFFu;
+  const uint32_t T2 = A, T1 = C & ~A, T0 = B & ~(C | A);
+  const uint32_t bot1 = C & ~B, bot2 = A & ~(B | C);
+  const uint32_t nF = ~F;
+  const uint32_t X1 = bot1 & nF, X2 = bot2 & nF, Y0 = T0 & nF, Y1 = T1 & nF;
+  const uint32_t mr = ((X1 & (Y0 >> 1)) | (X2 & (Y1 >> 1))) & 0x7777u;
+  const uint32_t md = ((X1 & (Y0 >> 4)) | (X2 & (Y1 >> 4))) & 0x0FFFu;
+  const uint32_t ml = ((X1 & (Y0 << 1)) | (X2 & (Y1 << 1))) & 0xEEEEu;
+  const uint32_t mu = ((X1 & (Y0 << 4)) | (X2 & (Y1 << 4))) & 0xFFF0u;
+  const uint32_t R12 = compress3(mr), L12 = compress3(ml >> 1), D12 = md, U12 = mu >> 4;
+  const uint32_t tp = (uint32_t)(st.w1 >> 48) & 1u;
+  const uint32_t pcs = (uint32_t)(st.w1 >> (24 * tp)) & 0xFFFFFFu;
+  const uint32_t pb = (pcs & 0xFFu) ? E : 0u;
+  const uint32_t pc = (pcs & 0xFF00u) ? (E | Y0) : 0u;
+  const uint32_t pa = (pcs & 0xFF0000u) ? (E | Y1) : 0u;
+  m[0] = R12 | (D12 << 12) | (L12 << 24);
+  m[1] = (L12 >> 8) | (U12 << 4) | (pb << 16);
+  m[2] = pc | (pa << 16);
+  // three equal tops in a row (step 1, starts in columns 0-1), in a column (step 4, rows 0-1), on
+  // a diagonal (step 5 from squares 0, 1, 4, 5; step 3 from squares 2, 3, 6, 7): the three planes
+  // are disjoint, so each step needs one AND chain per plane
+  uint32_t row = 0, col = 0, d5 = 0, d3 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int p = 0; p < 3; ++p) {
+    const uint32_t T = p == 0 ? T0 : (p == 1 ? T1 : T2);
+    row |= T & (T >> 1) & (T >> 2);
+    col |= T & (T >> 4) & (T >> 8);
+    d5 |= T & (T >> 5) & (T >> 10);
+    d3 |= T & (T >> 3) & (T >> 6);
+  }
+  return ((row & 0x3333u) | (col & 0x00FFu) | (d5 & 0x33u) | (d3 & 0xCCu)) != 0u;
+}
+
 template <class LBFn>
 CB_HD bool legal_moves(const CState &st, uint32_t m[3], LBFn LB) {
   return legal_moves_t<false>(st, m, LB);
