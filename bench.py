@@ -558,7 +558,7 @@ def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
         gs, ev, pr, game_of = tr.streamed_samples()
         if comm is not None:  # all-gather the finished (un-augmented) samples over NCCL (C ABI)
             g0 = time.perf_counter()
-            _, n_all, per_rank = tr.allgather_samples(comm, world)
+            ptr_all, n_all, per_rank = tr.allgather_samples(comm, world)
             out["gather_s"] += time.perf_counter() - g0
         torch.cuda.synchronize()
         out["seconds"] += time.perf_counter() - t0
@@ -578,6 +578,12 @@ def run_e2e(args, tr, torch, dist, dev, pinned_w, flat, G, barrier):
             np.array_equal(pr[rows].view(np.uint32), p2.view(np.uint32))):
         raise SystemExit("bench.py: streamed samples differ from Trainer::writeSamples")
     if comm is not None:
+        # the gathered rows of the last step: every rank's samples, in global game order
+        from corintho_ai_b200.dist import device_rows_as_tensor
+        games = device_rows_as_tensor(ptr_all, n_all, 102, dev)[:, 101].contiguous().view(torch.int32).cpu().numpy()
+        if not (np.all(np.diff(games) >= 0) and games[0] == 0 and games[-1] == G * world - 1 and
+                len(np.unique(games)) == G * world):
+            raise SystemExit("bench.py: the gathered samples are not in global game order")
         import corintho_ai_b200 as cb
         cb.lib().cb200_nccl_comm_destroy(C_void_p(comm))
     return out

@@ -87,6 +87,14 @@ __global__ void k_emit_assign(TreeParams P, int32_t *__restrict__ emitted, int32
   emitted[g] = stamp;
 }
 
+// move-major network output [96][ld] -> row-major [rows][96] (cb200_trainer_evaluate)
+__global__ void k_probs_row_major(const float *__restrict__ mm, int ld, int rows, float *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * CB200_NUM_MOVES) return;
+  const int r = i / CB200_NUM_MOVES, m = i - r * CB200_NUM_MOVES;
+  out[i] = mm[(size_t)m * ld + r];
+}
+
 // Un-augmented samples as 102-float rows for the NCCL gather: 4 words of cstate (bit-cast),
 // 96 move probabilities, the value label, the global game index (bit-cast).
 __global__ void __launch_bounds__(256)
@@ -1376,12 +1384,19 @@ int cb200_trainer_evaluate(cb200_trainer *t, int model, int n, const float *game
   if ((rc = run_net(t, model, t->d_packed, nullptr, n, n)) != CB200_OK) return rc;
   CB_CUDA(cudaMemcpyAsync(eval, t->d_eval, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (t->precision[model] == 1) {  // move-major [96][cap] on the device -> row-major for the caller
-    std::vector<float> tmp((size_t)CB200_NUM_MOVES * n);
-    CB_CUDA(cudaMemcpy2DAsync(tmp.data(), (size_t)n * sizeof(float), t->d_probs, t->cap * sizeof(float),
-                              (size_t)n * sizeof(float), CB200_NUM_MOVES, cudaMemcpyDeviceToHost, s));
+    // transposed on the device into the (idle) request-row buffer: cap * 70 floats >= n * 96 is not
+    // guaranteed, so rows go through it in slices
+    const size_t slice = t->cap * CB200_STATE_SIZE / CB200_NUM_MOVES;
+    for (size_t r0 = 0; r0 < (size_t)n; r0 += slice) {
+      const int rows = (int)std::min(slice, (size_t)n - r0);
+      k_probs_row_major<<<(rows * CB200_NUM_MOVES + 255) / 256, 256, 0, s>>>(t->d_probs + r0, (int)t->cap, rows,
+                                                                             t->d_rows);
+      CB_LAUNCHED();
+      CB_CUDA(cudaGetLastError());
+      CB_CUDA(cudaMemcpyAsync(probs + r0 * CB200_NUM_MOVES, t->d_rows, (size_t)rows * CB200_NUM_MOVES * sizeof(float),
+                              cudaMemcpyDeviceToHost, s));
+    }
     CB_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < n; ++i)
-      for (int m = 0; m < CB200_NUM_MOVES; ++m) probs[(size_t)i * CB200_NUM_MOVES + m] = tmp[(size_t)m * n + i];
     return CB200_OK;
   }
   CB_CUDA(cudaMemcpyAsync(probs, t->d_probs, (size_t)n * CB200_NUM_MOVES * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -29,3 +29,23 @@ extern "C" void shim_step_batch(int64_t n, const uint64_t *states, uint64_t seed
   }
 }
 extern "C" uint32_t shim_step_rnd(uint64_t seed, uint64_t i) { return cb200::step_rnd(seed, i); }
+
+// basic_moves() (the first half of legal_moves_t that the split K1 kernel runs on every position):
+// its "any line" flag must equal legal_moves_t's, and without a line its mask IS the legal mask.
+// Returns the number of positions where that fails.
+extern "C" int64_t shim_basic_moves_check(int64_t n, const uint64_t *states) {
+  using namespace cb200;
+  static const uint32_t ones[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  auto LB = [](int idx) { return idx < 102 ? kCLineBreakers[idx] : ones; };
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    CState s{states[2 * i], states[2 * i + 1]};
+    uint32_t m[3], b[3];
+    const bool lines = legal_moves_t<false>(s, m, LB);
+    const bool any = basic_moves(s, b);
+    if (any != lines) ++bad;
+    else if (!any && (b[0] != m[0] || b[1] != m[1] || b[2] != m[2])) ++bad;
+    else if (any && ((m[0] & ~b[0]) | (m[1] & ~b[1]) | (m[2] & ~b[2]))) ++bad;  // line rules only remove moves
+  }
+  return bad;
+}

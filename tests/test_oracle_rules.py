@@ -137,6 +137,19 @@ def test_swar_rules_header_matches_golden():
     assert [lib.shim_step_rnd(C.c_uint64(seed), C.c_uint64(i)) for i in range(64)] == list(r)
 
 
+def test_basic_moves_is_the_legal_mask_when_no_line_exists(ref):
+    """The split game-logic kernel (game_step.cuh) finishes positions without a line from
+    basic_moves() alone and queues the others: its line flag must equal legal_moves_t's and, when
+    no line exists, its mask must be the legal mask. 300 k reachable positions + the golden set."""
+    from corintho_ai_b200 import planes_from_reference_order
+    lib = _shim()
+    lib.shim_basic_moves_check.restype = C.c_int64
+    for states in (GOLD["states"], ref.gen_states(4242, 300000)):
+        pl = planes_from_reference_order(states)
+        bad = lib.shim_basic_moves_check(C.c_int64(len(pl)), pl.ctypes.data_as(C.c_void_p))
+        assert bad == 0
+
+
 def test_capital_fixups_are_exercised(oracle):
     """Q2: short capital row/column lines occur in the golden set (top==capital, short line)."""
     states = GOLD["states"]
