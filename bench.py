@@ -357,8 +357,10 @@ def run_engine_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = L.cb200_launch_count()
+    tr.set_profiling(False)  # clears the phase clocks
     dev_ms, sims, moves, evals, iters = timed_steps(tr)
     launches = L.cb200_launch_count() - launches0
+    phase_ms = tr.phase_times()  # of the timed (un-profiled) pass
     digest_timed = samples_digest(tr)
 
     # ---- (2) the SAME steps on the SAME schedule (stream groups, parking, persistent tail) with a
@@ -471,6 +473,17 @@ def run_engine_arm(args, rank, world, local_rank):
     roof["kernel_ms_per_step"] = {k: classes[k]["ms"] / args.steps for k in classes}
     roof["kernel_launches_per_step"] = {k: classes[k]["launches"] / args.steps for k in classes}
     roof["stream_overlap_factor"] = total_class_ms / max(1e-9, prof_ms)
+    # GPU-level rates of the two phases of the TIMED pass (host clock between the synchronisation
+    # points that separate them; simulations per phase from the profiled pass of the same games):
+    # what the whole device achieves while the overlapping kernels of a phase run
+    roof["phases_of_the_timed_pass"] = {
+        "lockstep": {"ms_per_step": phase_ms["lockstep_ms"] / args.steps, "simulations_per_step": ls_sims / args.steps,
+                     "algorithmic_gbs": ALGO_BYTES_PER_SIM * ls_sims / max(1e-9, phase_ms["lockstep_ms"] * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": ALGO_BYTES_PER_SIM * ls_sims / max(1e-9, phase_ms["lockstep_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "persistent_tail": {"ms_per_step": phase_ms["tail_ms"] / args.steps, "simulations_per_step": tail_sims / args.steps,
+                            "algorithmic_gbs": ALGO_BYTES_PER_SIM * tail_sims / max(1e-9, phase_ms["tail_ms"] * 1e-3) / 1e9,
+                            "frac_of_hbm_peak": ALGO_BYTES_PER_SIM * tail_sims / max(1e-9, phase_ms["tail_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
+    }
     roof["note"] = ("sum of kernel-class times per step = %.1f ms = %.2f x the profiled step (%.1f ms): kernels of "
                     "different stream groups overlap. Whole-step algorithmic rates of the timed pass: %.1f GB/s tree "
                     "traffic, %.2f TFLOP/s network"

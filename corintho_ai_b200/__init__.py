@@ -95,6 +95,7 @@ def lib():
         "cb200_trainer_set_profiling": (i32, [vp, i32]),
         "cb200_trainer_kernel_times": (i32, [vp, vp, vp]),
         "cb200_trainer_phase_split": (i32, [vp, vp]),
+        "cb200_trainer_phase_times": (i32, [vp, vp]),
         "cb200_tourney_create": (vp, [i32, C.c_char_p]),
         "cb200_tourney_destroy": (None, [vp]),
         "cb200_tourney_add_player": (i32, [vp, i32, i32, i32, i32, f32, f32, i32]),
@@ -393,6 +394,13 @@ class Trainer:
         _check(lib().cb200_trainer_phase_split(self._h, _ptr(out)))
         return {"lockstep_simulations": int(out[0]), "simulations": int(out[1]),
                 "lockstep_leaf_evals": int(out[2]), "leaf_evals": int(out[3])}
+
+    def phase_times(self):
+        """Host-clock ms spent in the lock-step phase / in the persistent kernels since the last
+        set_profiling() call."""
+        out = np.zeros(2, np.float64)
+        _check(lib().cb200_trainer_phase_times(self._h, _ptr(out)))
+        return {"lockstep_ms": float(out[0]), "tail_ms": float(out[1])}
 
     def raw_samples(self):
         n = self.num_samples()

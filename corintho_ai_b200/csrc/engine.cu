@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include <iomanip>
 #include <memory>
@@ -200,6 +201,9 @@ struct cb200_trainer {
   // (the rest of a run belongs to the persistent kernels); marks = values at the last snapshot
   long long searches_now = 0, searches_mark = 0, evals_mark = 0;
   long long lockstep_searches = 0, lockstep_evals = 0, total_searches = 0, total_evals = 0;
+  // host-clock duration of the two phases of fused training runs (always on; the switch between
+  // them is a host synchronisation point anyway); cleared by cb200_trainer_set_profiling
+  double lockstep_wall_ms = 0, tail_wall_ms = 0;
   double class_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long class_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -883,6 +887,14 @@ int cb200_trainer_set_profiling(cb200_trainer *t, int enable) {
   t->profiling = enable != 0;
   for (int i = 0; i < 8; ++i) t->class_ms[i] = 0, t->class_launches[i] = 0;
   t->lockstep_searches = t->lockstep_evals = t->total_searches = t->total_evals = 0;
+  t->lockstep_wall_ms = t->tail_wall_ms = 0;
+  return CB200_OK;
+}
+
+int cb200_trainer_phase_times(cb200_trainer *t, double out_ms[2]) {
+  int rc = guard(t);
+  if (rc) return rc;
+  out_ms[0] = t->lockstep_wall_ms, out_ms[1] = t->tail_wall_ms;
   return CB200_OK;
 }
 
@@ -1569,6 +1581,13 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   CB_CUDA(cudaStreamSynchronize(cur_stream()));
   int done_iters = 0, result = 0;
   long long live_games = t->P.num_games;
+  auto wall0 = std::chrono::steady_clock::now();
+  auto lap_ms = [&wall0]() {
+    const auto now = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(now - wall0).count();
+    wall0 = now;
+    return ms;
+  };
   // parking budget (TreeParams::yield_budget): a typical doIteration is ~16 searches x ~3 levels
   // = ~60 units; while many games are live, longer ones (end-game searches that keep hitting
   // terminal nodes) are cut into several launches. Once few games are left nobody gains from
@@ -1611,14 +1630,17 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       int rc = ps_list_games(t);
       if (rc != CB200_OK) return rc;
       t->ps_active = true, t->ps_from_lockstep = true;
+      t->lockstep_wall_ms += lap_ms();
       if (t->profiling && (rc = prof_mark(t, true)) != CB200_OK) return rc;
     }
     if (t->ps_active) {
       int rounds = 0;
       bool all_done = false;
       const int cap = max_iterations > 0 ? max_iterations - done_iters : (1 << 30);
+      lap_ms();
       int rc = run_persistent(t, cap, &rounds, &all_done);
       if (rc != CB200_OK) return rc;
+      t->tail_wall_ms += lap_ms();
       done_iters += rounds;
       if (all_done) result = 1;
       break;
@@ -1713,6 +1735,7 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
       live += c[2 + par];
     }
     live_games = live;
+    t->lockstep_wall_ms += lap_ms();
     if (live == 0) {
       result = 1;
       break;

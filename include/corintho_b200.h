@@ -202,6 +202,10 @@ int cb200_trainer_set_profiling(cb200_trainer *t, int enable);
  * ingested by lock-step launches, leaf evaluations in total}; the remainder belongs to the
  * persistent kernels (classes 4 and 5). Reset by cb200_trainer_set_profiling. */
 int cb200_trainer_phase_split(cb200_trainer *t, int64_t out[4]);
+/* Host-clock duration (ms) of the two phases of the fused training runs made since the last
+ * cb200_trainer_set_profiling call: out = {lock-step phase (stream groups), persistent kernels}.
+ * The phases are separated by host synchronisation points; measured with or without profiling. */
+int cb200_trainer_phase_times(cb200_trainer *t, double out_ms[2]);
 int cb200_trainer_kernel_times(cb200_trainer *t, double out_ms[8], int64_t out_launches[8]);
 
 /* Debug: per-warp phase cycle maxima/sums of the game-step kernel since the last call:
