@@ -141,6 +141,7 @@ struct cb200_trainer {
   float *d_gath = nullptr;  // all-gather: [world][max rows][102] padded blocks, then the result
   size_t gath_floats = 0;
   int32_t *d_gcounts = nullptr, *h_gcounts = nullptr;  // [world + 1] rows per rank (+ own count)
+  int gcounts_world = 0;    // communicator size the count buffers were allocated for
   int32_t *h_summary = nullptr;  // pinned
   NetF32 net32[2];
   NetTC nettc[2];
@@ -1256,9 +1257,13 @@ int cb200_trainer_allgather_samples(cb200_trainer *t, void *nccl_comm, void **ro
   int n_mine = 0;
   if ((rc = cb200_trainer_raw_samples_device(t, &mine, &n_mine)) != CB200_OK) return rc;
   cudaStream_t st = cur_stream();
-  if (!t->d_gcounts) {
+  if (world > t->gcounts_world) {  // first call, or a larger communicator than before
+    cudaFree(t->d_gcounts);
+    if (t->h_gcounts) cudaFreeHost(t->h_gcounts);
+    t->d_gcounts = nullptr, t->h_gcounts = nullptr, t->gcounts_world = 0;
     if ((rc = dmalloc(&t->d_gcounts, (size_t)world + 1)) != CB200_OK) return rc;
     CB_CUDA(cudaMallocHost((void **)&t->h_gcounts, ((size_t)world + 1) * sizeof(int32_t)));
+    t->gcounts_world = world;
   }
   // 1. row counts of every rank
   t->h_gcounts[world] = n_mine;
