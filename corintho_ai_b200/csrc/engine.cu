@@ -1978,7 +1978,7 @@ static int tourney_drain_logs(cb200_tourney *T) {
 // offsets + summary for one model id; h_summary = {requests, live matches, error, rows read}
 static int tourney_scan(cb200_tourney *T, int id) {
   cb200_trainer *t = T->t;
-  k_match_scan<<<1, 32, 0, cur_stream()>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs,
+  k_match_scan<<<1, 1024, 0, cur_stream()>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs,
                                          t->d_summary);
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
@@ -2134,7 +2134,7 @@ int cb200_tourney_run(cb200_tourney *T, int max_rounds) {
   int rounds = 0;
   for (;;) {
     // all_done() check (tourney.pyx:118) every few rounds: one small read-back
-    k_match_scan<<<1, 32, 0, st>>>(t->P, T->d_sides, 0x7fffffff, T->d_pack_offs, T->d_iter_offs, t->d_summary);
+    k_match_scan<<<1, 1024, 0, st>>>(t->P, T->d_sides, 0x7fffffff, T->d_pack_offs, T->d_iter_offs, t->d_summary);
     CB_LAUNCHED();
     CB_CUDA(cudaGetLastError());
     if ((rc = fetch_summary(t)) != CB200_OK) return rc;
@@ -2145,7 +2145,7 @@ int cb200_tourney_run(cb200_tourney *T, int max_rounds) {
     for (int r = 0; r < batch; ++r) {
       for (int id : T->model_order) {
         // offsets of both kinds + request count of this model (summary[0], read by the network)
-        k_match_scan<<<1, 32, 0, st>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs, t->d_summary);
+        k_match_scan<<<1, 1024, 0, st>>>(t->P, T->d_sides, id, T->d_pack_offs, T->d_iter_offs, t->d_summary);
         CB_LAUNCHED();
         long prs = CB200_NUM_MOVES, pcs = 1;
         if (id >= 0) {

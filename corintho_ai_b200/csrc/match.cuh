@@ -193,32 +193,64 @@ __global__ void __launch_bounds__(kTreeWarps * 32, 4)
   }
 }
 
-// Offsets of both kinds for one model id (single thread: a tourney has at most a few thousand
-// matches). pack_offs = contiguous packing of Tourney::writeRequests (tourney.cpp:44-52);
+// Offsets of both kinds for one model id (one CTA of 1024 threads; both are prefix sums).
+// pack_offs = contiguous packing of Tourney::writeRequests (tourney.cpp:44-52);
 // iter_offs = the answer offsets of Tourney::doIteration (tourney.cpp:54-62), which advance by
 // the request count of match i-1 whenever match i is selected -- literally.
 // summary = {requests of the selected matches, matches not done, error code, max row read}.
-__global__ void k_match_scan(TreeParams P, const MatchSide *__restrict__ sides_all, int model_id,
-                             int32_t *__restrict__ pack_offs, int32_t *__restrict__ iter_offs,
-                             int32_t *__restrict__ summary) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int pack = 0, it = 0, live = 0, err = 0, max_row = 0;
-  for (int g = 0; g < P.num_games; ++g) {
+__global__ void __launch_bounds__(1024)
+    k_match_scan(TreeParams P, const MatchSide *__restrict__ sides_all, int model_id,
+                 int32_t *__restrict__ pack_offs, int32_t *__restrict__ iter_offs,
+                 int32_t *__restrict__ summary) {
+  __shared__ int s_pack[1024], s_it[1024];
+  __shared__ int s_live, s_err, s_max;
+  const int t = threadIdx.x;
+  if (t == 0) s_live = 0, s_err = 0, s_max = 0;
+  __syncthreads();
+  const int per = (P.num_games + 1023) / 1024;
+  const int g0 = t * per, g1 = min(P.num_games, g0 + per);
+  // the amount iter_offs advances at match g, and the rows match g packs
+  auto step_of = [&](int g, int &n_sel) -> int {
     const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
     const bool sel = match_selected(ctl, sides_all + 2 * (size_t)g, model_id);
-    if (g > 0 && sel)
-      it += match_requests(P.ctl + (size_t)(g - 1) * kCtlWords, sides_all + 2 * (size_t)(g - 1));
-    iter_offs[g] = it;
-    pack_offs[g] = pack;
-    if (sel) {
-      const int n = match_requests(ctl, sides_all + 2 * (size_t)g);
-      pack += n;
-      if (it + n > max_row) max_row = it + n;
-    }
+    n_sel = sel ? match_requests(ctl, sides_all + 2 * (size_t)g) : -1;
+    return (g > 0 && sel)
+               ? match_requests(P.ctl + (size_t)(g - 1) * kCtlWords, sides_all + 2 * (size_t)(g - 1))
+               : 0;
+  };
+  int pack = 0, it = 0, live = 0, err = 0;
+  for (int g = g0; g < g1; ++g) {
+    int n_sel;
+    it += step_of(g, n_sel);
+    if (n_sel >= 0) pack += n_sel;
+    const int32_t *ctl = P.ctl + (size_t)g * kCtlWords;
     if (!ctl[CW_DONE]) ++live;
     if (ctl[CW_ERROR]) err = ctl[CW_ERROR];
   }
-  summary[0] = pack, summary[1] = live, summary[2] = err, summary[3] = max_row;
+  s_pack[t] = pack, s_it[t] = it;
+  if (live) atomicAdd(&s_live, live);
+  if (err) atomicMin(&s_err, err);
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scans over the 1024 partials
+    const int a = (t >= d) ? s_pack[t - d] : 0, b = (t >= d) ? s_it[t - d] : 0;
+    __syncthreads();
+    s_pack[t] += a, s_it[t] += b;
+    __syncthreads();
+  }
+  int run_pack = s_pack[t] - pack, run_it = s_it[t] - it, max_row = 0;
+  for (int g = g0; g < g1; ++g) {
+    int n_sel;
+    run_it += step_of(g, n_sel);
+    iter_offs[g] = run_it;
+    pack_offs[g] = run_pack;
+    if (n_sel >= 0) {
+      run_pack += n_sel;
+      if (run_it + n_sel > max_row) max_row = run_it + n_sel;
+    }
+  }
+  if (max_row) atomicMax(&s_max, max_row);
+  __syncthreads();
+  if (t == 0) summary[0] = s_pack[1023], summary[1] = s_live, summary[2] = s_err, summary[3] = s_max;
 }
 
 // Tourney::writeRequests (tourney.cpp:44-52): 70-float rows of the selected matches
