@@ -1515,8 +1515,13 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
   cudaStream_t st = t->g_stream[0];
   *rounds_done = 0, *all_done = false;
   TreeParams P = t->P;
-  P.yield_budget = 0;
+  // parking inside the persistent kernels (CB200_PS_YIELD = work budget per round, 0 = off; only
+  // while at least CB200_PS_YIELD_MIN_LIVE games are live)
+  int ps_yield = 0, ps_yield_min = 512;
+  if (const char *e = getenv("CB200_PS_YIELD")) ps_yield = atoi(e);
+  if (const char *e = getenv("CB200_PS_YIELD_MIN_LIVE")) ps_yield_min = atoi(e);
   while (*rounds_done < max_rounds) {
+    P.yield_budget = t->ps_n >= ps_yield_min ? ps_yield : 0;
     if (t->ps_n == 0) {
       *all_done = true;
       break;
