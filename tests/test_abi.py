@@ -75,3 +75,31 @@ def test_weight_folding_layout():
     s = np.float64(1.0) / np.sqrt(1.0 + 1e-3)
     w2 = flat[7100:7100 + 10000].reshape(100, 100)
     assert np.allclose(w2, p["layers"][1]["W"] * s, rtol=1e-6)
+
+
+def test_python_mirror_validates_buffers_like_the_cython_binding():
+    """The reference's Cython layer takes typed float32 memoryviews (main.pyx:30-38) and rejects
+    anything else; the ctypes mirror passes raw pointers, so it checks dtype / layout / size itself
+    (advisor finding, round 1). No GPU needed: the checks run before the library is called."""
+    import numpy as np
+    import pytest
+    import corintho_ai_b200 as cb
+    ok = np.zeros((4, 70), np.float32)
+    assert cb._out_f32(ok, 280, "x") is ok
+    for bad in (np.zeros((4, 70), np.float64), np.zeros((8, 70), np.float32)[::2], [0.0] * 280):
+        with pytest.raises(cb.Corintho200Error):
+            cb._out_f32(bad, 280, "x")
+    with pytest.raises(cb.Corintho200Error):
+        cb._out_f32(ok, 281, "x")                       # too small
+    ro = np.zeros(280, np.float32)
+    ro.setflags(write=False)
+    with pytest.raises(cb.Corintho200Error):
+        cb._out_f32(ro, 280, "x")                       # not writable
+    # inputs are converted (float64 / strided views become contiguous float32) but never short
+    conv = cb._in_f32(np.arange(8, dtype=np.float64)[::2], 4, "y")
+    assert conv.dtype == np.float32 and conv.flags.c_contiguous and conv.tolist() == [0.0, 2.0, 4.0, 6.0]
+    with pytest.raises(cb.Corintho200Error):
+        cb._in_f32(np.zeros(3, np.float32), 4, "y")
+    with pytest.raises(cb.Corintho200Error):
+        cb._in_f32(None, 1, "y")
+    assert cb._in_f32(None, 0, "y") is None
