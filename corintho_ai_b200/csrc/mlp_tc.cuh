@@ -300,7 +300,7 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
   const uint32_t tmem_row = tmem_tile + ((uint32_t)((warp & 3) * 32) << 16);     // lane offset
   uint8_t *myA = S.sA + wg * kTileBytes;  // hi copy; the lo copy (bf16x3) follows at + kTcABytes
   const uint32_t aaddr = smem_u32(myA);
-  uint32_t wcount[2] = {S.wcount[0], S.wcount[1]};
+  uint32_t wc0 = S.wcount[0], wc1 = S.wcount[1];  // scalars: a dynamically indexed array would live in local memory
   uint32_t mcount = S.mcount;
   if (t == 0) {  // both weight buffers are free here: fetch layers 0 and 1
     for (int b = 0; b < 2; ++b) {
@@ -343,8 +343,8 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
   for (int layer = 0; layer < kTcLayers; ++layer) {
     const int b = layer & 1;
     uint8_t *wbuf = sW + b * kBufBytes;
-    mbar_wait(wbar0 + 8 * b, wcount[b] & 1);
-    wcount[b] += 1;
+    mbar_wait(wbar0 + 8 * b, (b ? wc1 : wc0) & 1);
+    wc0 += b ? 0u : 1u, wc1 += b ? 1u : 0u;
     if (tile_live) {
     if (row == 0) {  // one thread per warpgroup issues the MMAs of its tile
       const uint32_t waddr = smem_u32(wbuf);
@@ -481,7 +481,7 @@ __device__ __forceinline__ void tc_forward(TcState &S, const uint8_t *__restrict
       bulk_g2s(smem_u32(wbuf), W + (size_t)(layer + 2) * kBufBytes, kBufBytes, wbar0 + 8 * b);
     }
   }
-  S.wcount[0] = wcount[0], S.wcount[1] = wcount[1];
+  S.wcount[0] = wc0, S.wcount[1] = wc1;
   S.mcount = mcount;
 }
 
