@@ -35,6 +35,9 @@ cdef extern from "corintho_b200.hpp":
         void writeSamples(float *game_states, float *eval_samples, float *prob_samples) except +
         void writeScores(string file) except +
         bool doIteration(float *evaluations, float *probabilities, int to_play) except +
+        # not in the reference: the network stays on the device (INTEGRATION.md section 3)
+        void setWeights(int model, const float *weights, size_t n_floats, int precision) except +
+        bool runSelfplay(int max_iterations, int stagger) except +
 
     cdef cppclass Tourney:
         Tourney(int num_threads, string log_folder) except +
@@ -96,6 +99,35 @@ def play_games(int num_games, str log_folder, int seed, int max_searches, int se
         if scores_file is not None:
             trainer.writeScores(str(scores_file).encode())
         n = trainer.num_samples()            # main.pyx:189-204
+        sample_states = np.zeros((max(n, 1) * _SYMMETRY_NUM, _GAME_STATE_SIZE), dtype=np.float32)
+        evaluation_labels = np.zeros(max(n, 1) * _SYMMETRY_NUM, dtype=np.float32)
+        probability_labels = np.zeros((max(n, 1) * _SYMMETRY_NUM, _NUM_MOVES), dtype=np.float32)
+        if n > 0:
+            trainer.writeSamples(&sample_states[0, 0], &evaluation_labels[0], &probability_labels[0, 0])
+        n *= _SYMMETRY_NUM
+        return (np.asarray(sample_states)[:n], np.asarray(evaluation_labels)[:n],
+                np.asarray(probability_labels)[:n], trainer.score(), trainer.avg_mate_length())
+    finally:
+        del trainer
+
+
+def play_games_fused(int num_games, str log_folder, int seed, int max_searches, int searches_per_eval,
+                     float c_puct, float epsilon, int num_logged, weights, int precision):
+    """play_games with the evaluation on the device: `weights` is the folded 127 997-float vector
+    (corintho_ai_b200.fold_batchnorm / tflite_import.load_tflite_weights), precision 0 fp32, 1 bf16,
+    2 fp16, 3 bf16x3. Same return value as play_games."""
+    cdef Trainer *trainer = new Trainer(num_games, log_folder.encode(), seed, max_searches, searches_per_eval,
+                                        c_puct, epsilon, num_logged, 1, False)
+    cdef float[::1] w = np.ascontiguousarray(weights, dtype=np.float32)
+    cdef int n
+    cdef float[:, ::1] sample_states
+    cdef float[::1] evaluation_labels
+    cdef float[:, ::1] probability_labels
+    try:
+        trainer.setWeights(0, &w[0], w.shape[0], precision)
+        while not trainer.runSelfplay(0, 1):
+            pass
+        n = trainer.num_samples()
         sample_states = np.zeros((max(n, 1) * _SYMMETRY_NUM, _GAME_STATE_SIZE), dtype=np.float32)
         evaluation_labels = np.zeros(max(n, 1) * _SYMMETRY_NUM, dtype=np.float32)
         probability_labels = np.zeros((max(n, 1) * _SYMMETRY_NUM, _NUM_MOVES), dtype=np.float32)

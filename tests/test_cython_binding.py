@@ -119,3 +119,20 @@ def test_run_tourney_through_cython_equals_oracle(cy, oracle, tmp_path):
                     if line.strip()])
     want = np.array(t.scores(), np.float64).reshape(-1, 3)
     assert got.shape == want.shape and (got == want).all()
+
+
+@pytest.mark.gpu
+def test_fused_selfplay_through_cython_equals_the_ctypes_mirror(cy):
+    """setWeights + runSelfplay of the C++ header (network on the device) vs corintho_ai_b200.Trainer."""
+    import corintho_ai_b200 as cb
+    w = cb.fold_batchnorm(cb.random_weights(3))
+    st, ev, pr, score, mate = cy.play_games_fused(96, "", 5, 64, 8, 1.0, 0.25, 0, w, 1)
+    t = cb.Trainer(96, "", 5, 64, 8, 1.0, 0.25, 0, 1, False)
+    t.set_weights(w, 0, "bf16")
+    while not t.run_selfplay(0, True):
+        pass
+    n = t.num_samples()
+    a, b, c = (np.zeros((n * 8, 70), np.float32), np.zeros(n * 8, np.float32), np.zeros((n * 8, 96), np.float32))
+    t.writeSamples(a, b, c)
+    assert st.shape[0] == n * 8 and _digest(st, ev, pr) == _digest(a, b, c)
+    assert np.float32(score).tobytes() == np.float32(t.score()).tobytes()
