@@ -233,6 +233,51 @@ def test_fused_selfplay_is_independent_of_parking_and_stream_groups(monkeypatch)
     assert default == base
 
 
+KNOB_SETS = [
+    {"CB200_MINBLOCKS": "4"}, {"CB200_MINBLOCKS": "5"}, {"CB200_MINBLOCKS": "7"}, {"CB200_MINBLOCKS": "8"},
+    {"CB200_NO_LIVE_LIST": "1"}, {"CB200_NO_OVERLAP": "1", "CB200_GROUPS": "3"},
+    {"CB200_PS_NO_REDEAL": "1"}, {"CB200_PS_REDEAL_PCT": "10", "CB200_PS_REDEAL_MIN": "4"},
+    {"CB200_PS_YIELD": "24", "CB200_PS_YIELD_MIN_LIVE": "1"}, {"CB200_PS_CAPACITY": "40"},
+    {"CB200_PS_CAPACITY": "2368"}, {"CB200_PS_CAPACITY": "2368", "CB200_PS_YIELD": "24", "CB200_PS_YIELD_MIN_LIVE": "1"},
+    {"CB200_GROUPS": "8", "CB200_YIELD": "30", "CB200_YIELD_MIN_LIVE": "16"},
+]
+
+
+def test_fused_selfplay_is_independent_of_every_other_knob(monkeypatch):
+    """DESIGN.md section 5's knob table: register budget of the game step, live lists, network CTA
+    form, persistent re-deal policy, persistent parking, take-over threshold -- none may change a
+    byte of the samples, the score or the exact counters (600 games: several stream groups, both
+    persistent kernel widths after the hand-over)."""
+    flat = cb.fold_batchnorm(cb.random_weights(21))
+    knobs = sorted({k for ks in KNOB_SETS for k in ks})
+
+    def run(env):
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        # lock-step loop until 100 games are left (the default would hand 600 games to the
+        # persistent kernels at once and leave the lock-step knobs untested), then the persistent tail
+        monkeypatch.setenv("CB200_PS_CAPACITY", "100")
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        t = cb.Trainer(600, "", 321, 64, 16, 1.0, 0.25)
+        t.set_weights(flat, 0, "bf16")
+        assert t.run_selfplay(0, stagger=False)
+        gs, ev, pr = t.write_samples()
+        c = t.counters()
+        return (gs.tobytes(), ev.tobytes(), pr.tobytes(), t.score().tobytes(),
+                (c["simulations"], c["moves"], c["leaf_evals"]))
+
+    base = run({})
+    t = cb.Trainer(600, "", 321, 64, 16, 1.0, 0.25)   # CB200_PS_CAPACITY=100 is still set: both loops run
+    t.set_weights(flat, 0, "bf16")
+    t.set_profiling(True)
+    assert t.run_selfplay(0, stagger=False)
+    kt = t.kernel_times()
+    assert kt["game_step"]["launches"] >= 20 and kt["fused_tail"]["launches"] >= 1
+    for env in KNOB_SETS:
+        assert run(env) == base, env
+
+
 def test_persistent_tail_equals_lock_step(monkeypatch):
     """Once the live games fit on the device at 8 per SM the run continues in one persistent
     kernel (game step + network per CTA). It must play exactly the games of the lock-step loop,
