@@ -35,8 +35,8 @@ FLOP_PER_EVAL = 253400.0         # unpadded dense FLOPs per leaf
 # (65 536 simulations = 109.4 MB algorithmic), from the `ncu --set full` capture summarised in
 # profiles/r02_ncu_k_iterate_lanes16_vs_32.txt; profiles/r01_ncu_k_iterate_k_mlp_tc_v3.txt gives
 # 1.36 MB for k_mlp_tc
-NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 146.333184e6 + 52.767232e6, "network": 1.356800e6 + 0.008960e6}
-NCU_SOURCE = "profiles/r02_ncu_k_iterate_lanes16_vs_32.txt, k_iterate<1, 32>"
+NCU_DRAM_BYTES_PER_DENSE_LAUNCH = {"game_step": 149.888000e6 + 59.357440e6, "network": 1.356032e6 + 0.000256e6}
+NCU_SOURCE = "profiles/r02_ncu_k_iterate_6ctas.txt, k_iterate<1, 32, 6>"
 
 
 def peaks():
@@ -465,7 +465,7 @@ def run_engine_arm(args, rank, world, local_rank):
     else:
         roof = hbm_roof("game_step", NCU_DRAM_BYTES_PER_DENSE_LAUNCH["game_step"])
     roof["traffic_note"] = ("dram__bytes of ONE game-step launch with every game live (ncu --set full, " + NCU_SOURCE +
-                            "): 199.1 MB for 109.4 MB algorithmic; `achieved` averages over all lock-step "
+                            "): 209.2 MB for 109.4 MB algorithmic; `achieved` averages over all lock-step "
                             "launches of the run, most of which carry fewer games")
     roof["peak_source"] = pk["source"]
     roof["measured_on"] = ("the timed schedule itself: %d stream groups, parking, persistent tail; CUDA-event pair per "
