@@ -1439,13 +1439,13 @@ static int ps_list_games(cb200_trainer *t) {
 }
 
 extern "C++" {
-template <bool kFp16, int kGames, int kL>
+template <int kMode, int kGames, int kL>
 static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit_done) {
   static bool attr_set[16] = {false};
   if (t->device < 16 && !attr_set[t->device]) {
-    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<kFp16, kGames, kL>,
+    CB_CUDA(cudaFuncSetAttribute(k_selfplay_persistent<kMode, kGames, kL>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ps_smem_bytes<kGames>()));
+                                 (int)ps_smem_bytes<kMode, kGames>()));
     attr_set[t->device] = true;
   }
   const float *ev0 = t->ps_from_lockstep ? t->d_eval : t->d_ps_eval[t->ps_cur];
@@ -1456,7 +1456,7 @@ static int ps_launch(cb200_trainer *t, const TreeParams &P, int rounds, int exit
   const int grid = t->ps_n < t->ps_ctas ? t->ps_n : t->ps_ctas;
   // two-model (gating match) runs: model 1 answers the other side's requests
   const uint8_t *w1 = P.testing ? (const uint8_t *)t->nettc[1].w : nullptr;
-  k_selfplay_persistent<kFp16, kGames, kL><<<grid, kGames * kL, ps_smem_bytes<kGames>(), t->g_stream[0]>>>(
+  k_selfplay_persistent<kMode, kGames, kL><<<grid, kGames * kL, ps_smem_bytes<kMode, kGames>(), t->g_stream[0]>>>(
       P, (const uint8_t *)t->nettc[0].w, w1, t->d_ps_list, t->ps_n, ev0, pr0, pcs0, t->d_ps_eval[nxt],
       t->d_ps_probs[nxt], t->ps_ld, t->d_ps_packed, rounds, exit_done, t->iterations_done,
       t->d_ps_out);
@@ -1535,7 +1535,10 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
     int exit_done = t->ps_n > redeal_min ? (int)((long long)t->ps_n * redeal_pct / 100) : 0x7fffffff;
     if (exit_done < 1) exit_done = 1;
     if (getenv("CB200_PS_NO_REDEAL")) exit_done = 0x7fffffff;
+    const int mode = t->nettc[0].mode;  // 0 bf16, 1 fp16, 2 bf16x3 (8 games per CTA only: shared memory)
     const bool wide = t->ps_n > t->ps_ctas * 8;
+    if (wide && mode == 2)
+      return set_error(CB200_ERR_STATE, "persistent kernel: bf16x3 networks run at most 8 games per SM");
     CB_CUDA(cudaMemsetAsync(t->d_ps_out, 0, 4 * sizeof(int32_t), st));
     int rc;
     {
@@ -1543,16 +1546,18 @@ static int run_persistent(cb200_trainer *t, int max_rounds, int *rounds_done, bo
       // lanes per game: one warp (the default: the tail is bound by the serial chain of a game,
       // which is shortest with 32 lanes) or 16 (CB200_PS_LANES=16)
       const bool half = t->ps_lanes == 16;
-      if (t->nettc[0].fp16)
-        rc = wide ? (half ? ps_launch<true, 16, 16>(t, P, rounds, exit_done)
-                          : ps_launch<true, 16, 32>(t, P, rounds, exit_done))
-                  : (half ? ps_launch<true, 8, 16>(t, P, rounds, exit_done)
-                          : ps_launch<true, 8, 32>(t, P, rounds, exit_done));
+      if (mode == 2)
+        rc = half ? ps_launch<2, 8, 16>(t, P, rounds, exit_done) : ps_launch<2, 8, 32>(t, P, rounds, exit_done);
+      else if (mode == 1)
+        rc = wide ? (half ? ps_launch<1, 16, 16>(t, P, rounds, exit_done)
+                          : ps_launch<1, 16, 32>(t, P, rounds, exit_done))
+                  : (half ? ps_launch<1, 8, 16>(t, P, rounds, exit_done)
+                          : ps_launch<1, 8, 32>(t, P, rounds, exit_done));
       else
-        rc = wide ? (half ? ps_launch<false, 16, 16>(t, P, rounds, exit_done)
-                          : ps_launch<false, 16, 32>(t, P, rounds, exit_done))
-                  : (half ? ps_launch<false, 8, 16>(t, P, rounds, exit_done)
-                          : ps_launch<false, 8, 32>(t, P, rounds, exit_done));
+        rc = wide ? (half ? ps_launch<0, 16, 16>(t, P, rounds, exit_done)
+                          : ps_launch<0, 16, 32>(t, P, rounds, exit_done))
+                  : (half ? ps_launch<0, 8, 16>(t, P, rounds, exit_done)
+                          : ps_launch<0, 8, 32>(t, P, rounds, exit_done));
     }
     if (rc != CB200_OK) return rc;
     CB_CUDA(cudaMemcpyAsync(t->h_ps_out, t->d_ps_out, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1608,17 +1613,18 @@ static int run_selfplay_groups(cb200_trainer *t, int max_iterations) {
   if (const char *e = getenv("CB200_YIELD_MIN_LIVE")) yield_min_live = atoi(e);
   // Persistent tail: once every live game fits on the device at 16 games per SM (and all games
   // have started), the rest of the run happens inside persistent kernels (persistent.cuh).
-  // (bf16x3 networks need 210 KB of shared memory: they stay in the lock-step loop)
-  const bool ps_ok = tc && t->nettc[model].mode != 2 && t->P.spe <= kPsRowsPerGame && !getenv("CB200_NO_PERSISTENT");
-  long long ps_capacity = (long long)t->ps_ctas * 16;
+  // (bf16x3 networks hold hi and lo operand copies in shared memory: 8 games per SM, not 16)
+  const bool ps_ok = tc && t->P.spe <= kPsRowsPerGame && !getenv("CB200_NO_PERSISTENT");
+  const long long ps_max = (long long)t->ps_ctas * (t->nettc[model].mode == 2 ? 8 : 16);
+  long long ps_capacity = ps_max;
   if (const char *e = getenv("CB200_PS_CAPACITY")) ps_capacity = atoll(e);
-  if (ps_capacity > (long long)t->ps_ctas * 16) ps_capacity = (long long)t->ps_ctas * 16;
+  if (ps_capacity > ps_max) ps_capacity = ps_max;
   const int stagger_span =
       t->stagger_div > 0 ? (t->P.first_game + t->P.num_games - 1) / t->stagger_div : 0;
   // With several stream groups the game step runs in its 96-register build (four CTAs leave
   // 16 K registers per SM) and the network in single-tile CTAs of 128 threads that fit beside
   // them, so that one group's network overlaps the other groups' tree work (2-3 % per run).
-  const bool overlap = tc && t->nettc[model].mode != 2 && ng > 1 && getenv("CB200_NO_OVERLAP") == nullptr;
+  const bool overlap = tc && ng > 1 && getenv("CB200_NO_OVERLAP") == nullptr;
   const bool use_lists = getenv("CB200_NO_LIVE_LIST") == nullptr;
   std::vector<int> group_live(ng, -1);  // live games per group at the last host sync (-1 = unknown)
   while (max_iterations <= 0 || done_iters < max_iterations) {
@@ -1787,8 +1793,8 @@ int cb200_trainer_run_selfplay(cb200_trainer *t, int max_iterations, int stagger
   // and every game resident at <= 16 per SM, the whole match runs in the persistent kernel
   // (persistent.cuh; each game's requests go to the row region of the model that owns its side).
   if ((t->iterations_done == 0 || t->ps_active) && t->precision[0] == 1 && t->precision[1] == 1 &&
-      t->nettc[0].mode == t->nettc[1].mode && t->nettc[0].mode != 2 && t->P.spe <= kPsRowsPerGame &&
-      t->P.num_games <= t->ps_ctas * 16 && !getenv("CB200_NO_PERSISTENT")) {
+      t->nettc[0].mode == t->nettc[1].mode && t->P.spe <= kPsRowsPerGame &&
+      t->P.num_games <= t->ps_ctas * (t->nettc[0].mode == 2 ? 8 : 16) && !getenv("CB200_NO_PERSISTENT")) {
     CB_CUDA(cudaStreamSynchronize(cur_stream()));
     if (!t->ps_active) {
       if ((rc = ps_list_games(t)) != CB200_OK) return rc;

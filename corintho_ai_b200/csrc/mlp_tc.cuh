@@ -49,9 +49,13 @@ constexpr int kTcLayerBytes = kTcWBytes;                 // 25088 (bias folded i
 constexpr int kTcOnes = 100;                             // activation columns 100,101 == 1
 constexpr int kTcThreads = 256;
 constexpr int kTcTmemCols = 256;                         // 2 tiles x 128 columns
-constexpr size_t kTcSmemBytes = 2 * kTcABytes + 2 * kTcLayerBytes + 64;
-// bf16x3: hi and lo copies of both activation tiles and of both weight buffers
-constexpr size_t kTcSmemBytesX3 = 2 * (2 * kTcABytes + 2 * kTcLayerBytes) + 64;
+// shared memory of a network CTA: `tiles` activation tiles (128 positions each) and two weight
+// buffers, everything in `parts` copies (bf16x3: hi and lo), four mbarriers, the TMEM slot
+__host__ __device__ constexpr size_t tc_smem_bytes(int tiles, int parts) {
+  return (size_t)tiles * parts * kTcABytes + 2 * (size_t)parts * kTcLayerBytes + 64;
+}
+constexpr size_t kTcSmemBytes = tc_smem_bytes(2, 1);    // 107 584
+constexpr size_t kTcSmemBytesX3 = tc_smem_bytes(2, 2);  // 215 104
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32 (bits 4-5 = 1),
 // A=B=BF16 (bits 7-9, 10-12 = 1), both K-major, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kTcIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTcN >> 3) << 17) |
@@ -243,8 +247,9 @@ __device__ __forceinline__ void tc_setup(TcState &S, uint8_t *smem, int nthreads
   S.nthreads = nthreads;
   S.parts = parts;
   S.tmem_cols = nthreads == kTcThreads ? kTcTmemCols : kTcTmemCols / 2;
-  S.sA = smem;                                 // 2 tiles x parts x kTcABytes
-  S.sW = smem + 2 * parts * kTcABytes;         // 2 buffers x parts x kTcLayerBytes
+  const int tiles = nthreads / 128;
+  S.sA = smem;                                 // tiles x parts x kTcABytes
+  S.sW = smem + tiles * parts * kTcABytes;     // 2 buffers x parts x kTcLayerBytes
   uint64_t *bars = reinterpret_cast<uint64_t *>(S.sW + 2 * parts * kTcLayerBytes);  // wbar[2], mbar[2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
   const int t = threadIdx.x, warp = t >> 5;
@@ -501,10 +506,11 @@ __global__ void __launch_bounds__(kTcThreads, kMode == 2 ? 1 : 2)
   tc_teardown(S);
 }
 
-// One tile per CTA (128 threads, 16 K registers): small enough to share an SM with four 96-register
-// game-step CTAs, so that one stream group's network overlaps the other groups' tree work.
-template <bool kFp16>
-__global__ void __launch_bounds__(128, 4)
+// One tile per CTA (128 threads; bf16 / fp16: 13 K registers and 77 KB of shared memory): small enough
+// to share an SM with five 80-register game-step CTAs, so that one stream group's network overlaps
+// the other groups' tree work. bf16x3: 154 KB, beside two game-step CTAs.
+template <int kMode>
+__global__ void __maxnreg__(kMode == 2 ? 168 : 104)
     k_mlp_tc1(const uint8_t *__restrict__ W, const ulonglong2 *__restrict__ states,
               const int32_t *__restrict__ n_ptr, int n_static, float *__restrict__ eval,
               float *__restrict__ probs, int probs_ld, int32_t *__restrict__ zero2) {
@@ -512,11 +518,10 @@ __global__ void __launch_bounds__(128, 4)
   const int n = n_ptr ? *n_ptr : n_static;
   if (zero2 && blockIdx.x == 0 && threadIdx.x == 0) zero2[0] = 0, zero2[2] = 0;
   TcState S;
-  tc_setup(S, smem, 128);
+  tc_setup(S, smem, 128, kMode == 2 ? 2 : 1);
   for (int tile = blockIdx.x; tile * 128 < n; tile += gridDim.x) {
     const int rows = n - tile * 128 < 128 ? n - tile * 128 : 128;
-    tc_forward<kFp16 ? 1 : 0>(S, W, states + tile * 128, rows, 0, eval + tile * 128, probs + tile * 128,
-                              probs_ld);
+    tc_forward<kMode>(S, W, states + tile * 128, rows, 0, eval + tile * 128, probs + tile * 128, probs_ld);
   }
   tc_teardown(S);
 }
@@ -606,7 +611,7 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   }
   if (n_max <= 0) return CB200_OK;
   cudaStream_t st = use_stream ? stream : cur_stream();
-  if (net.mode == 2) {  // bf16x3: 210 KB of shared memory, one CTA per SM
+  if (net.mode == 2 && !single_tile) {  // bf16x3, two tiles: 210 KB of shared memory, one CTA per SM
     const int pairs = (n_max + 255) / 256;
     k_mlp_tc<2><<<pairs < sms ? pairs : sms, kTcThreads, kTcSmemBytesX3, st>>>(
         (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
@@ -617,19 +622,24 @@ inline int launch_mlp_tc(const NetTC &net, const ulonglong2 *d_states, const int
   if (single_tile) {
     static bool attr1[16] = {false};
     if (dev < 16 && !attr1[dev]) {
-      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kTcSmemBytes));
-      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kTcSmemBytes));
+      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)tc_smem_bytes(1, 1)));
+      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)tc_smem_bytes(1, 1)));
+      CB_CUDA(cudaFuncSetAttribute(k_mlp_tc1<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)tc_smem_bytes(1, 2)));
       attr1[dev] = true;
     }
     const int tiles = (n_max + 127) / 128;
     const int g1 = tiles < sms ? tiles : sms;
-    if (net.fp16)
-      k_mlp_tc1<true><<<g1, 128, kTcSmemBytes, st>>>(
+    if (net.mode == 2)
+      k_mlp_tc1<2><<<g1, 128, tc_smem_bytes(1, 2), st>>>(
+          (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
+    else if (net.fp16)
+      k_mlp_tc1<1><<<g1, 128, tc_smem_bytes(1, 1), st>>>(
           (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
     else
-      k_mlp_tc1<false><<<g1, 128, kTcSmemBytes, st>>>(
+      k_mlp_tc1<0><<<g1, 128, tc_smem_bytes(1, 1), st>>>(
           (const uint8_t *)net.w, d_states, d_n, n_static, d_eval, d_probs, probs_ld, zero2);
     CB_LAUNCHED();
     CB_CUDA(cudaGetLastError());

@@ -18,11 +18,16 @@
 namespace cb200 {
 
 constexpr int kPsRowsPerGame = 16;           // request rows reserved per game (needs spe <= 16)
-template <int kGames>
-constexpr size_t ps_smem_bytes() {
-  return (kTcSmemBytes + 127) / 128 * 128 + kGames * sizeof(WarpSm);
+// shared memory of a persistent CTA: the network's (one tile for 8 games, two for 16; bf16x3 holds
+// hi and lo copies and fits with 8 games only), then one WarpSm per game
+template <int kMode, int kGames>
+__host__ __device__ constexpr size_t ps_tree_smem_off() {
+  return (tc_smem_bytes(kGames == 8 ? 1 : 2, kMode == 2 ? 2 : 1) + 127) / 128 * 128;
 }
-constexpr size_t kPsTreeSmemOff = (kTcSmemBytes + 127) / 128 * 128;
+template <int kMode, int kGames>
+__host__ __device__ constexpr size_t ps_smem_bytes() {
+  return ps_tree_smem_off<kMode, kGames>() + kGames * sizeof(WarpSm);
+}
 
 // live games in ascending index order: one warp, 32 flags per trip, ballot-ordered append
 __global__ void k_live_list(TreeParams P, int32_t *__restrict__ list, int32_t *__restrict__ count) {
@@ -47,7 +52,7 @@ __global__ void k_live_list(TreeParams P, int32_t *__restrict__ list, int32_t *_
 // this launch have finished (the host then deals the remaining games again). out[0] += games still
 // live when the CTA stopped, out[1] = min error code, out[2] = max rounds executed by a CTA,
 // out[3] = games finished during the launch.
-template <bool kFp16, int kGames, int kL>
+template <int kMode, int kGames, int kL>
 __global__ void __launch_bounds__(kGames * kL, 1)
     k_selfplay_persistent(TreeParams P, const uint8_t *__restrict__ W,
                           const uint8_t *__restrict__ W1, const int32_t *__restrict__ game_list,
@@ -55,6 +60,7 @@ __global__ void __launch_bounds__(kGames * kL, 1)
                           float *eval, float *probs, int ld, ulonglong2 *packed, int max_rounds,
                           int exit_done, int iteration0, int32_t *out) {
   static_assert(kGames == 8 || kGames == 16, "one or two network tiles per CTA");
+  static_assert(ps_smem_bytes<kMode, kGames>() <= 227 * 1024, "bf16x3 fits with 8 games per CTA only");
   constexpr int kNetThreads = kGames == 8 ? 128 : kTcThreads;  // one tile or two
   static_assert(kGames * kL >= kNetThreads, "too few threads for the network");
   const bool net_thread = threadIdx.x < kNetThreads;
@@ -65,8 +71,8 @@ __global__ void __launch_bounds__(kGames * kL, 1)
   __shared__ int32_t s_ctr[8];
   const bool two = W1 != nullptr;
   TcState S;
-  if (net_thread) tc_setup(S, smem, kNetThreads);
-  WarpSm *sm_all = reinterpret_cast<WarpSm *>(smem + kPsTreeSmemOff);
+  if (net_thread) tc_setup(S, smem, kNetThreads, kMode == 2 ? 2 : 1);
+  WarpSm *sm_all = reinterpret_cast<WarpSm *>(smem + ps_tree_smem_off<kMode, kGames>());
   const int grp = threadIdx.x / kL;
   const int slot = grp * gridDim.x + blockIdx.x;
   const int g = slot < n_list ? game_list[slot] : -1;
@@ -97,10 +103,9 @@ __global__ void __launch_bounds__(kGames * kL, 1)
     // every round ends with the network, so the answers of all queued requests are in the
     // CTA's rows whenever the kernel stops (a later launch continues from there)
     if (net_thread && n > 0)
-      tc_forward<kFp16 ? 1 : 0>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
+      tc_forward<kMode>(S, W, packed + row0, n, 0, eval + row0, probs + row0, ld);
     if (net_thread && n1 > 0)
-      tc_forward<kFp16 ? 1 : 0>(S, W1, packed + row0 + kRows, n1, 0, eval + row0 + kRows,
-                        probs + row0 + kRows, ld);
+      tc_forward<kMode>(S, W1, packed + row0 + kRows, n1, 0, eval + row0 + kRows, probs + row0 + kRows, ld);
     __syncthreads();  // answers visible to every warp; counters read before they are cleared
     if (live == 0 || s_ctr[3]) {
       ++round;

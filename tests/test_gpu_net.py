@@ -460,3 +460,31 @@ def test_fused_selfplay_bf16x3_equals_oracle_driven_by_the_same_network(oracle):
     assert gs.tobytes() == r["samples"][0].tobytes()
     assert ev.tobytes() == r["samples"][1].tobytes()
     assert pr.tobytes() == r["samples"][2].tobytes()
+
+
+@pytest.mark.parametrize("testing", [False, True])
+def test_bf16x3_persistent_tail_equals_lock_step(monkeypatch, testing):
+    """bf16x3 networks (hi + lo operand copies: 154 KB of shared memory for one tile) run the persistent
+    kernel at 8 games per CTA; one- and two-model runs must equal the lock-step loop byte for byte."""
+    w0, w1 = cb.fold_batchnorm(cb.random_weights(41)), cb.fold_batchnorm(cb.random_weights(42))
+
+    def run():
+        t = cb.Trainer(200, "", 17, 64, 16, 1.0, 0.0 if testing else 0.25, 0, 1, testing)
+        t.set_weights(w0, 0, "bf16x3")
+        if testing:
+            t.set_weights(w1, 1, "bf16x3")
+        t.set_profiling(True)
+        assert t.run_selfplay(0, stagger=False)
+        c = t.counters()
+        r = (t.score().tobytes(), t.avg_mate_length().tobytes(), (c["simulations"], c["moves"], c["leaf_evals"]))
+        if not testing:
+            r += tuple(a.tobytes() for a in t.write_samples())
+        return r, t.kernel_times()
+
+    monkeypatch.setenv("CB200_NO_PERSISTENT", "1")
+    base, kt0 = run()
+    assert kt0["fused_tail"]["launches"] == 0
+    monkeypatch.delenv("CB200_NO_PERSISTENT")
+    got, kt1 = run()
+    assert kt1["fused_tail"]["launches"] >= 1
+    assert got == base
