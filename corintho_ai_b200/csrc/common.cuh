@@ -59,6 +59,9 @@ inline void set_cur_stream(cudaStream_t s) { G().stream_of[cur_device_slot()] = 
 __device__ __align__(16) uint32_t d_line_breakers[103 * 4];  // entry 102 = all ones (no line)
 __device__ float d_gamma[1024];
 __device__ uint32_t d_inv32[128];  // floor(2^32 / d) for d = 1..127 ([0] unused; [1] = 2^32 - 1)
+// K1 fast path (rules.cuh: build_move_lut / build_nth_lut); copied to shared memory by the kernel
+__device__ __align__(16) uint32_t d_move_lut[96 * kMoveLutWords];
+__device__ __align__(16) uint8_t d_nth_lut[256 * 8];
 
 struct DeviceLB {
   __device__ __forceinline__ const uint32_t *operator()(int idx) const {
@@ -82,6 +85,11 @@ inline int ensure_tables() {
   inv[0] = 0, inv[1] = 0xFFFFFFFFu;
   for (uint32_t d = 2; d < 128; ++d) inv[d] = (uint32_t)(0x100000000ull / d);
   CB_CUDA(cudaMemcpyToSymbol(d_inv32, inv, sizeof(inv)));
+  static uint32_t mv[96 * kMoveLutWords];
+  static uint8_t nth[256 * 8];
+  build_move_lut(mv), build_nth_lut(nth);
+  CB_CUDA(cudaMemcpyToSymbol(d_move_lut, mv, sizeof(mv)));
+  CB_CUDA(cudaMemcpyToSymbol(d_nth_lut, nth, sizeof(nth)));
   if (dev < 16) G().tables_ready[dev] = true;
   return CB200_OK;
 }

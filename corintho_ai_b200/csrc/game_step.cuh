@@ -17,11 +17,13 @@ __global__ void __launch_bounds__(kStepThreads)
                 uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next,
                 float *__restrict__ enc) {
   __shared__ ulonglong2 sm_states[kEncode ? kStepThreads : 1];
-  // 32-bit indices: the launcher refuses more than 2^31 - 2^20 states per call
-  const int stride = (int)gridDim.x * kStepThreads;
+  // 32-bit indices: the launcher refuses more than 2^31 - 2^20 states per call; the loop counter
+  // is unsigned so that the last `+= stride` cannot wrap
+  const unsigned stride = gridDim.x * kStepThreads;
   // every warp runs the same number of trips so the cooperative encode stays convergent
-  const int n_round = (int)(((n + 31) / 32) * 32);
-  for (int i = (int)blockIdx.x * kStepThreads + threadIdx.x; i < n_round; i += stride) {
+  const unsigned n_round = (unsigned)(((n + 31) / 32) * 32);
+  for (unsigned iu = blockIdx.x * kStepThreads + threadIdx.x; iu < n_round; iu += stride) {
+    const int i = (int)iu;
     const bool live = i < n;
     CState s{0, 0};
     if (live) {
@@ -103,10 +105,10 @@ __global__ void __launch_bounds__(kStepThreads)
   const int tid = threadIdx.x;
   if (tid == 0) q_n = 0;
   __syncthreads();
-  const int stride = (int)gridDim.x * kStepThreads;
-  const int n_round = (int)(((n + kStepThreads - 1) / kStepThreads) * kStepThreads);  // uniform trip count per CTA
-  for (int base = (int)blockIdx.x * kStepThreads; base < n_round; base += stride) {
-    const int i = base + tid;
+  const unsigned stride = gridDim.x * kStepThreads;  // unsigned: the last `+= stride` cannot wrap
+  const unsigned n_round = (unsigned)(((n + kStepThreads - 1) / kStepThreads) * kStepThreads);  // uniform trip count per CTA
+  for (unsigned base = blockIdx.x * kStepThreads; base < n_round; base += stride) {
+    const int i = (int)(base + tid);
     if (i < n) {
       const ulonglong2 v = __ldg(states + i);
       const CState s{v.x, v.y};
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(kStepThreads)
     }
     __syncthreads();
     const int qn = q_n;
+    __syncthreads();  // every thread has read the count before the next trip's appends change it
     if (qn >= kStepThreads) {  // CTA-uniform: one queued position per thread
       const int e = qn - kStepThreads + tid;
       const ulonglong2 v = q_state[e];
@@ -141,6 +144,128 @@ __global__ void __launch_bounds__(kStepThreads)
     const bool lines = legal_moves_t<false>(s, m, DeviceLB());
     game_step_finish(q_idx[e], s, m, lines, seed, mask_flags, next);
   }
+}
+
+// K1, paired form (the default without encoding). The split idea above, with the integer-ALU
+// work per position cut further (the ALU pipe is what bounds K1):
+//   * a thread takes TWO positions per trip (i and i + 256: both loads and all stores stay
+//     coalesced) and runs the basic-rule mask and the "any line?" test on both at once, one
+//     position in each 16-bit half of every plane register (basic_moves_pair);
+//   * nth_move's last three levels and do_move's move decode are shared-memory tables
+//     (nth_move_lut / do_move_lut, 4.3 KB per CTA);
+//   * terminal positions (no legal move) skip the move instead of computing and discarding it.
+// Positions with a line are queued as in the split kernel and processed 256 at a time.
+struct SmemNthLut {
+  const uint8_t *p;
+  __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
+};
+
+// seed_c = seed + 0x9E3779B97F4A7C15 (computed once per thread): step_rnd's first line as one
+// multiply-add
+__device__ __forceinline__ void game_step_finish_lut(int i, const CState &s, const uint32_t m[3], bool lines,
+                                                     uint64_t seed_c, uint4 *__restrict__ mask_flags,
+                                                     ulonglong2 *__restrict__ next, const uint32_t *ML, SmemNthLut NL) {
+  const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
+  const uint32_t rnd = step_rnd_mix(seed_c + (uint64_t)(uint32_t)i * 0x9E3779B97F4A7C15ull);
+  const uint32_t dv = (uint32_t)max(nl, 1);
+  uint32_t rem = rnd - __umulhi(rnd, __ldg(d_inv32 + dv)) * dv;
+  rem -= rem >= dv ? dv : 0u;
+  CState o = s;
+  uint32_t tail = (lines ? (uint32_t)kResultLoss | 4u : (uint32_t)kResultDraw) | (0x7fu << 16);  // no legal move
+  if (nl > 0) {
+    const int pick = nth_move_lut(m, (int)rem, NL);
+    o = do_move_lut(s, pick, ML);
+    tail = (lines ? 4u : 0u) | ((uint32_t)nl << 8) | ((uint32_t)pick << 16);
+  }
+  mask_flags[i] = make_uint4(m[0], m[1], m[2], tail);
+  next[i] = make_ulonglong2(o.w0, o.w1);
+}
+
+__global__ void __launch_bounds__(kStepThreads)
+    k_game_step_pair(int64_t n, const ulonglong2 *__restrict__ states, uint64_t seed,
+                     uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next) {
+  constexpr int kQueue = 3 * kStepThreads;  // fewer than 256 entries before a trip, at most 512 more
+  __shared__ ulonglong2 q_state[kQueue];
+  __shared__ uint4 q_mask[kQueue];  // basic-rule mask (x, y, z) and the position's index (w)
+  __shared__ int q_n;
+  __shared__ __align__(16) uint32_t s_move[96 * kMoveLutWords];
+  __shared__ __align__(16) uint8_t s_nth[256 * 8];
+  const int tid = threadIdx.x;
+  reinterpret_cast<uint2 *>(s_nth)[tid] = reinterpret_cast<const uint2 *>(d_nth_lut)[tid];
+  if (tid < 96 * kMoveLutWords / 4)
+    reinterpret_cast<uint4 *>(s_move)[tid] = reinterpret_cast<const uint4 *>(d_move_lut)[tid];
+  if (tid == 0) q_n = 0;
+  __syncthreads();
+  const uint32_t *ML = s_move;
+  const SmemNthLut NL{s_nth};
+  const uint64_t seed_c = seed + 0x9E3779B97F4A7C15ull;
+  constexpr int kTrip = 2 * kStepThreads;
+  const unsigned stride = gridDim.x * kTrip;  // unsigned: the last `+= stride` cannot wrap
+  const unsigned n_round = (unsigned)(((n + kTrip - 1) / kTrip) * kTrip);  // uniform trip count per CTA
+  for (unsigned base = blockIdx.x * kTrip; base < n_round; base += stride) {
+    const unsigned ua = base + tid, ub = ua + kStepThreads;
+    if (ua < (unsigned)n) {
+      const bool hb = ub < (unsigned)n;
+      const int ia = (int)ua, ib = (int)ub;
+      const ulonglong2 va = __ldg(states + ia);
+      const ulonglong2 vb = hb ? __ldg(states + ib) : va;
+      const CState a{va.x, va.y}, b{vb.x, vb.y};
+      uint32_t ma[3], mb[3];
+      bool la, lb;
+      basic_moves_pair(a, b, ma, mb, la, lb);
+      if (!la) {
+        game_step_finish_lut(ia, a, ma, false, seed_c, mask_flags, next, ML, NL);
+      } else {
+        const int slot = atomicAdd(&q_n, 1);
+        q_state[slot] = va, q_mask[slot] = make_uint4(ma[0], ma[1], ma[2], (uint32_t)ia);
+      }
+      if (hb) {
+        if (!lb) {
+          game_step_finish_lut(ib, b, mb, false, seed_c, mask_flags, next, ML, NL);
+        } else {
+          const int slot = atomicAdd(&q_n, 1);
+          q_state[slot] = vb, q_mask[slot] = make_uint4(mb[0], mb[1], mb[2], (uint32_t)ib);
+        }
+      }
+    }
+    __syncthreads();
+    int qn = q_n;
+    __syncthreads();  // every thread has read the count before the next appends change it
+    if (qn >= kStepThreads) {  // CTA-uniform
+      do {
+        const int e = qn - kStepThreads + tid;
+        const ulonglong2 v = q_state[e];
+        const uint4 qm = q_mask[e];
+        const CState s{v.x, v.y};
+        uint32_t m[3] = {qm.x, qm.y, qm.z};
+        const bool lines = line_rules_on_basic(s, m, DeviceLB());
+        game_step_finish_lut((int)qm.w, s, m, lines, seed_c, mask_flags, next, ML, NL);
+        qn -= kStepThreads;
+      } while (qn >= kStepThreads);
+      __syncthreads();
+      if (tid == 0) q_n = qn;
+      __syncthreads();
+    }
+  }
+  for (int e = tid; e < q_n; e += kStepThreads) {  // drain
+    const ulonglong2 v = q_state[e];
+    const uint4 qm = q_mask[e];
+    const CState s{v.x, v.y};
+    uint32_t m[3] = {qm.x, qm.y, qm.z};
+    const bool lines = line_rules_on_basic(s, m, DeviceLB());
+    game_step_finish_lut((int)qm.w, s, m, lines, seed_c, mask_flags, next, ML, NL);
+  }
+}
+
+// resident CTAs of the paired kernel per SM (register- and shared-memory-limited), asked once
+inline int k1_pair_ctas_per_sm() {
+  static int ctas = 0;
+  if (ctas == 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_game_step_pair, kStepThreads, 0) != cudaSuccess || v < 1) v = 4;
+    ctas = v;
+  }
+  return ctas;
 }
 
 inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void *d_mask_flags,
@@ -164,9 +289,15 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
     k_game_step<false><<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next,
         nullptr);
-  else
+  else if (getenv("CB200_K1_SPLIT"))  // one position per thread (the form before the paired kernel)
     k_game_step_split<<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
+  else {
+    const int64_t want2 = (n + 2 * kStepThreads - 1) / (2 * kStepThreads);
+    const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm() * 4;
+    k_game_step_pair<<<(int)(want2 < cap2 ? want2 : cap2), kStepThreads, 0, cur_stream()>>>(
+        n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
+  }
   CB_LAUNCHED();
   CB_CUDA(cudaGetLastError());
   return CB200_OK;

@@ -114,89 +114,21 @@ CB_HD bool legal_moves_t(const CState &st, uint32_t m[3], LBFn LB) {
   uint32_t m2 = pc | (pa << 16);
   bool lines = false;
 
-  // ---- row lines (game.cpp:249-315, isCol=false): first row with a line, long > {0,1,2} > {1,2,3}
-  {
-    const uint32_t W0 = T0 & (T0 >> 1) & (T0 >> 2), W1 = T1 & (T1 >> 1) & (T1 >> 2),
-                   W2 = T2 & (T2 >> 1) & (T2 >> 2);
-    const uint32_t any1 = (W1 | (W1 >> 1)) & 0x1111u, any2 = (W2 | (W2 >> 1)) & 0x1111u;
-    const uint32_t Wa = W0 | W1 | W2;
-    const uint32_t left = Wa & 0x1111u, right = (Wa >> 1) & 0x1111u;
-    const uint32_t any = left | right;
-    if (kBranchless || any) {
-      const bool has = any != 0;
-      lines |= has;
-      const int i4 = has ? cb_ffs(any) - 1 : 0, i = i4 >> 2;
-      const int t = (int)((any1 >> i4) & 1u) + 2 * (int)((any2 >> i4) & 1u);
-      const bool l = (left >> i4) & 1u, r = (right >> i4) & 1u;
-      const int cat = (l && r) ? 2 : (l ? 0 : 1);  // RB, RL, RR (util.h:67-69)
-      lb_and(LB, has ? cat * 12 + i * 3 + t : 102, m0, m1, m2);
-      if (has && t == 2 && cat != 2) {  // capital fix-ups (game.cpp:280-309), column `e`
-        const int e = l ? 3 : 0;
-        const uint32_t colm = 0x111u << e;
-        m0 &= ~(colm << 12) | ((A & colm) << 12);        // down moves from (k,e), k=0..2
-        m1 &= ~(colm << 4) | (((A >> 4) & colm) << 4);   // up moves from (k,e), k=1..3
-      }
-    }
-  }
-  // ---- column lines (isCol=true): first column, long > rows{0,1,2} > rows{1,2,3}
-  {
-    const uint32_t W0 = T0 & (T0 >> 4) & (T0 >> 8), W1 = T1 & (T1 >> 4) & (T1 >> 8),
-                   W2 = T2 & (T2 >> 4) & (T2 >> 8);
-    const uint32_t any1 = (W1 | (W1 >> 4)) & 0xFu, any2 = (W2 | (W2 >> 4)) & 0xFu;
-    const uint32_t Wa = W0 | W1 | W2;
-    const uint32_t upper = Wa & 0xFu, lower = (Wa >> 4) & 0xFu;
-    const uint32_t any = upper | lower;
-    if (kBranchless || any) {
-      const bool has = any != 0;
-      lines |= has;
-      const int i = has ? cb_ffs(any) - 1 : 0;
-      const int t = (int)((any1 >> i) & 1u) + 2 * (int)((any2 >> i) & 1u);
-      const bool u = (upper >> i) & 1u, d = (lower >> i) & 1u;
-      const int cat = (u && d) ? 5 : (u ? 3 : 4);  // CB, CU, CD (util.h:70-72)
-      lb_and(LB, has ? cat * 12 + i * 3 + t : 102, m0, m1, m2);
-      if (has && t == 2 && cat != 5) {  // capital fix-ups along row `e`
-        const int e = u ? 3 : 0;
-        const uint32_t Arow = (A >> (4 * e)) & 0xFu;
-        const uint32_t rowm = 7u << (3 * e);
-        const uint32_t keepR = ~rowm | ((Arow & 7u) << (3 * e));         // right moves from (e,k)
-        const uint32_t keepL = ~rowm | (((Arow >> 1) & 7u) << (3 * e));  // left moves from (e,k)
-        m0 &= (keepR | ~0xFFFu) & ((keepL << 24) | 0x00FFFFFFu);
-        m1 &= ((keepL & 0xFFFu) >> 8) | ~0xFu;
-      }
-    }
-  }
-  // ---- diagonals. Three equal tops with square step 5 (bases 0,5 = main diagonal upper/lower,
-  // 1 = S1, 4 = S3) or step 3 (bases 3,6 = anti-diagonal upper/lower, 2 = S0, 7 = S2).
-  {
-    const uint32_t A5 = T0 & (T0 >> 5) & (T0 >> 10), B5 = T1 & (T1 >> 5) & (T1 >> 10),
-                   C5 = T2 & (T2 >> 5) & (T2 >> 10);
-    const uint32_t A3 = T0 & (T0 >> 3) & (T0 >> 6), B3 = T1 & (T1 >> 3) & (T1 >> 6),
-                   C3 = T2 & (T2 >> 3) & (T2 >> 6);
-    const uint32_t D5 = (A5 | B5 | C5) & 0x33u, D3 = (A3 | B3 | C3) & 0xCCu;
-    if (kBranchless || (D5 | D3)) {
-      // long diagonals (game.cpp:317-360): main then anti; long > upper > lower
-      const bool mu5 = D5 & 0x01u, ml5 = D5 & 0x20u, au3 = D3 & 0x08u, al3 = D3 & 0x40u;
-      const bool mainl = mu5 || ml5, antil = au3 || al3;
-      int D = mainl ? ((mu5 && ml5) ? 2 : (mu5 ? 0 : 1))    // D0B, D0U, D0D
-                    : ((au3 && al3) ? 5 : (au3 ? 3 : 4));   // D1B, D1U, D1D
-      int base = mainl ? (mu5 ? 0 : 5) : (au3 ? 3 : 6);
-      uint32_t b1 = mainl ? B5 : B3, b2 = mainl ? C5 : C3;
-      int t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
-      bool has = mainl || antil;
-      lines |= has;
-      lb_and(LB, has ? 72 + D * 3 + t : 102, m0, m1, m2);
-      // short diagonals (game.cpp:362-391): S0..S3, first found
-      const bool s0 = D3 & 0x04u, s1 = D5 & 0x02u, s2 = D3 & 0x80u, s3 = D5 & 0x10u;
-      D = s0 ? 6 : (s1 ? 7 : (s2 ? 8 : 9));
-      base = s0 ? 2 : (s1 ? 1 : (s2 ? 7 : 4));
-      const bool st5 = !s0 && (s1 || (!s2 && s3));
-      b1 = st5 ? B5 : B3, b2 = st5 ? C5 : C3;
-      t = (int)((b1 >> base) & 1u) + 2 * (int)((b2 >> base) & 1u);
-      has = s0 || s1 || s2 || s3;
-      lines |= has;
-      lb_and(LB, has ? 72 + D * 3 + t : 102, m0, m1, m2);
-    }
-  }
+#include "rules_lines.inc"
+  m[0] = m0, m[1] = m1, m[2] = m2;
+  return lines;
+}
+// legal_moves_t for a position whose basic-rule mask is known already (K1 queues it with the
+// position): only the line rules are left
+template <class LBFn>
+CB_HD bool line_rules_on_basic(const CState &st, uint32_t m[3], LBFn LB) {
+  const uint32_t lo = (uint32_t)st.w0, hi = (uint32_t)(st.w0 >> 32);
+  const uint32_t B = lo & 0xFFFFu, C = lo >> 16, A = hi & 0xFFFFu;
+  const uint32_t T2 = A, T1 = C & ~A, T0 = B & ~(C | A);
+  constexpr bool kBranchless = false;
+  uint32_t m0 = m[0], m1 = m[1], m2 = m[2];
+  bool lines = false;
+#include "rules_lines.inc"
   m[0] = m0, m[1] = m1, m[2] = m2;
   return lines;
 }
@@ -310,13 +242,202 @@ CB_HD int nth_move(const uint32_t m[3], int k) {
   return base;
 }
 
+// ---- K1 fast-path forms (game_step.cuh, k_game_step_pair). Same results as basic_moves /
+// nth_move / do_move above (tests/host_shim checks them against each other on the host and the
+// GPU tests against the oracle); written for the integer-ALU pipe, which bounds K1:
+//   * two positions per thread share every plane operation (16-bit planes of position a in the
+//     low half of a register, of position b in the high half);
+//   * the move decode of do_move and the last three levels of nth_move are table look-ups
+//     (shared memory on the device: the load/store pipe has room, the ALU pipe has none).
+
+// shift by (n & 31) / (n & 63): what SHF.*.W does; lets a table word be used as a shift count
+// without extracting the field first
+CB_HD uint32_t shr_w(uint32_t x, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(x, 0u, n);
+#else
+  return x >> (n & 31u);
+#endif
+}
+// low word of the 64-bit value hi:lo shifted right by (n & 31)
+CB_HD uint32_t shr_w64(uint32_t lo, uint32_t hi, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, n);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (n & 31u));
+#endif
+}
+CB_HD uint32_t shl_w(uint32_t x, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(0u, x, n);
+#else
+  return x << (n & 31u);
+#endif
+}
+
+// Move table (move.cpp:11-42 decode and every constant of do_move, done once on the host): four
+// words per move id, then two more per move id behind them (two arrays, so that the 16-byte and
+// the 8-byte load of a warp spread over the shared-memory banks):
+//   [4 id + 0] from | to << 8   stack moves: the squares; placements: from = to (moving a stack
+//                               onto itself changes nothing)
+//   [4 id + 1] piece-count decrement of the side to move, as seen by player 0: 1 << 8 * piece for
+//              a placement, 0 for a stack move
+//   [4 id + 2], [4 id + 3] AND mask of w0 (low, high word): clears the frozen plane and, for a
+//              stack move, the three piece bits of `from`
+//   [384 + 2 id], [385 + 2 id] OR mask of w0: the frozen bit of `to` and, for a placement, the
+//              piece's plane bit
+constexpr int kMoveLutWords = 6;  // per move id
+constexpr int kMoveLutOr = 96 * 4;  // first word of the OR masks
+inline void build_move_lut(uint32_t out[96 * kMoveLutWords]) {
+  for (int id = 0; id < 96; ++id) {
+    uint32_t from, to, dec;
+    uint64_t andm = 0x0000FFFFFFFFFFFFull, orm;
+    if (id < 48) {
+      const int dir = id / 12, r = id % 12, r3 = (r / 3) * 4 + r % 3;
+      from = (uint32_t)(dir == 0 ? r3 : (dir == 1 ? r : (dir == 2 ? r3 + 1 : r + 4)));
+      to = (uint32_t)(dir == 0 ? r3 + 1 : (dir == 1 ? r + 4 : (dir == 2 ? r3 : r)));
+      dec = 0;
+      andm &= ~(0x0000000100010001ull << from);
+      orm = 1ull << (48 + to);
+    } else {
+      to = (uint32_t)(id & 15), from = to, dec = 1u << (8 * ((id - 48) >> 4));
+      orm = (1ull << (48 + to)) | (1ull << (id - 48));  // id - 48 = 16 * piece + to
+    }
+    uint32_t *e = out + 4 * id, *f = out + kMoveLutOr + 2 * id;
+    e[0] = from | (to << 8), e[1] = dec, e[2] = (uint32_t)andm, e[3] = (uint32_t)(andm >> 32);
+    f[0] = (uint32_t)orm, f[1] = (uint32_t)(orm >> 32);
+  }
+}
+// Byte table of nth_move_lut: entry v * 8 + k = index of the k-th (0-based) set bit of byte v
+inline void build_nth_lut(uint8_t out[256 * 8]) {
+  for (int v = 0; v < 256; ++v) {
+    int k = 0;
+    for (int b = 0; b < 8; ++b)
+      if ((v >> b) & 1) out[v * 8 + k++] = (uint8_t)b;
+    for (; k < 8; ++k) out[v * 8 + k] = 0;
+  }
+}
+
+// do_move by table: `lut` is the table of build_move_lut (16-byte aligned). Legal moves only (a
+// placement's piece count is positive, so the decrement never borrows).
+CB_HD CState do_move_lut(const CState &st, int move, const uint32_t *lut) {
+  const uint32_t *e = lut + 4 * move, *f = lut + kMoveLutOr + 2 * move;
+#if defined(__CUDA_ARCH__)
+  const uint4 q = *reinterpret_cast<const uint4 *>(e);
+  const uint2 r = *reinterpret_cast<const uint2 *>(f);
+  const uint32_t ex = q.x, ey = q.y, and_lo = q.z, and_hi = q.w, or_lo = r.x, or_hi = r.y;
+#else
+  const uint32_t ex = e[0], ey = e[1], and_lo = e[2], and_hi = e[3], or_lo = f[0], or_hi = f[1];
+#endif
+  const uint32_t lo = (uint32_t)st.w0, hi = (uint32_t)(st.w0 >> 32);
+  const uint32_t tsh = ex >> 8;  // `to`; the shifts below use the low five bits of their count
+  // the stack of `from` (base and column bits s, 16 + s of lo; capital bit s of hi) lands on `to`
+  const uint32_t lo2 = (lo & and_lo) | or_lo | shl_w(shr_w(lo, ex) & 0x00010001u, tsh);
+  const uint32_t hi2 = (hi & and_hi) | or_hi | shl_w(shr_w(hi, ex) & 1u, tsh);
+  CState o;
+  o.w0 = (uint64_t)lo2 | ((uint64_t)hi2 << 32);
+  // the mover's counts sit 24 bits up for player 1; one signed multiply-add, then flip to_play
+  const uint32_t tp = (uint32_t)(st.w1 >> 48) & 1u;
+  const int32_t scale = tp ? -(1 << 24) : -1;
+  o.w1 = (uint64_t)((int64_t)st.w1 + (int64_t)(int32_t)ey * (int64_t)scale) ^ (1ull << 48);
+  return o;
+}
+
+// nth_move with the levels below a byte from the table NL(v * 8 + k)
+template <class NLFn>
+CB_HD int nth_move_lut(const uint32_t m[3], int k, NLFn NL) {
+  const int c0 = cb_popc(m[0]), c1 = cb_popc(m[1]);
+  const bool in0 = k < c0, in1 = k < c0 + c1;
+  uint32_t w = in0 ? m[0] : (in1 ? m[1] : m[2]);
+  int base = in0 ? 0 : (in1 ? 32 : 64);
+  k -= in0 ? 0 : (in1 ? c0 : c0 + c1);
+  {
+    const int c = cb_popc(w & 0xFFFFu);
+    const bool up = k >= c;
+    k -= up ? c : 0, w = up ? (w >> 16) : w, base += up ? 16 : 0;
+  }
+  {
+    const int c = cb_popc(w & 0xFFu);
+    const bool up = k >= c;
+    k -= up ? c : 0, w = up ? (w >> 8) : w, base += up ? 8 : 0;
+  }
+  return base + (int)NL((w & 0xFFu) * 8u + (uint32_t)(k & 7));
+}
+
+// basic_moves for two positions at once. Every shifted plane is masked so that no bit crosses
+// from one half into the other: right shifts by 1 / 4 are followed by 0x7777 / 0x0FFF, left
+// shifts by 0xEEEE / 0xFFF0, and the line tests keep only start squares whose three squares lie
+// inside one half (the masks of basic_moves, doubled).
+CB_HD void basic_moves_pair(const CState &a, const CState &b, uint32_t ma[3], uint32_t mb[3], bool &line_a,
+                            bool &line_b) {
+  const uint32_t alo = (uint32_t)a.w0, ahi = (uint32_t)(a.w0 >> 32);
+  const uint32_t blo = (uint32_t)b.w0, bhi = (uint32_t)(b.w0 >> 32);
+#if defined(__CUDA_ARCH__)
+  const uint32_t B = __byte_perm(alo, blo, 0x5410), C = __byte_perm(alo, blo, 0x7632);
+  const uint32_t A = __byte_perm(ahi, bhi, 0x5410), F = __byte_perm(ahi, bhi, 0x7632);
+#else
+  const uint32_t B = (alo & 0xFFFFu) | (blo << 16), C = (alo >> 16) | (blo & 0xFFFF0000u);
+  const uint32_t A = (ahi & 0xFFFFu) | (bhi << 16), F = (ahi >> 16) | (bhi & 0xFFFF0000u);
+#endif
+  const uint32_t E = ~(B | C | A);
+  const uint32_t T2 = A, T1 = C & ~A, T0 = B & ~(C | A);
+  const uint32_t nF = ~F;
+  const uint32_t X1 = C & ~B & nF, X2 = A & ~(B | C) & nF, Y0 = T0 & nF, Y1 = T1 & nF;
+  const uint32_t mr = ((X1 & (Y0 >> 1)) | (X2 & (Y1 >> 1))) & 0x77777777u;
+  const uint32_t md = ((X1 & (Y0 >> 4)) | (X2 & (Y1 >> 4))) & 0x0FFF0FFFu;
+  const uint32_t ml = ((X1 & (Y0 << 1)) | (X2 & (Y1 << 1))) & 0xEEEEEEEEu;
+  const uint32_t mu = ((X1 & (Y0 << 4)) | (X2 & (Y1 << 4))) & 0xFFF0FFF0u;
+  // compress3 with LEFT shifts only (they run on the FMA pipe as multiplications, right shifts
+  // on the ALU pipe): row r moves up by 3 - r, so R3 = compress3(mr) << 3 and, because ml holds
+  // columns 1-3, L4 = compress3(ml >> 1) << 4. The masks drop whatever a shift carries from the
+  // low half into the high half.
+  const uint32_t R3 = ((mr << 3) & 0x00380038u) | ((mr << 2) & 0x01C001C0u) | ((mr << 1) & 0x0E000E00u) |
+                      (mr & 0x70007000u);
+  const uint32_t L4 = ((ml << 3) & 0x00700070u) | ((ml << 2) & 0x03800380u) | ((ml << 1) & 0x1C001C00u) |
+                      (ml & 0xE000E000u);
+  const uint32_t EY0 = E | Y0, EY1 = E | Y1;
+  {
+    const uint32_t alo1 = (uint32_t)a.w1, ahi1 = (uint32_t)(a.w1 >> 32);
+    const uint32_t pcs = shr_w64(alo1, ahi1, ((ahi1 >> 16) & 1u) * 24u);
+    const uint32_t pb = (pcs & 0xFFu) ? (E << 16) : 0u;
+    const uint32_t pc = (pcs & 0xFF00u) ? (EY0 & 0xFFFFu) : 0u;
+    const uint32_t pa = (pcs & 0xFF0000u) ? (EY1 << 16) : 0u;
+    ma[0] = ((R3 >> 3) & 0xFFFu) | ((md << 12) & 0x00FFF000u) | (L4 << 20);
+    ma[1] = ((L4 >> 12) & 0xFu) | (mu & 0xFFF0u) | pb;
+    ma[2] = pc | pa;
+  }
+  {
+    const uint32_t blo1 = (uint32_t)b.w1, bhi1 = (uint32_t)(b.w1 >> 32);
+    const uint32_t pcs = shr_w64(blo1, bhi1, ((bhi1 >> 16) & 1u) * 24u);
+    const uint32_t pb = (pcs & 0xFFu) ? (E & 0xFFFF0000u) : 0u;
+    const uint32_t pc = (pcs & 0xFF00u) ? (EY0 >> 16) : 0u;
+    const uint32_t pa = (pcs & 0xFF0000u) ? (EY1 & 0xFFFF0000u) : 0u;
+    mb[0] = (R3 >> 19) | ((md >> 4) & 0x00FFF000u) | ((L4 << 4) & 0xFF000000u);
+    mb[1] = (L4 >> 28) | ((mu >> 16) & 0xFFF0u) | pb;
+    mb[2] = pc | pa;
+  }
+  // Lines, again with left shifts: P_k marks the squares whose top equals the top k squares
+  // before them (the three top planes are disjoint), P_k & (P_k << k) the END square of three
+  // equal tops with step k. Valid end squares: step 1 columns 2-3, step 4 rows 2-3, step 5
+  // squares 10, 11, 14, 15, step 3 squares 8, 9, 12, 13 -- none of them can be reached by a bit
+  // shifted in from the low half.
+  const uint32_t P1 = (T0 & (T0 << 1)) | (T1 & (T1 << 1)) | (T2 & (T2 << 1));
+  const uint32_t P4 = (T0 & (T0 << 4)) | (T1 & (T1 << 4)) | (T2 & (T2 << 4));
+  const uint32_t P5 = (T0 & (T0 << 5)) | (T1 & (T1 << 5)) | (T2 & (T2 << 5));
+  const uint32_t P3 = (T0 & (T0 << 3)) | (T1 & (T1 << 3)) | (T2 & (T2 << 3));
+  const uint32_t any = (P1 & (P1 << 1) & 0xCCCCCCCCu) | (P4 & (P4 << 4) & 0xFF00FF00u) |
+                       (P5 & (P5 << 5) & 0xCC00CC00u) | (P3 & (P3 << 3) & 0x33003300u);
+  line_a = (any & 0xFFFFu) != 0u;
+  line_b = (any >> 16) != 0u;
+}
+
 // deterministic per-state random word of the game-logic workload (splitmix64 finaliser)
-CB_HD uint32_t step_rnd(uint64_t seed, uint64_t i) {
-  uint64_t z = seed + (i + 1) * 0x9E3779B97F4A7C15ull;
+CB_HD uint32_t step_rnd_mix(uint64_t z) {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
+CB_HD uint32_t step_rnd(uint64_t seed, uint64_t i) { return step_rnd_mix(seed + (i + 1) * 0x9E3779B97F4A7C15ull); }
 
 }  // namespace cb200
 #endif

@@ -49,3 +49,48 @@ extern "C" int64_t shim_basic_moves_check(int64_t n, const uint64_t *states) {
   }
   return bad;
 }
+
+// The paired K1 kernel's forms (basic_moves_pair, nth_move_lut, do_move_lut) against the ones
+// they replace, on the host. Positions i and n-1-i are paired (so both halves see every
+// position); for every position every legal move goes through do_move_lut and every rank k
+// through nth_move_lut. Returns the number of disagreements.
+extern "C" int64_t shim_fast_path_check(int64_t n, const uint64_t *states) {
+  using namespace cb200;
+  static const uint32_t ones[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  auto LB = [](int idx) { return idx < 102 ? kCLineBreakers[idx] : ones; };
+  static uint32_t mv[96 * kMoveLutWords];
+  static uint8_t nth[256 * 8];
+  build_move_lut(mv), build_nth_lut(nth);
+  const uint32_t *ML = mv;
+  auto NL = [](uint32_t i) { return (uint32_t)nth[i]; };
+  int64_t bad = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const CState a{states[2 * i], states[2 * i + 1]};
+    const int64_t j = n - 1 - i;
+    const CState b{states[2 * j], states[2 * j + 1]};
+    uint32_t ra[3], rb[3], pa[3], pb[3];
+    const bool la = basic_moves(a, ra), lb = basic_moves(b, rb);
+    bool qa, qb;
+    basic_moves_pair(a, b, pa, pb, qa, qb);
+    if (qa != la || qb != lb) ++bad;
+    for (int w = 0; w < 3; ++w)
+      if (pa[w] != ra[w] || pb[w] != rb[w]) ++bad;
+    uint32_t m[3];
+    legal_moves_t<false>(a, m, LB);
+    const int nl = cb_popc(m[0]) + cb_popc(m[1]) + cb_popc(m[2]);
+    for (int k = 0; k < nl; ++k) {
+      const int id = nth_move(m, k);
+      if (nth_move_lut(m, k, NL) != id) ++bad;
+      const CState x = do_move(a, id), y = do_move_lut(a, id, ML);
+      if (x.w0 != y.w0 || x.w1 != y.w1) ++bad;
+    }
+    // the basic-rule mask is what the fast path draws from when no line exists; its moves are a
+    // superset of the legal ones, so run them through both do_move forms as well
+    for (int id = 0; id < 96; ++id)
+      if ((ra[id >> 5] >> (id & 31)) & 1u) {
+        const CState x = do_move(a, id), y = do_move_lut(a, id, ML);
+        if (x.w0 != y.w0 || x.w1 != y.w1) ++bad;
+      }
+  }
+  return bad;
+}

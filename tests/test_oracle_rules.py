@@ -150,6 +150,19 @@ def test_basic_moves_is_the_legal_mask_when_no_line_exists(ref):
         assert bad == 0
 
 
+def test_paired_fast_path_forms_equal_the_plain_ones(ref):
+    """k_game_step_pair (game_step.cuh) runs basic_moves_pair / nth_move_lut / do_move_lut; on the
+    host they must agree with basic_moves / nth_move / do_move for every position, every legal move
+    and every rank. 300 k reachable positions + the golden set, paired first-with-last."""
+    from corintho_ai_b200 import planes_from_reference_order
+    lib = _shim()
+    lib.shim_fast_path_check.restype = C.c_int64
+    for states in (GOLD["states"], ref.gen_states(777, 300000)):
+        pl = planes_from_reference_order(states)
+        bad = lib.shim_fast_path_check(C.c_int64(len(pl)), pl.ctypes.data_as(C.c_void_p))
+        assert bad == 0
+
+
 def test_capital_fixups_are_exercised(oracle):
     """Q2: short capital row/column lines occur in the golden set (top==capital, short line)."""
     states = GOLD["states"]
