@@ -164,11 +164,13 @@ struct SmemNthLut {
 // multiply-add
 __device__ __forceinline__ void game_step_finish_lut(int i, const CState &s, const uint32_t m[3], bool lines,
                                                      uint64_t seed_c, uint4 *__restrict__ mask_flags,
-                                                     ulonglong2 *__restrict__ next, const uint32_t *ML, SmemNthLut NL) {
+                                                     ulonglong2 *__restrict__ next, const uint32_t *ML, SmemNthLut NL,
+                                                     const uint32_t *inv32) {
   const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
   const uint32_t rnd = step_rnd_mix(seed_c + (uint64_t)(uint32_t)i * 0x9E3779B97F4A7C15ull);
-  const uint32_t dv = (uint32_t)max(nl, 1);
-  uint32_t rem = rnd - __umulhi(rnd, __ldg(d_inv32 + dv)) * dv;
+  // rnd % nl as in game_step_finish; inv32[0] = 0 leaves a meaningless rem that nl == 0 never uses
+  const uint32_t dv = (uint32_t)nl;
+  uint32_t rem = rnd - __umulhi(rnd, inv32[dv]) * dv;
   rem -= rem >= dv ? dv : 0u;
   CState o = s;
   uint32_t tail = (lines ? (uint32_t)kResultLoss | 4u : (uint32_t)kResultDraw) | (0x7fu << 16);  // no legal move
@@ -190,8 +192,10 @@ __global__ void __launch_bounds__(kStepThreads)
   __shared__ int q_n;
   __shared__ __align__(16) uint32_t s_move[96 * kMoveLutWords];
   __shared__ __align__(16) uint8_t s_nth[256 * 8];
+  __shared__ uint32_t s_inv[128];
   const int tid = threadIdx.x;
   reinterpret_cast<uint2 *>(s_nth)[tid] = reinterpret_cast<const uint2 *>(d_nth_lut)[tid];
+  if (tid < 128) s_inv[tid] = d_inv32[tid];
   if (tid < 96 * kMoveLutWords / 4)
     reinterpret_cast<uint4 *>(s_move)[tid] = reinterpret_cast<const uint4 *>(d_move_lut)[tid];
   if (tid == 0) q_n = 0;
@@ -214,14 +218,14 @@ __global__ void __launch_bounds__(kStepThreads)
       bool la, lb;
       basic_moves_pair(a, b, ma, mb, la, lb);
       if (!la) {
-        game_step_finish_lut(ia, a, ma, false, seed_c, mask_flags, next, ML, NL);
+        game_step_finish_lut(ia, a, ma, false, seed_c, mask_flags, next, ML, NL, s_inv);
       } else {
         const int slot = atomicAdd(&q_n, 1);
         q_state[slot] = va, q_mask[slot] = make_uint4(ma[0], ma[1], ma[2], (uint32_t)ia);
       }
       if (hb) {
         if (!lb) {
-          game_step_finish_lut(ib, b, mb, false, seed_c, mask_flags, next, ML, NL);
+          game_step_finish_lut(ib, b, mb, false, seed_c, mask_flags, next, ML, NL, s_inv);
         } else {
           const int slot = atomicAdd(&q_n, 1);
           q_state[slot] = vb, q_mask[slot] = make_uint4(mb[0], mb[1], mb[2], (uint32_t)ib);
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(kStepThreads)
         const CState s{v.x, v.y};
         uint32_t m[3] = {qm.x, qm.y, qm.z};
         const bool lines = line_rules_on_basic(s, m, DeviceLB());
-        game_step_finish_lut((int)qm.w, s, m, lines, seed_c, mask_flags, next, ML, NL);
+        game_step_finish_lut((int)qm.w, s, m, lines, seed_c, mask_flags, next, ML, NL, s_inv);
         qn -= kStepThreads;
       } while (qn >= kStepThreads);
       __syncthreads();
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kStepThreads)
     const CState s{v.x, v.y};
     uint32_t m[3] = {qm.x, qm.y, qm.z};
     const bool lines = line_rules_on_basic(s, m, DeviceLB());
-    game_step_finish_lut((int)qm.w, s, m, lines, seed_c, mask_flags, next, ML, NL);
+    game_step_finish_lut((int)qm.w, s, m, lines, seed_c, mask_flags, next, ML, NL, s_inv);
   }
 }
 
@@ -293,8 +297,11 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
     k_game_step_split<<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   else {
+    // a few waves of CTAs, each looping over its share (CB200_K1_WAVES: sweep knob, default 4)
+    const char *wv = getenv("CB200_K1_WAVES");
+    const int waves = wv && atoi(wv) > 0 ? atoi(wv) : 4;
     const int64_t want2 = (n + 2 * kStepThreads - 1) / (2 * kStepThreads);
-    const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm() * 4;
+    const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm() * waves;
     k_game_step_pair<<<(int)(want2 < cap2 ? want2 : cap2), kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   }

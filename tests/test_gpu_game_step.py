@@ -35,6 +35,35 @@ def test_game_step_ragged_sizes(oracle, n):
     assert enc.tobytes() == e2.tobytes()
 
 
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 511, 512, 513, 767, 1025, 4097, 20000])
+def test_game_step_ragged_sizes_without_encoding(oracle, n):
+    """The paired kernel (two positions per thread, 512 per trip): every tail shape -- a lone
+    position, a thread whose second position is past the end, a partly filled last trip."""
+    states = GOLD["states"][:n]
+    mf, nx, _ = cb.game_step(cb.planes_from_reference_order(states), 11)
+    masks, flags, nxt, _ = oracle.step_batch(states, step_rnd(11, n), want_enc=False)
+    assert (mf[:, :3] == masks).all() and (mf[:, 3] == flags).all()
+    assert (cb.reference_order_from_planes(nx) == nxt).all()
+
+
+@pytest.mark.parametrize("env", [{}, {"CB200_K1_WAVES": "1"}, {"CB200_K1_SPLIT": "1"}, {"CB200_K1_SELECT_ONLY": "1"}],
+                         ids=["paired", "paired-one-wave", "split", "select-only"])
+def test_game_step_kernel_forms_vs_oracle(oracle, ref, monkeypatch, env):
+    """All three forms of the game-logic kernel (paired = default, split, select-only) and the
+    paired one with a single wave of CTAs (many trips per CTA: the queue wraps through several
+    flushes) against the oracle on 256 k reachable positions."""
+    for k in ("CB200_K1_WAVES", "CB200_K1_SPLIT", "CB200_K1_SELECT_ONLY"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 1 << 18
+    states = ref.gen_states(4711, n)
+    mf, nx, _ = cb.game_step(cb.planes_from_reference_order(states), 5)
+    masks, flags, nxt, _ = oracle.step_batch(states, step_rnd(5, n), want_enc=False, threads=8)
+    assert (mf[:, :3] == masks).all() and (mf[:, 3] == flags).all()
+    assert (cb.reference_order_from_planes(nx) == nxt).all()
+
+
 def test_game_step_1m_states_vs_oracle(oracle, ref):
     """BASELINE.json configs[1] size: 1M reachable states, bit-exact against the oracle."""
     n = 1 << 20
