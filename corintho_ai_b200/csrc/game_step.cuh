@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kStepThreads)
   }
 }
 
-// K1, paired form (the default without encoding). The split idea above, with the integer-ALU
+// K1, paired form with one queue per CTA (CB200_K1_PAIR=2). The split idea above, with the integer-ALU
 // work per position cut further (the ALU pipe is what bounds K1):
 //   * a thread takes TWO positions per trip (i and i + 256: both loads and all stores stay
 //     coalesced) and runs the basic-rule mask and the "any line?" test on both at once, one
@@ -261,15 +261,123 @@ __global__ void __launch_bounds__(kStepThreads)
   }
 }
 
-// resident CTAs of the paired kernel per SM (register- and shared-memory-limited), asked once
-inline int k1_pair_ctas_per_sm() {
-  static int ctas = 0;
-  if (ctas == 0) {
-    int v = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_game_step_pair, kStepThreads, 0) != cudaSuccess || v < 1) v = 4;
-    ctas = v;
+// K1, paired form with one queue per WARP (the default). k_game_step_pair above synchronises the
+// CTA twice per trip: its ncu capture shows the warps of a CTA waiting together for their loads
+// right after the barrier (long-scoreboard 7.2, barrier 2.5 stall cycles per issue, issue slots
+// 66 % busy). Here every warp owns a queue of 96 entries and a warp-uniform count in a register:
+//   * appending is two ballots and predicated stores (no atomics, no branch: the warp is still
+//     converged right after basic_moves_pair);
+//   * a warp flushes 32 queued positions whenever it has them -- __syncwarp only, no __syncthreads
+//     inside the loop, so the 56 warps of an SM drift apart and cover each other's load latency;
+//   * kPrefetch: the next trip's two positions are requested before the current ones are processed.
+template <bool kPrefetch, int kMinBlocks>
+__global__ void __launch_bounds__(kStepThreads, kMinBlocks)
+    k_game_step_pairw(int64_t n, const ulonglong2 *__restrict__ states, uint64_t seed,
+                      uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next) {
+  constexpr int kWarps = kStepThreads / 32;
+  constexpr int kWQ = 96;  // fewer than 32 entries before a trip, at most 64 more
+  __shared__ ulonglong2 q_state[kWarps * kWQ];
+  __shared__ uint4 q_mask[kWarps * kWQ];  // basic-rule mask (x, y, z) and the position's index (w)
+  __shared__ __align__(16) uint32_t s_move[96 * kMoveLutWords];
+  __shared__ __align__(16) uint8_t s_nth[256 * 8];
+  __shared__ uint32_t s_inv[128];
+  const int tid = threadIdx.x;
+  reinterpret_cast<uint2 *>(s_nth)[tid] = reinterpret_cast<const uint2 *>(d_nth_lut)[tid];
+  if (tid < 128) s_inv[tid] = d_inv32[tid];
+  if (tid < 96 * kMoveLutWords / 4)
+    reinterpret_cast<uint4 *>(s_move)[tid] = reinterpret_cast<const uint4 *>(d_move_lut)[tid];
+  __syncthreads();
+  const uint32_t *ML = s_move;
+  const SmemNthLut NL{s_nth};
+  const int lane = tid & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  ulonglong2 *qs = q_state + (tid >> 5) * kWQ;
+  uint4 *qm = q_mask + (tid >> 5) * kWQ;
+  int qn = 0;  // entries in this warp's queue (warp-uniform)
+  const uint64_t seed_c = seed + 0x9E3779B97F4A7C15ull;
+  constexpr int kTrip = 2 * kStepThreads;
+  const unsigned un = (unsigned)n;
+  const unsigned stride = gridDim.x * kTrip;  // unsigned: the last `+= stride` cannot wrap
+  const unsigned n_round = (unsigned)(((n + kTrip - 1) / kTrip) * kTrip);  // every lane of a warp runs every trip
+  const ulonglong2 none = make_ulonglong2(0ull, 0ull);  // empty board, no pieces: no move, no line
+  unsigned base = blockIdx.x * kTrip;
+  ulonglong2 pa = none, pb = none;
+  if (kPrefetch && base < n_round) {
+    if (base + tid < un) pa = __ldg(states + base + tid);
+    if (base + tid + kStepThreads < un) pb = __ldg(states + base + tid + kStepThreads);
   }
-  return ctas;
+  for (; base < n_round; base += stride) {
+    const unsigned ua = base + tid, ub = ua + kStepThreads;
+    const bool ha = ua < un, hb = ub < un;
+    ulonglong2 va, vb;
+    if (kPrefetch) {
+      va = pa, vb = pb;
+      const unsigned na = ua + stride, nb = ub + stride;  // past n_round means past n
+      pa = na < un ? __ldg(states + na) : none;
+      pb = nb < un ? __ldg(states + nb) : none;
+    } else {
+      va = ha ? __ldg(states + ua) : none;
+      vb = hb ? __ldg(states + ub) : none;
+    }
+    const CState a{va.x, va.y}, b{vb.x, vb.y};
+    uint32_t ma[3], mb[3];
+    bool la, lb;
+    basic_moves_pair(a, b, ma, mb, la, lb);
+    const bool qa = ha && la, qb = hb && lb;
+    const unsigned ba = __ballot_sync(kFull, qa), bb = __ballot_sync(kFull, qb);
+    if (qa) {
+      const int slot = qn + __popc(ba & lt);
+      qs[slot] = va, qm[slot] = make_uint4(ma[0], ma[1], ma[2], ua);
+    }
+    qn += __popc(ba);
+    if (qb) {
+      const int slot = qn + __popc(bb & lt);
+      qs[slot] = vb, qm[slot] = make_uint4(mb[0], mb[1], mb[2], ub);
+    }
+    qn += __popc(bb);
+    if (ha && !la) game_step_finish_lut((int)ua, a, ma, false, seed_c, mask_flags, next, ML, NL, s_inv);
+    if (hb && !lb) game_step_finish_lut((int)ub, b, mb, false, seed_c, mask_flags, next, ML, NL, s_inv);
+    __syncwarp();  // the appended entries are visible to the whole warp
+    while (qn >= 32) {  // warp-uniform
+      qn -= 32;
+      const ulonglong2 v = qs[qn + lane];
+      const uint4 w = qm[qn + lane];
+      const CState s{v.x, v.y};
+      uint32_t m[3] = {w.x, w.y, w.z};
+      const bool lines = line_rules_on_basic(s, m, DeviceLB());
+      game_step_finish_lut((int)w.w, s, m, lines, seed_c, mask_flags, next, ML, NL, s_inv);
+    }
+    __syncwarp();  // flush reads done before the next trip's appends reuse the slots
+  }
+  if (lane < qn) {  // drain: fewer than 32 entries are left
+    const ulonglong2 v = qs[lane];
+    const uint4 w = qm[lane];
+    const CState s{v.x, v.y};
+    uint32_t m[3] = {w.x, w.y, w.z};
+    const bool lines = line_rules_on_basic(s, m, DeviceLB());
+    game_step_finish_lut((int)w.w, s, m, lines, seed_c, mask_flags, next, ML, NL, s_inv);
+  }
+}
+
+// resident CTAs of a paired kernel per SM (register- and shared-memory-limited), asked once per form
+typedef void (*K1PairFn)(int64_t, const ulonglong2 *, uint64_t, uint4 *, ulonglong2 *);
+inline K1PairFn k1_pair_kernel(int form) {
+  switch (form) {
+    case 1: return k_game_step_pairw<true, 1>;
+    case 2: return k_game_step_pair;
+    case 3: return k_game_step_pairw<false, 7>;
+    case 4: return k_game_step_pairw<true, 6>;
+    default: return k_game_step_pairw<false, 1>;
+  }
+}
+inline int k1_pair_ctas_per_sm(int form) {
+  static int ctas[5] = {0, 0, 0, 0, 0};
+  if (ctas[form] == 0) {
+    int v = 0;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k1_pair_kernel(form), kStepThreads, 0);
+    ctas[form] = e == cudaSuccess && v >= 1 ? v : 4;
+  }
+  return ctas[form];
 }
 
 inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void *d_mask_flags,
@@ -297,12 +405,16 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
     k_game_step_split<<<grid, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   else {
-    // a few waves of CTAs, each looping over its share (CB200_K1_WAVES: sweep knob, default 4)
-    const char *wv = getenv("CB200_K1_WAVES");
-    const int waves = wv && atoi(wv) > 0 ? atoi(wv) : 4;
+    // a few waves of CTAs, each looping over its share (CB200_K1_WAVES: sweep knob, default 8).
+    // CB200_K1_PAIR: 0 = queue per warp (default), 1 = the same with prefetch, 2 = queue per CTA,
+    // 3 / 4 = forms 0 / 1 compiled for 7 / 6 resident CTAs per SM
+    const char *wv = getenv("CB200_K1_WAVES"), *fv = getenv("CB200_K1_PAIR");
+    const int waves = wv && atoi(wv) > 0 ? atoi(wv) : 8;
+    const int form = fv && atoi(fv) >= 0 && atoi(fv) <= 4 ? atoi(fv) : 0;
     const int64_t want2 = (n + 2 * kStepThreads - 1) / (2 * kStepThreads);
-    const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm() * waves;
-    k_game_step_pair<<<(int)(want2 < cap2 ? want2 : cap2), kStepThreads, 0, cur_stream()>>>(
+    const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm(form) * waves;
+    const int grid2 = (int)(want2 < cap2 ? want2 : cap2);
+    k1_pair_kernel(form)<<<grid2, kStepThreads, 0, cur_stream()>>>(
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   }
   CB_LAUNCHED();

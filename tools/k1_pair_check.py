@@ -1,5 +1,5 @@
-"""K1 at the bench size (64 Mi device-resident reachable positions): the paired kernel (default)
-against the split and the select-only kernels -- outputs compared on the device for every
+"""K1 at the bench size (64 Mi device-resident reachable positions): the paired kernel (default;
+CB200_K1_PAIR selects its other forms) against the split and the select-only kernels -- outputs compared on the device for every
 position, then every variant timed like bench.measure_game_logic (10 launches, CUDA events)."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,7 +22,7 @@ def step(src, seed, m, dst):
 
 
 def variant(env):
-    for k in ("CB200_K1_SPLIT", "CB200_K1_SELECT_ONLY", "CB200_K1_WAVES"):
+    for k in ("CB200_K1_SPLIT", "CB200_K1_SELECT_ONLY", "CB200_K1_WAVES", "CB200_K1_PAIR"):
         os.environ.pop(k, None)
     os.environ.update(env)
 
@@ -38,7 +38,8 @@ same = True
 for r in range(3):
     variant({})
     step(a, 500 + r, mf, b)
-    for env in ({"CB200_K1_SPLIT": "1"}, {"CB200_K1_SELECT_ONLY": "1"}, {"CB200_K1_WAVES": "1"}):
+    for env in ({"CB200_K1_SPLIT": "1"}, {"CB200_K1_SELECT_ONLY": "1"}, {"CB200_K1_WAVES": "1"}, {"CB200_K1_PAIR": "1"},
+                {"CB200_K1_PAIR": "2"}, {"CB200_K1_PAIR": "3"}, {"CB200_K1_PAIR": "4"}):
         variant(env)
         step(a, 500 + r, mf2, b2)
         torch.cuda.synchronize()
@@ -48,13 +49,16 @@ for r in range(3):
             bad = int(((mf != mf2).any(1) | (b != b2).any(1)).sum())
             out.setdefault("mismatch", []).append({"round": r, "env": env, "positions": bad})
     a, b = b, a
-out["paired_equals_split_and_select_only"] = same
+out["every_form_equals_the_default"] = same
 del b2, mf2
 variant({})
 timings = {}
-for name, env in (("pair", {}), ("pair_waves1", {"CB200_K1_WAVES": "1"}), ("pair_waves2", {"CB200_K1_WAVES": "2"}),
-                  ("pair_waves8", {"CB200_K1_WAVES": "8"}), ("pair_waves32", {"CB200_K1_WAVES": "32"}),
-                  ("split", {"CB200_K1_SPLIT": "1"}), ("select_only", {"CB200_K1_SELECT_ONLY": "1"}), ("pair_again", {})):
+forms = [("pair", {})]
+for f in ("0", "1", "2", "3", "4"):
+    for w in ("2", "4", "8", "32"):
+        forms.append(("pair_form%s_waves%s" % (f, w), {"CB200_K1_PAIR": f, "CB200_K1_WAVES": w}))
+forms += [("split", {"CB200_K1_SPLIT": "1"}), ("select_only", {"CB200_K1_SELECT_ONLY": "1"}), ("pair_again", {})]
+for name, env in forms:
     variant(env)
     step(a, 7, mf, b)
     torch.cuda.synchronize()
