@@ -349,9 +349,21 @@ __global__ void __launch_bounds__(kStepThreads, kMinBlocks)
     }
     __syncwarp();  // flush reads done before the next trip's appends reuse the slots
   }
-  if (lane < qn) {  // drain: fewer than 32 entries are left
-    const ulonglong2 v = qs[lane];
-    const uint4 w = qm[lane];
+  // drain: every warp is left with fewer than 32 entries; pooled over the CTA (fewer than 256) so
+  // that full warps process them instead of eight half-empty ones
+  __shared__ int s_left[kWarps];
+  if (lane == 0) s_left[tid >> 5] = qn;
+  __syncthreads();
+  int total = 0, src = -1;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) {
+    const int c = s_left[w];
+    if (src < 0 && tid < total + c) src = w * kWQ + (tid - total);
+    total += c;
+  }
+  if (src >= 0) {
+    const ulonglong2 v = q_state[src];
+    const uint4 w = q_mask[src];
     const CState s{v.x, v.y};
     uint32_t m[3] = {w.x, w.y, w.z};
     const bool lines = line_rules_on_basic(s, m, DeviceLB());

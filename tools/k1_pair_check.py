@@ -55,7 +55,7 @@ variant({})
 timings = {}
 forms = [("pair", {})]
 for f in ("0", "1", "2", "3", "4"):
-    for w in ("2", "4", "8", "32"):
+    for w in ("4", "8", "16"):
         forms.append(("pair_form%s_waves%s" % (f, w), {"CB200_K1_PAIR": f, "CB200_K1_WAVES": w}))
 forms += [("split", {"CB200_K1_SPLIT": "1"}), ("select_only", {"CB200_K1_SELECT_ONLY": "1"}), ("pair_again", {})]
 for name, env in forms:
