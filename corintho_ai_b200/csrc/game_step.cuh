@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(kStepThreads)
 //     (nth_move_lut / do_move_lut, 4.3 KB per CTA);
 //   * terminal positions (no legal move) skip the move instead of computing and discarding it.
 // Positions with a line are queued as in the split kernel and processed 256 at a time.
+struct SmemLB {
+  const uint32_t *p;
+  __device__ __forceinline__ const uint32_t *operator()(int idx) const { return p + 4 * idx; }
+};
 struct SmemNthLut {
   const uint8_t *p;
   __device__ __forceinline__ uint32_t operator()(uint32_t i) const { return p[i]; }
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(kStepThreads)
   }
 }
 
-// K1, paired form with one queue per WARP (the default). k_game_step_pair above synchronises the
+// K1, paired form with one queue per WARP (the default, with kPrefetch). k_game_step_pair above synchronises the
 // CTA twice per trip: its ncu capture shows the warps of a CTA waiting together for their loads
 // right after the barrier (long-scoreboard 7.2, barrier 2.5 stall cycles per issue, issue slots
 // 66 % busy). Here every warp owns a queue of 96 entries and a warp-uniform count in a register:
@@ -281,7 +285,9 @@ __global__ void __launch_bounds__(kStepThreads, kMinBlocks)
   __shared__ __align__(16) uint32_t s_move[96 * kMoveLutWords];
   __shared__ __align__(16) uint8_t s_nth[256 * 8];
   __shared__ uint32_t s_inv[128];
+  __shared__ __align__(16) uint32_t s_lb[103 * 4];  // line-breaker masks (1.6 KB): the flush reads four per position
   const int tid = threadIdx.x;
+  if (tid < 103) reinterpret_cast<uint4 *>(s_lb)[tid] = reinterpret_cast<const uint4 *>(d_line_breakers)[tid];
   reinterpret_cast<uint2 *>(s_nth)[tid] = reinterpret_cast<const uint2 *>(d_nth_lut)[tid];
   if (tid < 128) s_inv[tid] = d_inv32[tid];
   if (tid < 96 * kMoveLutWords / 4)
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(kStepThreads, kMinBlocks)
       const uint4 w = qm[qn + lane];
       const CState s{v.x, v.y};
       uint32_t m[3] = {w.x, w.y, w.z};
-      const bool lines = line_rules_on_basic(s, m, DeviceLB());
+      const bool lines = line_rules_on_basic(s, m, SmemLB{s_lb});
       game_step_finish_lut((int)w.w, s, m, lines, seed_c, mask_flags, next, ML, NL, s_inv);
     }
     __syncwarp();  // flush reads done before the next trip's appends reuse the slots
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(kStepThreads, kMinBlocks)
     const uint4 w = q_mask[src];
     const CState s{v.x, v.y};
     uint32_t m[3] = {w.x, w.y, w.z};
-    const bool lines = line_rules_on_basic(s, m, DeviceLB());
+    const bool lines = line_rules_on_basic(s, m, SmemLB{s_lb});
     game_step_finish_lut((int)w.w, s, m, lines, seed_c, mask_flags, next, ML, NL, s_inv);
   }
 }
@@ -418,11 +424,11 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   else {
     // a few waves of CTAs, each looping over its share (CB200_K1_WAVES: sweep knob, default 8).
-    // CB200_K1_PAIR: 0 = queue per warp (default), 1 = the same with prefetch, 2 = queue per CTA,
+    // CB200_K1_PAIR: 0 = queue per warp, 1 = the same with prefetch (default), 2 = queue per CTA,
     // 3 / 4 = forms 0 / 1 compiled for 7 / 6 resident CTAs per SM
     const char *wv = getenv("CB200_K1_WAVES"), *fv = getenv("CB200_K1_PAIR");
     const int waves = wv && atoi(wv) > 0 ? atoi(wv) : 8;
-    const int form = fv && atoi(fv) >= 0 && atoi(fv) <= 4 ? atoi(fv) : 0;
+    const int form = fv && atoi(fv) >= 0 && atoi(fv) <= 4 ? atoi(fv) : 1;
     const int64_t want2 = (n + 2 * kStepThreads - 1) / (2 * kStepThreads);
     const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm(form) * waves;
     const int grid2 = (int)(want2 < cap2 ? want2 : cap2);

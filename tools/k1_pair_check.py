@@ -54,8 +54,8 @@ del b2, mf2
 variant({})
 timings = {}
 forms = [("pair", {})]
-for f in ("0", "1", "2", "3", "4"):
-    for w in ("4", "8", "16"):
+for f, ws in (("0", ("8",)), ("1", ("4", "8", "16")), ("2", ("8",)), ("3", ("8",)), ("4", ("8",))):
+    for w in ws:
         forms.append(("pair_form%s_waves%s" % (f, w), {"CB200_K1_PAIR": f, "CB200_K1_WAVES": w}))
 forms += [("split", {"CB200_K1_SPLIT": "1"}), ("select_only", {"CB200_K1_SELECT_ONLY": "1"}), ("pair_again", {})]
 for name, env in forms:
