@@ -265,7 +265,28 @@ __global__ void __launch_bounds__(kStepThreads)
   }
 }
 
-// K1, paired form with one queue per WARP (the default, with kPrefetch). k_game_step_pair above synchronises the
+// Both positions of a thread finished together, without a branch: the two dependent chains
+// (popcount -> rank -> nth_move -> table -> do_move) are independent of each other, so the
+// compiler can interleave them; lanes whose position is queued (or absent) compute a discarded
+// result in the slots they would idle in anyway. Only the stores are predicated. A position
+// without a legal move draws a meaningless but in-range move id (nth_move_lut never leaves the
+// tables) and keeps its state by a select.
+__device__ __forceinline__ void game_step_finish_one_sel(const CState &s, const uint32_t m[3], uint32_t idx,
+                                                         uint64_t seed_c, const uint32_t *ML, SmemNthLut NL,
+                                                         const uint32_t *inv32, uint32_t &tail, CState &o) {
+  const int nl = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
+  const uint32_t rnd = step_rnd_mix(seed_c + (uint64_t)idx * 0x9E3779B97F4A7C15ull);
+  const uint32_t dv = (uint32_t)nl;
+  uint32_t rem = rnd - __umulhi(rnd, inv32[dv]) * dv;
+  rem -= rem >= dv ? dv : 0u;
+  const int pick = nth_move_lut(m, (int)rem, NL);
+  const CState moved = do_move_lut(s, pick, ML);
+  const bool any = nl > 0;
+  o.w0 = any ? moved.w0 : s.w0, o.w1 = any ? moved.w1 : s.w1;
+  tail = any ? (((uint32_t)nl << 8) | ((uint32_t)pick << 16)) : ((uint32_t)kResultDraw | (0x7fu << 16));
+}
+
+// K1, paired form with one queue per WARP (the default, with kPrefetch and kJoint). k_game_step_pair above synchronises the
 // CTA twice per trip: its ncu capture shows the warps of a CTA waiting together for their loads
 // right after the barrier (long-scoreboard 7.2, barrier 2.5 stall cycles per issue, issue slots
 // 66 % busy). Here every warp owns a queue of 96 entries and a warp-uniform count in a register:
@@ -274,7 +295,7 @@ __global__ void __launch_bounds__(kStepThreads)
 //   * a warp flushes 32 queued positions whenever it has them -- __syncwarp only, no __syncthreads
 //     inside the loop, so the 56 warps of an SM drift apart and cover each other's load latency;
 //   * kPrefetch: the next trip's two positions are requested before the current ones are processed.
-template <bool kPrefetch, int kMinBlocks>
+template <bool kPrefetch, int kMinBlocks, bool kJoint = false>
 __global__ void __launch_bounds__(kStepThreads, kMinBlocks)
     k_game_step_pairw(int64_t n, const ulonglong2 *__restrict__ states, uint64_t seed,
                       uint4 *__restrict__ mask_flags, ulonglong2 *__restrict__ next) {
@@ -341,8 +362,23 @@ __global__ void __launch_bounds__(kStepThreads, kMinBlocks)
       qs[slot] = vb, qm[slot] = make_uint4(mb[0], mb[1], mb[2], ub);
     }
     qn += __popc(bb);
-    if (ha && !la) game_step_finish_lut((int)ua, a, ma, false, seed_c, mask_flags, next, ML, NL, s_inv);
-    if (hb && !lb) game_step_finish_lut((int)ub, b, mb, false, seed_c, mask_flags, next, ML, NL, s_inv);
+    if (kJoint) {
+      uint32_t ta, tb;
+      CState oa, ob;
+      game_step_finish_one_sel(a, ma, ua, seed_c, ML, NL, s_inv, ta, oa);
+      game_step_finish_one_sel(b, mb, ub, seed_c, ML, NL, s_inv, tb, ob);
+      if (ha && !la) {
+        mask_flags[ua] = make_uint4(ma[0], ma[1], ma[2], ta);
+        next[ua] = make_ulonglong2(oa.w0, oa.w1);
+      }
+      if (hb && !lb) {
+        mask_flags[ub] = make_uint4(mb[0], mb[1], mb[2], tb);
+        next[ub] = make_ulonglong2(ob.w0, ob.w1);
+      }
+    } else {
+      if (ha && !la) game_step_finish_lut((int)ua, a, ma, false, seed_c, mask_flags, next, ML, NL, s_inv);
+      if (hb && !lb) game_step_finish_lut((int)ub, b, mb, false, seed_c, mask_flags, next, ML, NL, s_inv);
+    }
     __syncwarp();  // the appended entries are visible to the whole warp
     while (qn >= 32) {  // warp-uniform
       qn -= 32;
@@ -385,11 +421,13 @@ inline K1PairFn k1_pair_kernel(int form) {
     case 2: return k_game_step_pair;
     case 3: return k_game_step_pairw<false, 7>;
     case 4: return k_game_step_pairw<true, 6>;
+    case 5: return k_game_step_pairw<false, 1, true>;
+    case 6: return k_game_step_pairw<true, 1, true>;
     default: return k_game_step_pairw<false, 1>;
   }
 }
 inline int k1_pair_ctas_per_sm(int form) {
-  static int ctas[5] = {0, 0, 0, 0, 0};
+  static int ctas[7] = {0, 0, 0, 0, 0, 0, 0};
   if (ctas[form] == 0) {
     int v = 0;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k1_pair_kernel(form), kStepThreads, 0);
@@ -424,11 +462,12 @@ inline int launch_game_step(int64_t n, const void *d_states, uint64_t seed, void
         n, (const ulonglong2 *)d_states, seed, (uint4 *)d_mask_flags, (ulonglong2 *)d_next);
   else {
     // a few waves of CTAs, each looping over its share (CB200_K1_WAVES: sweep knob, default 8).
-    // CB200_K1_PAIR: 0 = queue per warp, 1 = the same with prefetch (default), 2 = queue per CTA,
-    // 3 / 4 = forms 0 / 1 compiled for 7 / 6 resident CTAs per SM
+    // CB200_K1_PAIR: 0 = queue per warp, 1 = the same with prefetch, 2 = queue per CTA,
+    // 3 / 4 = forms 0 / 1 compiled for 7 / 6 resident CTAs per SM, 5 / 6 = forms 0 / 1 with both positions of a
+    // thread finished together, branch-free (6 is the default)
     const char *wv = getenv("CB200_K1_WAVES"), *fv = getenv("CB200_K1_PAIR");
     const int waves = wv && atoi(wv) > 0 ? atoi(wv) : 8;
-    const int form = fv && atoi(fv) >= 0 && atoi(fv) <= 4 ? atoi(fv) : 1;
+    const int form = fv && atoi(fv) >= 0 && atoi(fv) <= 6 ? atoi(fv) : 6;
     const int64_t want2 = (n + 2 * kStepThreads - 1) / (2 * kStepThreads);
     const int64_t cap2 = (int64_t)sms * k1_pair_ctas_per_sm(form) * waves;
     const int grid2 = (int)(want2 < cap2 ? want2 : cap2);

@@ -46,14 +46,16 @@ def test_game_step_ragged_sizes_without_encoding(oracle, n):
     assert (cb.reference_order_from_planes(nx) == nxt).all()
 
 
-@pytest.mark.parametrize("env", [{}, {"CB200_K1_WAVES": "1"}, {"CB200_K1_PAIR": "1"}, {"CB200_K1_PAIR": "2"},
-                                 {"CB200_K1_PAIR": "3"}, {"CB200_K1_PAIR": "4"}, {"CB200_K1_SPLIT": "1"},
-                                 {"CB200_K1_SELECT_ONLY": "1"}],
-                         ids=["paired", "paired-one-wave", "paired-prefetch", "paired-cta-queue", "paired-7-ctas",
-                              "paired-prefetch-6-ctas", "split", "select-only"])
+@pytest.mark.parametrize("env", [{}, {"CB200_K1_WAVES": "1"}, {"CB200_K1_PAIR": "0"}, {"CB200_K1_PAIR": "1"},
+                                 {"CB200_K1_PAIR": "2"}, {"CB200_K1_PAIR": "3"}, {"CB200_K1_PAIR": "4"},
+                                 {"CB200_K1_PAIR": "5"}, {"CB200_K1_SPLIT": "1"}, {"CB200_K1_SELECT_ONLY": "1"}],
+                         ids=["paired", "paired-one-wave", "paired-branchy-finish", "paired-branchy-finish-prefetch",
+                              "paired-cta-queue", "paired-7-ctas", "paired-prefetch-6-ctas", "paired-joint-finish-no-prefetch",
+                              "split", "select-only"])
 def test_game_step_kernel_forms_vs_oracle(oracle, ref, monkeypatch, env):
-    """Every form of the game-logic kernel (paired with a queue per warp = default, with prefetch,
-    with a queue per CTA, register-capped builds; split; select-only) and the default with a single
+    """Every form of the game-logic kernel (paired with a queue per warp, prefetch and the joint
+    branch-free finish = default; without either; with a queue per CTA; register-capped builds;
+    split; select-only) and the default with a single
     wave of CTAs (many trips per CTA: the queues wrap through several flushes) against the oracle
     on 256 k reachable positions."""
     for k in ("CB200_K1_WAVES", "CB200_K1_PAIR", "CB200_K1_SPLIT", "CB200_K1_SELECT_ONLY"):

@@ -39,7 +39,8 @@ for r in range(3):
     variant({})
     step(a, 500 + r, mf, b)
     for env in ({"CB200_K1_SPLIT": "1"}, {"CB200_K1_SELECT_ONLY": "1"}, {"CB200_K1_WAVES": "1"}, {"CB200_K1_PAIR": "1"},
-                {"CB200_K1_PAIR": "2"}, {"CB200_K1_PAIR": "3"}, {"CB200_K1_PAIR": "4"}):
+                {"CB200_K1_PAIR": "2"}, {"CB200_K1_PAIR": "3"}, {"CB200_K1_PAIR": "4"}, {"CB200_K1_PAIR": "5"},
+                {"CB200_K1_PAIR": "6"}, {"CB200_K1_PAIR": "0"}):
         variant(env)
         step(a, 500 + r, mf2, b2)
         torch.cuda.synchronize()
@@ -54,7 +55,7 @@ del b2, mf2
 variant({})
 timings = {}
 forms = [("pair", {})]
-for f, ws in (("0", ("8",)), ("1", ("4", "8", "16")), ("2", ("8",)), ("3", ("8",)), ("4", ("8",))):
+for f, ws in (("0", ("8",)), ("1", ("8",)), ("5", ("8",)), ("6", ("4", "8", "16")), ("2", ("8",)), ("4", ("8",))):
     for w in ws:
         forms.append(("pair_form%s_waves%s" % (f, w), {"CB200_K1_PAIR": f, "CB200_K1_WAVES": w}))
 forms += [("split", {"CB200_K1_SPLIT": "1"}), ("select_only", {"CB200_K1_SELECT_ONLY": "1"}), ("pair_again", {})]
