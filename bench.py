@@ -238,8 +238,8 @@ def measure_game_logic(torch, cb, dev, n=1 << 26, reps=10):
     return {"states_per_sec": n / (ms * 1e-3), "states_per_launch": n, "ms_per_launch": ms,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": gbs / pk["hbm_gbs"], "algorithmic_bytes_per_state": 46, "moved_bytes_per_state": 48,
-                         "note": "paired kernel (two positions per thread, a queue per warp, table-driven nth_move / do_move): "
-                                 "10.7 warp instructions per position, ALU pipe 76 %, issue slots 71 %, DRAM 45 % busy in the ncu capture "
+                         "note": "paired kernel (two positions per thread finished together branch-free, a queue per warp, table-driven nth_move / do_move): "
+                                 "10.7 warp instructions per position, ALU pipe 76 %, issue slots 71 %, DRAM 45 % busy in the ncu capture (of the form before the joint finish) "
                                  "profiles/r02_ncu_k_game_step_pair.txt -- no single limiter left; forms and history in "
                                  "profiles/r02_k1_paired_variants.txt"}}
 
